@@ -1,0 +1,211 @@
+/* include/svo_b200.h -- C ABI of libsvo_b200.so, the B200 (sm_100a) implementation of the rpg_svo
+ * direct-tracking hot path.  Plain pointers and sizes only; no torch / C++ types cross this line.
+ *
+ * Each entry point replaces one reference interface (paths relative to the rpg_svo tree):
+ *   svo_b200_sparse_img_align*      <- svo::SparseImgAlign::run               svo/include/svo/sparse_img_align.h:43-57
+ *                                      (+ getFisherInformation via H_out)     svo/src/sparse_img_align.cpp:43-82
+ *   svo_b200_sparse_residuals       <- SparseImgAlign::computeResiduals       svo/src/sparse_img_align.cpp:147-243
+ *   svo_b200_align2d_batch/_1d      <- feature_alignment::align2D / align1D   svo/include/svo/feature_alignment.h:29-44
+ *   svo_b200_find_match_direct      <- Matcher::findMatchDirect               svo/include/svo/matcher.h:109-112
+ *   svo_b200_pose_optimize          <- pose_optimizer::optimizeGaussNewton    svo/include/svo/pose_optimizer.h:37-45
+ *   svo_b200_depth_filter_update    <- DepthFilter::updateSeeds               svo/include/svo/depth_filter.h:155
+ *                                      (Matcher::findEpipolarMatchDirect, updateSeed, computeTau inside)
+ *   svo_b200_frame_*                <- svo::Frame image pyramid               svo/include/svo/frame.h:52, svo/src/frame.cpp:156-165
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative SVO_B200_E* code on argument / CUDA errors;
+ *     svo_b200_last_error(ctx) gives the text.  Algorithmic "failures" (no features, GN rollback,
+ *     align not converged, seed without match) are reported in-band exactly like the reference and
+ *     are NOT errors.  Nothing throws across this boundary.
+ *   - SE3 = row-major 3x4 [R|t] doubles (12 values).  Images are 8-bit, row pitch == width.
+ *   - host pointers are caller-owned and only read/written during the call; device memory is owned
+ *     by the context.  One context = one GPU + one CUDA stream; use one context per calling host
+ *     thread (tracking / mapping), as the reference's two threads do.
+ *   - there is NO CPU fallback: if no CUDA device is usable, svo_b200_create fails.
+ */
+#ifndef SVO_B200_H_
+#define SVO_B200_H_
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVO_B200_MAX_LEVELS 8
+
+#define SVO_B200_OK 0
+#define SVO_B200_EINVAL (-1)   /* bad argument */
+#define SVO_B200_ECUDA (-2)    /* CUDA runtime error */
+#define SVO_B200_ENOMEM (-3)   /* allocation failure */
+#define SVO_B200_ELIMIT (-4)   /* size beyond what the kernels support */
+
+typedef struct svo_b200_ctx svo_b200_ctx;
+typedef struct svo_b200_frame svo_b200_frame;
+
+/* [EXT] vk::PinholeCamera without distortion (the only model the hot path's synthetic configs use) */
+typedef struct {
+  double fx, fy, cx, cy;
+  int width, height;
+} svo_b200_camera;
+
+/* ------------------------------------------------------------------ context ------------- */
+int svo_b200_create(svo_b200_ctx** ctx_out, int device);
+void svo_b200_destroy(svo_b200_ctx* ctx);
+const char* svo_b200_last_error(const svo_b200_ctx* ctx);
+/* cudaStream_t of the context (for CUDA-event timing by the caller) */
+void* svo_b200_stream(svo_b200_ctx* ctx);
+int svo_b200_synchronize(svo_b200_ctx* ctx);
+/* number of kernels this context has launched since creation */
+uint64_t svo_b200_launch_count(const svo_b200_ctx* ctx);
+const char* svo_b200_version(void);
+
+/* ------------------------------------------------------------------ frames -------------- */
+/* A frame = an image pyramid resident in HBM (svo::Frame::img_pyr_).  Level l has size
+ * (width >> l, height >> l) (integer division, svo/src/frame.cpp:162). */
+int svo_b200_frame_create(svo_b200_ctx* ctx, int width, int height, int n_levels,
+                          svo_b200_frame** frame_out);
+/* Upload n_given >= 1 levels from host memory (levels[l] has pitch == width>>l).  Levels
+ * n_given..n_levels-1 are built on the device with the scalar vk::halfSample rule
+ * (a+b+c+d)/4.  The copy is asynchronous on the context stream when host memory is pinned. */
+int svo_b200_frame_upload(svo_b200_ctx* ctx, svo_b200_frame* frame, const uint8_t* const* levels,
+                          int n_given);
+/* Device-to-device variant: level 0 already on this GPU. */
+int svo_b200_frame_upload_device(svo_b200_ctx* ctx, svo_b200_frame* frame, const void* level0_dev);
+int svo_b200_frame_download_level(svo_b200_ctx* ctx, const svo_b200_frame* frame, int level,
+                                  uint8_t* out);
+void svo_b200_frame_destroy(svo_b200_ctx* ctx, svo_b200_frame* frame);
+
+/* ------------------------------------------------------------------ SparseImgAlign ------ */
+typedef struct {
+  int max_level, min_level; /* coarsest / finest pyramid level (ctor args) */
+  int n_iter;               /* max GN iterations per level */
+  double eps;               /* convergence threshold on |x|_inf; reference: 1e-6 */
+} svo_b200_sia_options;
+
+/* Per-iteration record, same fields as the oracle's trace (tests only). */
+typedef struct {
+  int level, iter, accepted, n_meas;
+  double chi2;
+  double x[6];
+  double T[12];
+} svo_b200_sia_iter;
+
+/* Per-pair counters used for the algorithmic-bytes model. */
+typedef struct {
+  int32_t n_iters;      /* residual passes executed, all levels */
+  int32_t sum_visible;  /* sum over levels of |visible set| at that level */
+  int32_t sum_in_image; /* sum over passes of patches inside the current image */
+  int32_t n_tracked;    /* return value of run(): patches in the last pass */
+} svo_b200_sia_stats;
+
+/* One frame pair.  T_cur_from_ref_io: in = cur.T_f_w * ref.T_f_w^-1, out = optimised value
+ * (the caller forms cur.T_f_w_ = T_cur_from_ref * ref.T_f_w_, sparse_img_align.cpp:70).
+ * px: N x 2 level-0 pixels; f: N x 3 unit bearings; point_pos: N x 3 world points;
+ * has_point: N flags (point != NULL); ref_pos = ref_frame->pos().
+ * Outputs (each may be NULL): visible_out N bytes; H_out 36 doubles (H_ of the last pass);
+ * stats_out; trace_out/trace_cap/n_trace_out. */
+int svo_b200_sparse_img_align(svo_b200_ctx* ctx, const svo_b200_frame* ref, const svo_b200_frame* cur,
+                              const svo_b200_camera* cam, const svo_b200_sia_options* opt,
+                              double* T_cur_from_ref_io, const double* px, const double* f,
+                              const double* point_pos, const uint8_t* has_point,
+                              const double* ref_pos, int N, uint8_t* visible_out, double* H_out,
+                              svo_b200_sia_stats* stats_out, svo_b200_sia_iter* trace_out,
+                              int trace_cap, int* n_trace_out);
+
+/* Batch of B independent frame pairs (one CTA each).  Three-phase API so that the caller can
+ * time the device part alone: stage (H2D of poses + features), run (kernels), fetch (D2H).
+ * feat_offset has B+1 entries; pair b owns features [feat_offset[b], feat_offset[b+1]). */
+int svo_b200_sia_batch_stage(svo_b200_ctx* ctx, int B, const svo_b200_frame* const* ref,
+                             const svo_b200_frame* const* cur, const svo_b200_camera* cam,
+                             const svo_b200_sia_options* opt, const double* T_cur_from_ref /*B*12*/,
+                             const int* feat_offset, const double* px, const double* f,
+                             const double* point_pos, const uint8_t* has_point,
+                             const double* ref_pos /*B*3*/);
+int svo_b200_sia_batch_run(svo_b200_ctx* ctx);
+int svo_b200_sia_batch_fetch(svo_b200_ctx* ctx, double* T_out /*B*12*/, uint8_t* visible_out,
+                             double* H_out /*B*36 or NULL*/, svo_b200_sia_stats* stats_out /*B or NULL*/);
+
+/* computeResiduals(model, linearize=true) at one level and pose, exposing the caches; visible_io
+ * carries the set-only visibility flags in and out. */
+int svo_b200_sparse_residuals(svo_b200_ctx* ctx, const svo_b200_frame* ref, const svo_b200_frame* cur,
+                              const svo_b200_camera* cam, int level, const double* T_cur_from_ref,
+                              const double* px, const double* f, const double* point_pos,
+                              const uint8_t* has_point, const double* ref_pos, int N,
+                              uint8_t* visible_io, float* ref_patch_out /*N*16*/,
+                              float* residuals_out /*N*16, NaN where not evaluated*/,
+                              uint8_t* in_image_out /*N*/, double* H_out /*36*/, double* Jres_out /*6*/,
+                              double* chi2_out, int64_t* n_meas_out);
+
+/* ------------------------------------------------------------------ feature alignment --- */
+/* M independent align2D calls on levels of one frame: ref_patch_with_border M*100, ref_patch M*64,
+ * level[M], px_io M*2 (level coordinates).  converged_out[M]: 1 / 0 as the reference's bool. */
+int svo_b200_align2d_batch(svo_b200_ctx* ctx, const svo_b200_frame* cur, int M, const int* level,
+                           const uint8_t* ref_patch_with_border, const uint8_t* ref_patch,
+                           int n_iter, double* px_io, uint8_t* converged_out);
+int svo_b200_align1d_batch(svo_b200_ctx* ctx, const svo_b200_frame* cur, int M, const int* level,
+                           const float* dir /*M*2*/, const uint8_t* ref_patch_with_border,
+                           const uint8_t* ref_patch, int n_iter, double* px_io,
+                           uint8_t* converged_out, double* h_inv_out);
+
+/* M Matcher::findMatchDirect calls (after Point::getCloseViewObs chose the reference feature):
+ * warp the 10x10 reference patch (getWarpMatrixAffine, getBestSearchLevel, warpAffine) and align.
+ * ref_index[M] selects one of n_ref reference frames / poses. */
+typedef struct {
+  int max_search_level; /* Config::nPyrLevels()-1 */
+  int align_max_iter;   /* Matcher::Options::align_max_iter = 10 */
+} svo_b200_match_options;
+int svo_b200_find_match_direct(svo_b200_ctx* ctx, const svo_b200_frame* const* ref_frames,
+                               const double* ref_T_f_w /*n_ref*12*/, int n_ref,
+                               const svo_b200_frame* cur, const double* cur_T_f_w,
+                               const svo_b200_camera* cam, const svo_b200_match_options* opt, int M,
+                               const int* ref_index, const double* ref_px, const double* ref_f,
+                               const int* ref_level, const int* ftr_type, const double* ref_grad,
+                               const double* point_pos /*M*3*/, double* px_cur_io /*M*2*/,
+                               uint8_t* success_out, int* search_level_out, double* A_cur_ref_out /*M*4*/,
+                               double* h_inv_out);
+
+/* ------------------------------------------------------------------ pose optimizer ------ */
+typedef struct {
+  double estimated_scale, error_init, error_final;
+  int64_t num_obs;
+  int n_iter_done;
+  double cov[36];
+} svo_b200_pose_opt_result;
+int svo_b200_pose_optimize(svo_b200_ctx* ctx, double reproj_thresh, int n_iter,
+                           double fx /*cam->errorMultiplier2()*/, double* T_f_w_io, const double* f,
+                           const double* point_pos, const int* level, uint8_t* has_point_io, int N,
+                           svo_b200_pose_opt_result* out);
+
+/* ------------------------------------------------------------------ depth filter -------- */
+#define SVO_B200_SEED_TOO_OLD 1
+#define SVO_B200_SEED_BEHIND 2
+#define SVO_B200_SEED_NOT_IN_FRAME 3
+#define SVO_B200_SEED_NO_MATCH 4
+#define SVO_B200_SEED_UPDATED 5
+#define SVO_B200_SEED_CONVERGED 6
+#define SVO_B200_SEED_NAN 7
+
+typedef struct {
+  int max_n_kfs;                         /* DepthFilter::Options::max_n_kfs = 3 */
+  double seed_convergence_sigma2_thresh; /* 200 */
+  int max_search_level;                  /* Config::nPyrLevels()-1 */
+  int align_max_iter;                    /* 10 */
+  int max_epi_search_steps;              /* 1000 */
+} svo_b200_depth_options;
+
+/* DepthFilter::updateSeeds over M seeds in SoA form.  Seeds are updated in place; status_out tells
+ * the host which list operations / callbacks to replay in list order. */
+int svo_b200_depth_filter_update(svo_b200_ctx* ctx, const svo_b200_frame* const* ref_frames,
+                                 const double* ref_T_f_w, int n_ref, const svo_b200_frame* cur,
+                                 const double* cur_T_f_w, const svo_b200_camera* cam,
+                                 const svo_b200_depth_options* opt, int M, const int* ref_index,
+                                 const double* ftr_px, const double* ftr_f, const int* ftr_level,
+                                 const int* ftr_type, const double* ftr_grad, const int* batch_id,
+                                 int batch_counter, float* a, float* b, float* mu, float* z_range,
+                                 float* sigma2, uint8_t* status_out, double* px_cur_out,
+                                 double* z_out, int* n_zmssd_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVO_B200_H_ */

@@ -1,0 +1,311 @@
+"""ctypes binding of the CPU oracle (oracle/libsvo_oracle.so) -- TEST INFRASTRUCTURE ONLY.
+
+Import this module only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  The product package (rpg_svo_b200) must never import it.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libsvo_oracle.so")
+MAX_LEVELS = 8
+
+
+def build(force: bool = False) -> str:
+    srcs = ["svo_oracle.cpp", "svo_oracle_align.inc", "svo_oracle_depth.inc", "svo_oracle_pose.inc",
+            "oracle_math.h", "svo_oracle.h", "Makefile"]
+    stale = force or not os.path.exists(_LIB_PATH) or any(
+        os.path.getmtime(os.path.join(_HERE, s)) > os.path.getmtime(_LIB_PATH) for s in srcs)
+    if stale:
+        subprocess.check_call(["make", "-s", "-C", _HERE] + (["-B"] if force else []))
+    return _LIB_PATH
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("width", C.c_int), ("height", C.c_int)]
+
+
+class SiaIter(C.Structure):
+    _fields_ = [("level", C.c_int), ("iter", C.c_int), ("accepted", C.c_int), ("n_meas", C.c_int),
+                ("chi2", C.c_double), ("x", C.c_double * 6), ("T", C.c_double * 12)]
+
+
+class MatchResult(C.Structure):
+    _fields_ = [("success", C.c_int), ("search_level", C.c_int), ("px_cur", C.c_double * 2),
+                ("A_cur_ref", C.c_double * 4), ("h_inv", C.c_double)]
+
+
+class EpiResult(C.Structure):
+    _fields_ = [("success", C.c_int), ("reject", C.c_int), ("search_level", C.c_int),
+                ("n_zmssd_evals", C.c_int), ("n_align_iter", C.c_int), ("epi_length", C.c_double),
+                ("px_cur", C.c_double * 2), ("depth", C.c_double), ("h_inv", C.c_double)]
+
+
+class PoseOptResult(C.Structure):
+    _fields_ = [("estimated_scale", C.c_double), ("error_init", C.c_double),
+                ("error_final", C.c_double), ("num_obs", C.c_int64), ("n_iter_done", C.c_int),
+                ("cov", C.c_double * 36)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        _lib = C.CDLL(_LIB_PATH)
+        _lib.orc_sparse_img_align_run.restype = C.c_int64
+        _lib.orc_compute_tau.restype = C.c_double
+        _lib.orc_compute_tau.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double]
+        _lib.orc_update_seed.argtypes = [C.c_float, C.c_float] + [C.c_void_p] * 5
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def cam_struct(cam) -> Camera:
+    return Camera(cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height)
+
+
+def _level_ptrs(pyr):
+    arr = (C.c_void_p * len(pyr))()
+    for i, im in enumerate(pyr):
+        assert im.dtype == np.uint8 and im.flags.c_contiguous
+        arr[i] = im.ctypes.data
+    cols = np.array([im.shape[1] for im in pyr], dtype=np.int32)
+    rows = np.array([im.shape[0] for im in pyr], dtype=np.int32)
+    return arr, cols, rows
+
+
+def c64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def sparse_img_align(ref_pyr, cur_pyr, cam, T_init, px, f, pos, has_point, ref_pos, max_level,
+                     min_level, n_iter=30, eps=1e-6, want_trace=True):
+    """svo::SparseImgAlign::run restated.  Returns dict(T, n_tracked, visible, H, residuals, trace)."""
+    L = lib()
+    n = int(px.shape[0])
+    rp, cols, rows = _level_ptrs(ref_pyr)
+    cp, _, _ = _level_ptrs(cur_pyr)
+    T = c64(T_init).copy().reshape(12)
+    visible = np.zeros(max(n, 1), dtype=np.uint8)
+    H = np.zeros(36)
+    res = np.zeros((max(n, 1), 16), dtype=np.float32)
+    cap = (max_level - min_level + 1) * max(n_iter, 1) + 8
+    trace = (SiaIter * cap)()
+    ntr = C.c_int(0)
+    cs = cam_struct(cam)
+    px, f, pos = c64(px), c64(f), c64(pos)
+    hp = np.ascontiguousarray(has_point, dtype=np.uint8)
+    rpos = c64(ref_pos)
+    ret = L.orc_sparse_img_align_run(rp, cp, _p(cols), _p(rows), len(ref_pyr), C.byref(cs), _p(T),
+                                     _p(px), _p(f), _p(pos), _p(hp), _p(rpos), n, max_level,
+                                     min_level, n_iter, C.c_double(eps), _p(visible), _p(H), _p(res),
+                                     trace if want_trace else None, cap, C.byref(ntr))
+    tr = []
+    if want_trace:
+        for k in range(min(ntr.value, cap)):
+            r = trace[k]
+            tr.append(dict(level=r.level, iter=r.iter, accepted=r.accepted, n_meas=r.n_meas,
+                           chi2=r.chi2, x=np.array(r.x[:]), T=np.array(r.T[:]).reshape(3, 4)))
+    return dict(T=T.reshape(3, 4), n_tracked=int(ret), visible=visible[:n], H=H.reshape(6, 6),
+                residuals=res[:n], trace=tr)
+
+
+def sparse_residuals(ref_img, cur_img, level, cam, T, px, f, pos, has_point, ref_pos, visible_in=None):
+    L = lib()
+    n = int(px.shape[0])
+    rows, cols = ref_img.shape
+    vis = np.zeros(n, dtype=np.uint8) if visible_in is None else np.ascontiguousarray(visible_in, np.uint8).copy()
+    ref_patch = np.zeros((n, 16), np.float32)
+    jac = np.zeros((n, 16, 6))
+    res = np.zeros((n, 16), np.float32)
+    inimg = np.zeros(n, np.uint8)
+    H = np.zeros(36)
+    Jres = np.zeros(6)
+    chi2 = C.c_double(0)
+    nm = C.c_int64(0)
+    cs = cam_struct(cam)
+    px, f, pos = c64(px), c64(f), c64(pos)
+    hp = np.ascontiguousarray(has_point, dtype=np.uint8)
+    T = c64(T).reshape(12)
+    rpos = c64(ref_pos)
+    L.orc_sparse_residuals(_p(ref_img), _p(cur_img), cols, rows, level, C.byref(cs), _p(T), _p(px),
+                           _p(f), _p(pos), _p(hp), _p(rpos), n, _p(vis), _p(ref_patch), _p(jac),
+                           _p(res), _p(inimg), _p(H), _p(Jres), C.byref(chi2), C.byref(nm))
+    return dict(visible=vis, ref_patch=ref_patch, jac=jac, residuals=res, in_image=inimg,
+                H=H.reshape(6, 6), Jres=Jres, chi2=chi2.value, n_meas=nm.value)
+
+
+def half_sample(img):
+    out = np.zeros((img.shape[0] // 2, img.shape[1] // 2), np.uint8)
+    lib().orc_half_sample(_p(np.ascontiguousarray(img)), img.shape[1], img.shape[0], _p(out))
+    return out
+
+
+def se3_exp(x):
+    T = np.zeros(12)
+    lib().orc_se3_exp(_p(c64(x)), _p(T))
+    return T.reshape(3, 4)
+
+
+def se3_mul(A, B):
+    Cm = np.zeros(12)
+    lib().orc_se3_mul(_p(c64(A).reshape(12)), _p(c64(B).reshape(12)), _p(Cm))
+    return Cm.reshape(3, 4)
+
+
+def se3_inv(A):
+    Cm = np.zeros(12)
+    lib().orc_se3_inv(_p(c64(A).reshape(12)), _p(Cm))
+    return Cm.reshape(3, 4)
+
+
+def ldlt6_solve(H, b):
+    x = np.zeros(6)
+    lib().orc_ldlt6_solve(_p(c64(H).reshape(36)), _p(c64(b)), _p(x))
+    return x
+
+
+def align2d(cur_img, pwb, ref_patch, n_iter, px):
+    px = c64(px).copy()
+    ok = lib().orc_align2d(_p(cur_img), cur_img.shape[1], cur_img.shape[0], cur_img.strides[0],
+                           _p(np.ascontiguousarray(pwb, np.uint8)), _p(np.ascontiguousarray(ref_patch, np.uint8)),
+                           n_iter, _p(px))
+    return bool(ok), px
+
+
+def align1d(cur_img, direction, pwb, ref_patch, n_iter, px):
+    px = c64(px).copy()
+    d = np.ascontiguousarray(direction, np.float32)
+    h = C.c_double(0)
+    ok = lib().orc_align1d(_p(cur_img), cur_img.shape[1], cur_img.shape[0], cur_img.strides[0], _p(d),
+                           _p(np.ascontiguousarray(pwb, np.uint8)), _p(np.ascontiguousarray(ref_patch, np.uint8)),
+                           n_iter, _p(px), C.byref(h))
+    return bool(ok), px, h.value
+
+
+def warp_matrix_affine(cam, px_ref, f_ref, depth, T_cur_ref, level_ref):
+    A = np.zeros(4)
+    cs = cam_struct(cam)
+    lib().orc_get_warp_matrix_affine(C.byref(cs), C.byref(cs), _p(c64(px_ref)), _p(c64(f_ref)),
+                                     C.c_double(depth), _p(c64(T_cur_ref).reshape(12)), level_ref, _p(A))
+    return A.reshape(2, 2)
+
+
+def best_search_level(A, max_level):
+    return lib().orc_get_best_search_level(_p(c64(A).reshape(4)), max_level)
+
+
+def warp_affine(A, img_ref, px_ref, level_ref, search_level, halfpatch_size):
+    patch = np.zeros((2 * halfpatch_size, 2 * halfpatch_size), np.uint8)
+    ok = lib().orc_warp_affine(_p(c64(A).reshape(4)), _p(img_ref), img_ref.shape[1], img_ref.shape[0],
+                               _p(c64(px_ref)), level_ref, search_level, halfpatch_size, _p(patch))
+    return bool(ok), patch
+
+
+def depth_from_triangulation(T, f_ref, f_cur):
+    d = C.c_double(0)
+    ok = lib().orc_depth_from_triangulation(_p(c64(T).reshape(12)), _p(c64(f_ref)), _p(c64(f_cur)), C.byref(d))
+    return bool(ok), d.value
+
+
+def find_match_direct(ref_pyr, cur_pyr, cam, T_cur_ref, ref_px, ref_f, ref_level, ftr_type, ref_grad,
+                      depth_ref, max_search_level, align_max_iter, px_cur):
+    rp, cols, rows = _level_ptrs(ref_pyr)
+    cp, _, _ = _level_ptrs(cur_pyr)
+    out = MatchResult()
+    cs = cam_struct(cam)
+    lib().orc_find_match_direct(rp, cp, _p(cols), _p(rows), len(ref_pyr), C.byref(cs),
+                                _p(c64(T_cur_ref).reshape(12)), _p(c64(ref_px)), _p(c64(ref_f)),
+                                ref_level, ftr_type, _p(c64(ref_grad)), C.c_double(depth_ref),
+                                max_search_level, align_max_iter, _p(c64(px_cur)), C.byref(out))
+    return dict(success=bool(out.success), search_level=out.search_level,
+                px_cur=np.array(out.px_cur[:]), A_cur_ref=np.array(out.A_cur_ref[:]).reshape(2, 2),
+                h_inv=out.h_inv)
+
+
+def find_epipolar_match_direct(ref_pyr, cur_pyr, cam, T_cur_ref, ref_px, ref_f, ref_level, ftr_type,
+                               ref_grad, d_est, d_min, d_max, max_search_level, align_max_iter=10,
+                               max_epi_search_steps=1000, align_1d=False):
+    rp, cols, rows = _level_ptrs(ref_pyr)
+    cp, _, _ = _level_ptrs(cur_pyr)
+    out = EpiResult()
+    cs = cam_struct(cam)
+    lib().orc_find_epipolar_match_direct(rp, cp, _p(cols), _p(rows), len(ref_pyr), C.byref(cs),
+                                         _p(c64(T_cur_ref).reshape(12)), _p(c64(ref_px)),
+                                         _p(c64(ref_f)), ref_level, ftr_type, _p(c64(ref_grad)),
+                                         C.c_double(d_est), C.c_double(d_min), C.c_double(d_max),
+                                         max_search_level, align_max_iter, max_epi_search_steps,
+                                         int(align_1d), C.byref(out))
+    return dict(success=bool(out.success), reject=bool(out.reject), search_level=out.search_level,
+                n_zmssd=out.n_zmssd_evals, epi_length=out.epi_length, px_cur=np.array(out.px_cur[:]),
+                depth=out.depth, h_inv=out.h_inv)
+
+
+def update_seed(x, tau2, a, b, mu, z_range, sigma2):
+    """Returns the updated (a, b, mu, z_range, sigma2) as float32 scalars."""
+    s = np.array([a, b, mu, z_range, sigma2], dtype=np.float32)
+    base = s.ctypes.data
+    lib().orc_update_seed(C.c_float(x), C.c_float(tau2), base, base + 4, base + 8, base + 12, base + 16)
+    return s
+
+
+def compute_tau(T_ref_cur, f, z, px_error_angle):
+    return lib().orc_compute_tau(_p(c64(T_ref_cur).reshape(12)), _p(c64(f)), z, px_error_angle)
+
+
+def depth_filter_update(ref_pyrs, ref_T_f_w, cur_pyr, cur_T_f_w, cam, ref_index, ftr_px, ftr_f,
+                        ftr_level, ftr_type, ftr_grad, batch_id, batch_counter, seeds, max_n_kfs=3,
+                        sigma2_thresh=200.0, max_search_level=2):
+    """seeds: dict of float32 arrays a,b,mu,z_range,sigma2 (updated copies are returned)."""
+    n_ref = len(ref_pyrs)
+    nl = len(cur_pyr)
+    flat = (C.c_void_p * (n_ref * nl))()
+    for r, pyr in enumerate(ref_pyrs):
+        for l, im in enumerate(pyr):
+            flat[r * nl + l] = im.ctypes.data
+    cp, cols, rows = _level_ptrs(cur_pyr)
+    M = len(ref_index)
+    out = {k: np.ascontiguousarray(seeds[k], np.float32).copy() for k in ("a", "b", "mu", "z_range", "sigma2")}
+    status = np.zeros(M, np.uint8)
+    pxc = np.zeros((M, 2))
+    z = np.zeros(M)
+    nz = np.zeros(M, np.int32)
+    cs = cam_struct(cam)
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    refT = c64(np.asarray(ref_T_f_w)).reshape(-1)
+    ri, fl, ft, bi = i32(ref_index), i32(ftr_level), i32(ftr_type), i32(batch_id)
+    fpx, ff, fg = c64(ftr_px), c64(ftr_f), c64(ftr_grad)
+    lib().orc_depth_filter_update(flat, _p(refT), n_ref, cp, _p(c64(cur_T_f_w).reshape(12)), _p(cols),
+                                  _p(rows), nl, C.byref(cs), M, _p(ri), _p(fpx), _p(ff), _p(fl),
+                                  _p(ft), _p(fg), _p(bi), batch_counter, max_n_kfs,
+                                  C.c_double(sigma2_thresh), max_search_level, _p(out["a"]),
+                                  _p(out["b"]), _p(out["mu"]), _p(out["z_range"]), _p(out["sigma2"]),
+                                  _p(status), _p(pxc), _p(z), _p(nz))
+    out.update(status=status, px_cur=pxc, z=z, n_zmssd=nz)
+    return out
+
+
+def pose_optimize(reproj_thresh, n_iter, fx, T_f_w, f, pos, level, has_point):
+    T = c64(T_f_w).copy().reshape(12)
+    hp = np.ascontiguousarray(has_point, np.uint8).copy()
+    out = PoseOptResult()
+    lv = np.ascontiguousarray(level, np.int32)
+    f, pos = c64(f), c64(pos)
+    lib().orc_pose_optimize(C.c_double(reproj_thresh), n_iter, C.c_double(fx), _p(T), _p(f), _p(pos),
+                            _p(lv), _p(hp), len(hp), C.byref(out))
+    return dict(T=T.reshape(3, 4), has_point=hp, estimated_scale=out.estimated_scale,
+                error_init=out.error_init, error_final=out.error_final, num_obs=out.num_obs,
+                n_iter_done=out.n_iter_done, cov=np.array(out.cov[:]).reshape(6, 6))

@@ -1,0 +1,253 @@
+"""ctypes binding of libsvo_b200.so -- the thin Python face of the C ABI in include/svo_b200.h.
+
+The product path is the CUDA library.  There is no CPU fallback: `load()` raises if the shared
+library has not been built, and `Context()` raises if no CUDA device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvo_b200.so")
+MAX_LEVELS = 8
+
+
+class SvoB200Error(RuntimeError):
+    pass
+
+
+class Camera(C.Structure):
+    _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
+                ("width", C.c_int), ("height", C.c_int)]
+
+
+class SiaOptions(C.Structure):
+    _fields_ = [("max_level", C.c_int), ("min_level", C.c_int), ("n_iter", C.c_int), ("eps", C.c_double)]
+
+
+class SiaIter(C.Structure):
+    _fields_ = [("level", C.c_int), ("iter", C.c_int), ("accepted", C.c_int), ("n_meas", C.c_int),
+                ("chi2", C.c_double), ("x", C.c_double * 6), ("T", C.c_double * 12)]
+
+
+class SiaStats(C.Structure):
+    _fields_ = [("n_iters", C.c_int32), ("sum_visible", C.c_int32), ("sum_in_image", C.c_int32),
+                ("n_tracked", C.c_int32)]
+
+
+class MatchOptions(C.Structure):
+    _fields_ = [("max_search_level", C.c_int), ("align_max_iter", C.c_int)]
+
+
+class PoseOptResult(C.Structure):
+    _fields_ = [("estimated_scale", C.c_double), ("error_init", C.c_double), ("error_final", C.c_double),
+                ("num_obs", C.c_int64), ("n_iter_done", C.c_int), ("cov", C.c_double * 36)]
+
+
+class DepthOptions(C.Structure):
+    _fields_ = [("max_n_kfs", C.c_int), ("seed_convergence_sigma2_thresh", C.c_double),
+                ("max_search_level", C.c_int), ("align_max_iter", C.c_int), ("max_epi_search_steps", C.c_int)]
+
+
+SIA_STATS_DTYPE = np.dtype([("n_iters", np.int32), ("sum_visible", np.int32),
+                            ("sum_in_image", np.int32), ("n_tracked", np.int32)])
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the CUDA library; fail loudly if it is missing (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise SvoB200Error(f"{LIB_PATH} is missing: build it with `python -m rpg_svo_b200.build` "
+                               "(there is no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.svo_b200_last_error.restype = C.c_char_p
+        _lib.svo_b200_version.restype = C.c_char_p
+        _lib.svo_b200_stream.restype = C.c_void_p
+        _lib.svo_b200_launch_count.restype = C.c_uint64
+        for name in ("svo_b200_last_error", "svo_b200_stream", "svo_b200_launch_count",
+                     "svo_b200_synchronize", "svo_b200_destroy"):
+            getattr(_lib, name).argtypes = [C.c_void_p]
+        _lib.svo_b200_frame_destroy.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.svo_b200_frame_destroy.restype = None
+        _lib.svo_b200_destroy.restype = None
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def c64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def cam_struct(cam) -> Camera:
+    return Camera(cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height)
+
+
+class Frame:
+    """An image pyramid resident in HBM (the image side of svo::Frame)."""
+
+    def __init__(self, ctx: "Context", width: int, height: int, n_levels: int):
+        self.ctx, self.width, self.height, self.n_levels = ctx, width, height, n_levels
+        h = C.c_void_p()
+        ctx._check(ctx.lib.svo_b200_frame_create(ctx.h, width, height, n_levels, C.byref(h)))
+        self.h = h
+
+    def upload(self, levels) -> "Frame":
+        """levels: list of >=1 contiguous uint8 arrays (level 0 first); missing levels are built on the GPU."""
+        arr = (C.c_void_p * len(levels))()
+        keep = []
+        for i, im in enumerate(levels):
+            im = np.ascontiguousarray(im, dtype=np.uint8)
+            assert im.shape == (self.height >> i, self.width >> i), (im.shape, i)
+            keep.append(im)
+            arr[i] = im.ctypes.data
+        self.ctx._check(self.ctx.lib.svo_b200_frame_upload(self.ctx.h, self.h, arr, len(levels)))
+        self.ctx.synchronize()  # host arrays may be freed by the caller right after
+        return self
+
+    def upload_ptrs(self, ptrs) -> None:
+        """Asynchronous upload from raw (pinned) host pointers; the caller keeps the memory alive."""
+        arr = (C.c_void_p * len(ptrs))(*ptrs)
+        self.ctx._check(self.ctx.lib.svo_b200_frame_upload(self.ctx.h, self.h, arr, len(ptrs)))
+
+    def upload_device(self, dev_ptr: int) -> None:
+        self.ctx._check(self.ctx.lib.svo_b200_frame_upload_device(self.ctx.h, self.h, C.c_void_p(dev_ptr)))
+
+    def download_level(self, level: int) -> np.ndarray:
+        out = np.zeros((self.height >> level, self.width >> level), np.uint8)
+        self.ctx._check(self.ctx.lib.svo_b200_frame_download_level(self.ctx.h, self.h, level, _p(out)))
+        return out
+
+    def destroy(self):
+        if self.h:
+            self.ctx.lib.svo_b200_frame_destroy(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            if self.h and self.ctx.h:
+                self.destroy()
+        except Exception:
+            pass
+
+
+class Context:
+    """One GPU + one CUDA stream (use one per calling host thread)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.svo_b200_create(C.byref(h), device)
+        if rc != 0:
+            raise SvoB200Error(f"svo_b200_create(device={device}) failed with {rc}: no usable CUDA device "
+                               "(the CUDA path is the only path)")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            self.lib.svo_b200_destroy(self.h)
+            self.h = None
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise SvoB200Error(f"svo_b200 error {rc}: {self.lib.svo_b200_last_error(self.h).decode()}")
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.svo_b200_stream(self.h))
+
+    def synchronize(self):
+        self._check(self.lib.svo_b200_synchronize(self.h))
+
+    def launch_count(self) -> int:
+        return int(self.lib.svo_b200_launch_count(self.h))
+
+    def frame(self, pyr) -> Frame:
+        """Create + upload a frame from a full host pyramid (list of uint8 arrays)."""
+        f = Frame(self, pyr[0].shape[1], pyr[0].shape[0], len(pyr))
+        return f.upload(pyr)
+
+    def frame_from_level0(self, img, n_levels: int) -> Frame:
+        f = Frame(self, img.shape[1], img.shape[0], n_levels)
+        return f.upload([img])
+
+    # ------------------------------------------------------------------ SparseImgAlign
+    def sparse_img_align(self, ref: Frame, cur: Frame, cam, T_init, px, f, pos, has_point, ref_pos,
+                         max_level, min_level, n_iter=30, eps=1e-6, want_trace=False):
+        n = int(np.asarray(px).shape[0])
+        T = c64(T_init).copy().reshape(12)
+        px, f, pos, rpos = c64(px), c64(f), c64(pos), c64(ref_pos)
+        hp = np.ascontiguousarray(has_point, dtype=np.uint8)
+        visible = np.zeros(max(n, 1), np.uint8)
+        H = np.zeros(36)
+        stats = SiaStats()
+        cap = ((max_level - min_level + 1) * max(n_iter, 1) + 8) if want_trace else 0
+        trace = (SiaIter * cap)() if cap else None
+        ntr = C.c_int(0)
+        cs = cam_struct(cam)
+        opt = SiaOptions(max_level, min_level, n_iter, eps)
+        self._check(self.lib.svo_b200_sparse_img_align(
+            self.h, ref.h, cur.h, C.byref(cs), C.byref(opt), _p(T), _p(px), _p(f), _p(pos), _p(hp),
+            _p(rpos), n, _p(visible), _p(H), C.byref(stats), trace, cap, C.byref(ntr)))
+        tr = []
+        for k in range(min(ntr.value, cap)):
+            r = trace[k]
+            tr.append(dict(level=r.level, iter=r.iter, accepted=r.accepted, n_meas=r.n_meas, chi2=r.chi2,
+                           x=np.array(r.x[:]), T=np.array(r.T[:]).reshape(3, 4)))
+        return dict(T=T.reshape(3, 4), n_tracked=int(stats.n_tracked), visible=visible[:n],
+                    H=H.reshape(6, 6), trace=tr,
+                    stats=dict(n_iters=stats.n_iters, sum_visible=stats.sum_visible,
+                               sum_in_image=stats.sum_in_image, n_tracked=stats.n_tracked))
+
+    def sia_batch_stage(self, refs, curs, cam, T_init, feat_offset, px, f, pos, has_point, ref_pos,
+                        max_level, min_level, n_iter=30, eps=1e-6):
+        B = len(refs)
+        ra = (C.c_void_p * B)(*[r.h.value for r in refs])
+        ca = (C.c_void_p * B)(*[c.h.value for c in curs])
+        cs = cam_struct(cam)
+        opt = SiaOptions(max_level, min_level, n_iter, eps)
+        self._batch = dict(B=B, n=int(feat_offset[-1] - feat_offset[0]))
+        fo = np.ascontiguousarray(feat_offset, np.int32)
+        T, px, f, pos, rpos = c64(T_init), c64(px), c64(f), c64(pos), c64(ref_pos)
+        hp = np.ascontiguousarray(has_point, np.uint8)
+        self._check(self.lib.svo_b200_sia_batch_stage(self.h, B, ra, ca, C.byref(cs), C.byref(opt), _p(T),
+                                                      _p(fo), _p(px), _p(f), _p(pos), _p(hp), _p(rpos)))
+
+    def sia_batch_run(self):
+        self._check(self.lib.svo_b200_sia_batch_run(self.h))
+
+    def sia_batch_fetch(self, want_H=False):
+        B, n = self._batch["B"], self._batch["n"]
+        T = np.zeros((B, 3, 4))
+        vis = np.zeros(max(n, 1), np.uint8)
+        H = np.zeros((B, 6, 6)) if want_H else None
+        stats = np.zeros(B, SIA_STATS_DTYPE)
+        self._check(self.lib.svo_b200_sia_batch_fetch(self.h, _p(T), _p(vis), _p(H), _p(stats)))
+        return dict(T=T, visible=vis[:n], H=H, stats=stats)
+
+    def sparse_residuals(self, ref: Frame, cur: Frame, cam, level, T, px, f, pos, has_point, ref_pos,
+                         visible_in=None):
+        n = int(np.asarray(px).shape[0])
+        vis = np.zeros(n, np.uint8) if visible_in is None else np.ascontiguousarray(visible_in, np.uint8).copy()
+        ref_patch = np.zeros((n, 16), np.float32)
+        res = np.zeros((n, 16), np.float32)
+        inimg = np.zeros(n, np.uint8)
+        H, Jres = np.zeros(36), np.zeros(6)
+        chi2, nm = C.c_double(0), C.c_int64(0)
+        cs = cam_struct(cam)
+        T, px, f, pos, rpos = c64(T).reshape(12), c64(px), c64(f), c64(pos), c64(ref_pos)
+        hp = np.ascontiguousarray(has_point, np.uint8)
+        self._check(self.lib.svo_b200_sparse_residuals(
+            self.h, ref.h, cur.h, C.byref(cs), level, _p(T), _p(px), _p(f), _p(pos), _p(hp), _p(rpos), n,
+            _p(vis), _p(ref_patch), _p(res), _p(inimg), _p(H), _p(Jres), C.byref(chi2), C.byref(nm)))
+        return dict(visible=vis, ref_patch=ref_patch, residuals=res, in_image=inimg, H=H.reshape(6, 6),
+                    Jres=Jres, chi2=chi2.value, n_meas=nm.value)

@@ -1,0 +1,226 @@
+// rpg_svo_b200/csrc/context.cu -- context lifetime, frame (image pyramid) residency in HBM and the
+// on-device pyramid build.  Replaces the image side of svo::Frame (svo/include/svo/frame.h:40-84,
+// svo/src/frame.cpp:48-59,156-165).
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "ctx.h"
+
+namespace svo {
+
+int set_err(svo_b200_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+
+int ensure_dev(svo_b200_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return 0;
+  if (b.p) {
+    SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t cap = bytes + bytes / 4 + 4096;
+  SVO_CUDA_CHECK(ctx, cudaMalloc(&b.p, cap));
+  b.cap = cap;
+  return 0;
+}
+
+int ensure_host(svo_b200_ctx* ctx, HostBuf& b, size_t bytes) {
+  if (bytes <= b.cap) return 0;
+  if (b.p) {
+    SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFreeHost(b.p);
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  size_t cap = bytes + bytes / 4 + 4096;
+  SVO_CUDA_CHECK(ctx, cudaMallocHost(&b.p, cap));
+  b.cap = cap;
+  return 0;
+}
+
+// [EXT] vk::halfSample scalar rule: out = (a + b + c + d) / 4 with integer division, rows/2 x cols/2
+// (svo/src/frame.cpp:156-165).  HBM-bound byte kernel: each thread produces 4 output pixels from two
+// 8-byte row segments (coalesced 64-bit loads, one 32-bit store).
+__global__ void half_sample_kernel(const uint8_t* __restrict__ in, int in_w, int in_h,
+                                   uint8_t* __restrict__ out, int out_w, int out_h) {
+  const int quads = (out_w + 3) / 4;
+  const int total = quads * out_h;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int y = idx / quads, qx = idx - y * quads;
+    const int x0 = qx * 4;
+    const uint8_t* top = in + (size_t)(2 * y) * in_w + 2 * x0;
+    const uint8_t* bot = top + in_w;
+    if (x0 + 4 <= out_w && ((in_w & 7) == 0)) {
+      const uint2 t = *reinterpret_cast<const uint2*>(top);
+      const uint2 b = *reinterpret_cast<const uint2*>(bot);
+      uint32_t r = 0;
+      const uint32_t tw[2] = {t.x, t.y}, bw[2] = {b.x, b.y};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t tt = tw[k >> 1] >> ((k & 1) * 16), bb = bw[k >> 1] >> ((k & 1) * 16);
+        const uint32_t s = (tt & 0xff) + ((tt >> 8) & 0xff) + (bb & 0xff) + ((bb >> 8) & 0xff);
+        r |= (s >> 2) << (8 * k);
+      }
+      *reinterpret_cast<uint32_t*>(out + (size_t)y * out_w + x0) = r;
+    } else {
+      for (int k = 0; k < 4 && x0 + k < out_w; ++k) {
+        const uint32_t s = (uint32_t)top[2 * k] + top[2 * k + 1] + bot[2 * k] + bot[2 * k + 1];
+        out[(size_t)y * out_w + x0 + k] = (uint8_t)(s >> 2);
+      }
+    }
+  }
+}
+
+static int build_levels(svo_b200_ctx* ctx, svo_b200_frame* fr, int from_level) {
+  for (int l = from_level; l < fr->n_levels; ++l) {
+    const int total = ((fr->w[l] + 3) / 4) * fr->h[l];
+    if (total <= 0) continue;
+    const int threads = 256;
+    int blocks = (total + threads - 1) / threads;
+    if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
+    half_sample_kernel<<<blocks, threads, 0, ctx->stream>>>(fr->lvl(l - 1), fr->w[l - 1], fr->h[l - 1],
+                                                            fr->lvl(l), fr->w[l], fr->h[l]);
+    ctx->launches++;
+  }
+  SVO_CUDA_CHECK(ctx, cudaGetLastError());
+  return 0;
+}
+
+}  // namespace svo
+
+using namespace svo;
+
+extern "C" {
+
+const char* svo_b200_version(void) { return "svo_b200 0.1 (sm_100a)"; }
+
+int svo_b200_create(svo_b200_ctx** ctx_out, int device) {
+  if (!ctx_out) return SVO_B200_EINVAL;
+  *ctx_out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+    fprintf(stderr, "svo_b200_create: no usable CUDA device %d (%s); there is no CPU fallback\n", device,
+            e != cudaSuccess ? cudaGetErrorString(e) : "device index out of range");
+    return SVO_B200_ECUDA;
+  }
+  svo_b200_ctx* ctx = new svo_b200_ctx();
+  ctx->device = device;
+  if (cudaSetDevice(device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    fprintf(stderr, "svo_b200_create: cannot initialise device %d: %s\n", device,
+            cudaGetErrorString(cudaGetLastError()));
+    delete ctx;
+    return SVO_B200_ECUDA;
+  }
+  cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  *ctx_out = ctx;
+  return SVO_B200_OK;
+}
+
+void svo_b200_destroy(svo_b200_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  sia_batch_free(ctx);
+  if (ctx->d_in.p) cudaFree(ctx->d_in.p);
+  if (ctx->d_out.p) cudaFree(ctx->d_out.p);
+  if (ctx->d_scratch.p) cudaFree(ctx->d_scratch.p);
+  if (ctx->h_in.p) cudaFreeHost(ctx->h_in.p);
+  if (ctx->h_out.p) cudaFreeHost(ctx->h_out.p);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* svo_b200_last_error(const svo_b200_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+void* svo_b200_stream(svo_b200_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+uint64_t svo_b200_launch_count(const svo_b200_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int svo_b200_synchronize(svo_b200_ctx* ctx) {
+  if (!ctx) return SVO_B200_EINVAL;
+  SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int svo_b200_frame_create(svo_b200_ctx* ctx, int width, int height, int n_levels,
+                          svo_b200_frame** frame_out) {
+  if (!ctx || !frame_out || width <= 0 || height <= 0 || n_levels < 1 || n_levels > SVO_B200_MAX_LEVELS)
+    return set_err(ctx, SVO_B200_EINVAL, "frame_create: bad size %dx%d levels %d", width, height, n_levels);
+  cudaSetDevice(ctx->device);
+  svo_b200_frame* fr = new svo_b200_frame();
+  fr->width = width;
+  fr->height = height;
+  fr->n_levels = n_levels;
+  size_t off = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    fr->w[l] = l ? fr->w[l - 1] / 2 : width;
+    fr->h[l] = l ? fr->h[l - 1] / 2 : height;
+    if (fr->w[l] <= 0 || fr->h[l] <= 0) {
+      delete fr;
+      return set_err(ctx, SVO_B200_EINVAL, "frame_create: level %d is empty", l);
+    }
+    fr->off[l] = off;
+    off += ((size_t)fr->w[l] * fr->h[l] + 255 + 16) / 256 * 256;  // +16: kernels may read one word past
+  }
+  fr->bytes = off;
+  cudaError_t e = cudaMalloc((void**)&fr->base, fr->bytes);
+  if (e != cudaSuccess) {
+    delete fr;
+    return set_err(ctx, SVO_B200_ENOMEM, "frame_create: cudaMalloc(%zu): %s", off, cudaGetErrorString(e));
+  }
+  cudaMemsetAsync(fr->base, 0, fr->bytes, ctx->stream);
+  *frame_out = fr;
+  return 0;
+}
+
+int svo_b200_frame_upload(svo_b200_ctx* ctx, svo_b200_frame* fr, const uint8_t* const* levels, int n_given) {
+  if (!ctx || !fr || !levels || n_given < 1 || n_given > fr->n_levels)
+    return set_err(ctx, SVO_B200_EINVAL, "frame_upload: bad arguments");
+  cudaSetDevice(ctx->device);
+  for (int l = 0; l < n_given; ++l) {
+    if (!levels[l]) return set_err(ctx, SVO_B200_EINVAL, "frame_upload: level %d is NULL", l);
+    SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(fr->lvl(l), levels[l], (size_t)fr->w[l] * fr->h[l],
+                                        cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return build_levels(ctx, fr, n_given);
+}
+
+int svo_b200_frame_upload_device(svo_b200_ctx* ctx, svo_b200_frame* fr, const void* level0_dev) {
+  if (!ctx || !fr || !level0_dev) return set_err(ctx, SVO_B200_EINVAL, "frame_upload_device: bad arguments");
+  cudaSetDevice(ctx->device);
+  SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(fr->lvl(0), level0_dev, (size_t)fr->w[0] * fr->h[0],
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+  return build_levels(ctx, fr, 1);
+}
+
+int svo_b200_frame_download_level(svo_b200_ctx* ctx, const svo_b200_frame* fr, int level, uint8_t* out) {
+  if (!ctx || !fr || !out || level < 0 || level >= fr->n_levels)
+    return set_err(ctx, SVO_B200_EINVAL, "frame_download_level: bad arguments");
+  cudaSetDevice(ctx->device);
+  SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(out, fr->lvl(level), (size_t)fr->w[level] * fr->h[level],
+                                      cudaMemcpyDeviceToHost, ctx->stream));
+  SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+void svo_b200_frame_destroy(svo_b200_ctx* ctx, svo_b200_frame* fr) {
+  if (!fr) return;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  if (fr->base) cudaFree(fr->base);
+  delete fr;
+}
+
+}  // extern "C"

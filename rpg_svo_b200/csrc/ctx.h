@@ -1,0 +1,74 @@
+// rpg_svo_b200/csrc/ctx.h -- internal: context, frame and helper declarations shared by the .cu files.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/svo_b200.h"
+
+struct svo_b200_frame {
+  int width = 0, height = 0, n_levels = 0;
+  int w[SVO_B200_MAX_LEVELS] = {0}, h[SVO_B200_MAX_LEVELS] = {0};
+  uint8_t* base = nullptr;  // one allocation, levels at 256-byte aligned offsets
+  size_t off[SVO_B200_MAX_LEVELS] = {0};
+  size_t bytes = 0;
+  uint8_t* lvl(int l) const { return base + off[l]; }
+};
+
+// Grow-only device / pinned-host buffers owned by the context.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+struct HostBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+};
+
+namespace svo {
+struct SiaBatchState;  // defined in sparse_align.cu
+}
+
+struct svo_b200_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  // generic scratch (each entry point carves what it needs)
+  DevBuf d_in, d_out, d_scratch;
+  HostBuf h_in, h_out;
+  svo::SiaBatchState* sia = nullptr;
+};
+
+namespace svo {
+
+int set_err(svo_b200_ctx* ctx, int code, const char* fmt, ...);
+int ensure_dev(svo_b200_ctx* ctx, DevBuf& b, size_t bytes);
+int ensure_host(svo_b200_ctx* ctx, HostBuf& b, size_t bytes);
+
+#define SVO_CUDA_CHECK(ctx, call)                                                                   \
+  do {                                                                                              \
+    cudaError_t _e = (call);                                                                        \
+    if (_e != cudaSuccess)                                                                          \
+      return svo::set_err((ctx), SVO_B200_ECUDA, "%s failed: %s (%s:%d)", #call,                    \
+                          cudaGetErrorString(_e), __FILE__, __LINE__);                              \
+  } while (0)
+
+// Bump allocator over a byte buffer (host staging mirrored 1:1 on the device).
+struct Carver {
+  size_t off = 0;
+  size_t take(size_t bytes, size_t align = 256) {
+    off = (off + align - 1) / align * align;
+    size_t o = off;
+    off += bytes;
+    return o;
+  }
+};
+
+void sia_batch_free(svo_b200_ctx* ctx);
+
+}  // namespace svo

@@ -1,0 +1,844 @@
+// rpg_svo_b200/csrc/sparse_align.cu -- svo::SparseImgAlign on sm_100a.
+//
+// Replaces svo/src/sparse_img_align.cpp:43-258 (run / precomputeReferencePatches /
+// computeResiduals / solve / update) together with the Gauss-Newton driver of
+// vk::NLLSSolver<6,SE3>::optimizeGaussNewton [EXT] that the class derives from.
+//
+// Design (B200-first, not a translation):
+//   * one CTA per frame pair runs the WHOLE coarse-to-fine loop on the device: no host round trip
+//     per Gauss-Newton iteration, batches of pairs fill the 148 SMs (grid = #pairs).
+//   * one thread owns one feature (FPT features when N > blockDim): its bearing/depth state lives in
+//     registers for the whole run; the 4x4 reference patch, and its two gradient images, live in
+//     shared memory in pixel-major (SoA) order so a warp's accesses are conflict free.
+//   * inverse-compositional structure is exploited: the per-pixel Jacobian is
+//     J_p = dx_p * a + dy_p * b with a, b per-FEATURE 6-vectors, hence
+//        sum_p J_p J_p^T = Sxx aa^T + Sxy (ab^T + ba^T) + Syy bb^T     (pose independent)
+//        sum_p J_p r_p   = (sum dx_p r_p) a + (sum dy_p r_p) b
+//     so the 6x6 normal matrix is reduced and factorised ONCE per level (and re-formed only in the
+//     iterations where some patch leaves the current image), and an iteration costs 3 f32 FMAs per
+//     pixel plus ~15 f64 FMAs per feature instead of the reference's 27 f64 MACs per pixel.
+//   * the packed feature records of the pair and the coarse current-level images are staged into
+//     shared memory with TMA bulk copies (cp.async.bulk + mbarrier); fine levels are gathered with
+//     two aligned 32-bit read-only loads per 5-byte footprint row.
+//   * each warp folds its partial sums (6 Jres + chi2 + counts) with __shfl_down; one thread does
+//     the 6x6 substitution, SE3 exp and the accept / rollback decision and broadcasts the new pose.
+// Precision follows the reference per quantity: f32 interpolation/residual/chi2, f64 geometry and
+// normal equations.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "ctx.h"
+#include "svo_math.cuh"
+
+namespace svo {
+
+constexpr int kPatchArea = 16;
+constexpr int kPartK = 22;  // widest block reduction: 21 unique H entries + 1 count
+constexpr int kMaxWarps = 32;
+
+struct SiaJob {  // one frame pair; array lives in device memory
+  const uint8_t* ref_lvl[SVO_B200_MAX_LEVELS];
+  const uint8_t* cur_lvl[SVO_B200_MAX_LEVELS];
+  const uint8_t* blob;  // packed features: px[np*2] f[np*3] pos[np*3] (f64) then has_point[np] (u8)
+  int n_feat, n_pad;
+  int feat_off;  // offset of this pair in visible_out
+  int pad_;
+  double T[12];
+  double ref_pos[3];
+};
+
+struct SiaParams {
+  const SiaJob* jobs;
+  int w[SVO_B200_MAX_LEVELS], h[SVO_B200_MAX_LEVELS];
+  double fx, fy, cx, cy;
+  int max_level, min_level, n_iter;
+  double eps;
+  int stage_cap;  // bytes of the TMA staging region in shared memory
+  int slots;      // blockDim * FPT feature slots (patch arrays are [3][16][slots])
+  double* T_out;
+  double* H_out;
+  uint8_t* visible_out;
+  svo_b200_sia_stats* stats;
+  svo_b200_sia_iter* trace;
+  int trace_cap;
+  int* n_trace;
+  // EVAL mode (svo_b200_sparse_residuals)
+  int eval_level;
+  const uint8_t* visible_in;
+  float* ref_patch_out;
+  float* residuals_out;
+  uint8_t* in_image_out;
+  double* Jres_out;
+  double* chi2_out;
+  long long* n_meas_out;
+};
+
+struct SiaShared {
+  uint64_t mbar;
+  double R[9];
+  double t[3];
+  double part[kMaxWarps * kPartK];
+  double Hs[36];       // H_ of the current pass (scaled), full symmetric
+  double Htot[36];     // sum over the level's visible set (scaled)
+  double ldl[36];      // factorisation used for the current solve
+  double ldl_tot[36];  // factorisation of Htot
+  double x[8];
+  double sums[kPartK];
+  Pose model, old_model;
+  double chi2_prev;
+  int tr[8], tr_tot[8];
+  int stop, done, slow, n_in_last;
+  int n_iters, sum_vis, sum_in, n_trace;
+  unsigned mbar_phase;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Unaligned byte-row fetch: `n` <= 8 consecutive bytes starting at byte offset `off` from a
+// 4-byte aligned base, as two (or three) aligned 32-bit loads + funnel shifts.
+// ---------------------------------------------------------------------------------------------
+template <bool SMEM>
+__device__ __forceinline__ uint32_t ld_word(const uint8_t* base, int word_off) {
+  if (SMEM) return *reinterpret_cast<const uint32_t*>(base + word_off);
+  return __ldg(reinterpret_cast<const uint32_t*>(base + word_off));
+}
+template <bool SMEM>
+__device__ __forceinline__ void fetch8(const uint8_t* base, int off, uint32_t& lo, uint32_t& hi) {
+  const int a = off & ~3;
+  const unsigned sh = (unsigned)(off & 3) * 8u;
+  const uint32_t w0 = ld_word<SMEM>(base, a), w1 = ld_word<SMEM>(base, a + 4);
+  lo = __funnelshift_r(w0, w1, sh);
+  hi = w1 >> sh;  // valid bytes: 4 - (off&3); callers needing more use fetch12
+}
+template <bool SMEM>
+__device__ __forceinline__ void fetch12(const uint8_t* base, int off, uint32_t& lo, uint32_t& hi) {
+  const int a = off & ~3;
+  const unsigned sh = (unsigned)(off & 3) * 8u;
+  const uint32_t w0 = ld_word<SMEM>(base, a), w1 = ld_word<SMEM>(base, a + 4),
+                 w2 = ld_word<SMEM>(base, a + 8);
+  lo = __funnelshift_r(w0, w1, sh);
+  hi = __funnelshift_r(w1, w2, sh);
+}
+__device__ __forceinline__ float byte_f(uint32_t w, int k) { return (float)((w >> (8 * k)) & 0xffu); }
+
+// per-feature unscaled Jacobian rows: a = row0 of jacobian_xyz2uv, b = row1 (frame.h:116-138)
+__device__ __forceinline__ void jac_rows(double x, double y, double zi, double (&a)[6], double (&b)[6]) {
+  const double X = x * zi, Y = y * zi;
+  a[0] = -zi; a[1] = 0.0; a[2] = X * zi; a[3] = X * Y; a[4] = -(1.0 + X * X); a[5] = Y;
+  b[0] = 0.0; b[1] = -zi; b[2] = Y * zi; b[3] = 1.0 + Y * Y; b[4] = -(X * Y); b[5] = -X;
+}
+// h[21] (upper triangle, row-major) += Sxx aa^T + Sxy (ab^T + ba^T) + Syy bb^T
+__device__ __forceinline__ void add_h(double x, double y, double zi, double sxx, double sxy, double syy,
+                                      double* h) {
+  double a[6], b[6];
+  jac_rows(x, y, zi, a, b);
+  int idx = 0;
+#pragma unroll
+  for (int r = 0; r < 6; ++r)
+#pragma unroll
+    for (int c = r; c < 6; ++c, ++idx)
+      h[idx] += sxx * (a[r] * a[c]) + sxy * (a[r] * b[c] + b[r] * a[c]) + syy * (b[r] * b[c]);
+}
+
+// Sum `K` doubles over the block: on return thread 0..K-1 of warp 0 ... the totals are in s.sums
+// (valid for warp 0 after its __syncwarp).  Contains ONE __syncthreads.
+template <int K>
+__device__ __forceinline__ void block_sum_to_warp0(double (&v)[K], SiaShared& s, int nwarps) {
+  warp_sum<K>(v);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) s.part[warp * kPartK + k] = v[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+    if (lane < K) {
+      double acc = 0.0;
+      for (int wv = 0; wv < nwarps; ++wv) acc += s.part[wv * kPartK + lane];
+      s.sums[lane] = acc;
+    }
+    __syncwarp();
+  }
+}
+
+__device__ inline void publish_model(SiaShared& s) {
+  qmatrix(s.model.q, s.R);
+  s.t[0] = s.model.t[0]; s.t[1] = s.model.t[1]; s.t[2] = s.model.t[2];
+}
+
+// Thread 0: given Jres in s.x (already scaled/negated) and the factorisation in (ldl, tr), run the
+// tail of one NLLSSolver::optimizeGaussNewton iteration [EXT]: solve, accept/rollback, update.
+__device__ inline void gn_finish(SiaShared& s, const SiaParams& P, const double* ldl, const int* tr,
+                                 int level, int iter, double chi2sum, int n_in) {
+  const int n_meas = n_in * kPatchArea;
+  const float chi2f = (float)chi2sum;
+  const double new_chi2 = (double)(chi2f / (float)n_meas);  // sparse_img_align.cpp:242 (NaN if 0)
+  double Jres[6];
+  for (int k = 0; k < 6; ++k) Jres[k] = s.x[k];
+  ldlt6_solve(ldl, tr, s.x);
+  if (isnan(s.x[0])) s.stop = 1;  // solve() == 0 (:248-250)
+  int accepted;
+  if ((iter > 0 && new_chi2 > s.chi2_prev) || s.stop) {
+    s.model = s.old_model;  // rollback
+    s.done = 1;
+    accepted = 0;
+  } else {
+    double mx[6];
+    for (int k = 0; k < 6; ++k) mx[k] = -s.x[k];
+    const Pose nm = pose_mul(s.model, se3_exp(mx));  // T_new = T_old * exp(-x)  (:257)
+    s.old_model = s.model;
+    s.model = nm;
+    s.chi2_prev = new_chi2;
+    accepted = 1;
+    double m = 0;
+    for (int k = 0; k < 6; ++k) m = fmax(m, fabs(s.x[k]));
+    if (m <= P.eps) s.done = 1;
+  }
+  s.n_in_last = n_in;
+  s.n_iters++;
+  s.sum_in += n_in;
+  publish_model(s);
+  if (P.trace) {
+    if (s.n_trace < P.trace_cap) {
+      svo_b200_sia_iter& r = P.trace[s.n_trace];
+      r.level = level; r.iter = iter; r.accepted = accepted; r.n_meas = n_meas; r.chi2 = new_chi2;
+      for (int k = 0; k < 6; ++k) r.x[k] = s.x[k];
+      pose_to_rt12(s.model, r.T);
+    }
+    s.n_trace++;
+  }
+  (void)Jres;
+}
+
+template <int FPT, bool EVAL>
+__global__ void __launch_bounds__(512) sia_kernel(const SiaParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SiaShared& s = *reinterpret_cast<SiaShared*>(smem_raw);
+  const int S = P.slots;
+  float* pat_ref = reinterpret_cast<float*>(smem_raw + ((sizeof(SiaShared) + 15) & ~size_t(15)));
+  float* pat_dx = pat_ref + kPatchArea * S;
+  float* pat_dy = pat_dx + kPatchArea * S;
+  uint8_t* stage = reinterpret_cast<uint8_t*>(pat_dy + kPatchArea * S);  // 16-byte aligned
+
+  const SiaJob& job = P.jobs[blockIdx.x];
+  const int tid = threadIdx.x, T = blockDim.x, nwarps = (T + 31) >> 5;
+  const int N = job.n_feat;
+
+  const int np = job.n_pad;
+  const uint32_t blob_bytes = (uint32_t)np * 65u;
+  const bool blob_staged = blob_bytes <= (uint32_t)P.stage_cap;
+  if (tid == 0) {
+    mbar_init(&s.mbar, 1);
+    fence_mbar_init();
+    // use k of the barrier completes phase parity k&1; the blob copy (if any) is use 0
+    s.mbar_phase = blob_staged ? 0u : 1u;
+    s.model = pose_from_rt12(job.T);
+    s.old_model = s.model;
+    s.chi2_prev = 1e10;  // NLLSSolver::reset() [EXT]
+    s.stop = 0; s.done = 0; s.slow = 0; s.n_in_last = 0;
+    s.n_iters = 0; s.sum_vis = 0; s.sum_in = 0; s.n_trace = 0;
+    for (int k = 0; k < 36; ++k) s.Hs[k] = 0.0;
+    publish_model(s);
+  }
+  __syncthreads();
+
+  // ---- stage the packed feature records of this pair with one TMA bulk copy -----------------
+  if (blob_staged) {
+    if (tid == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&s.mbar, blob_bytes);
+      tma_bulk_g2s(stage, job.blob, blob_bytes, &s.mbar);
+    }
+    mbar_wait(&s.mbar, 0);
+  }
+  const uint8_t* blob = blob_staged ? stage : job.blob;
+  const double* b_px = reinterpret_cast<const double*>(blob);
+  const double* b_f = b_px + 2 * np;
+  const double* b_pos = b_f + 3 * np;
+  const uint8_t* b_hp = reinterpret_cast<const uint8_t*>(b_pos + 3 * np);
+
+  // per-feature register state
+  double fx_[FPT], fy_[FPT], fz_[FPT], fzi_[FPT], fpx_[FPT], fpy_[FPT];
+  unsigned hp_mask = 0, vis_mask = 0, in_mask = 0;
+#pragma unroll
+  for (int k = 0; k < FPT; ++k) {
+    const int i = tid + k * T;
+    fx_[k] = fy_[k] = 0.0; fz_[k] = fzi_[k] = 1.0; fpx_[k] = fpy_[k] = -1e6;
+    if (i < N) {
+      fpx_[k] = b_px[2 * i];
+      fpy_[k] = b_px[2 * i + 1];
+      const double dxp = b_pos[3 * i] - job.ref_pos[0], dyp = b_pos[3 * i + 1] - job.ref_pos[1],
+                   dzp = b_pos[3 * i + 2] - job.ref_pos[2];
+      const double depth = sqrt(dxp * dxp + dyp * dyp + dzp * dzp);  // :107  |pos - ref_pos|
+      fx_[k] = b_f[3 * i] * depth;                                    // :108  xyz_ref = f * depth
+      fy_[k] = b_f[3 * i + 1] * depth;
+      fz_[k] = b_f[3 * i + 2] * depth;
+      fzi_[k] = 1.0 / fz_[k];
+      if (b_hp[i]) hp_mask |= 1u << k;
+      if (EVAL && P.visible_in[i]) vis_mask |= 1u << k;
+    }
+  }
+  __syncthreads();  // everyone is done with the staged blob; the stage region may be reused
+
+  const int lvl_hi = EVAL ? P.eval_level : P.max_level;
+  const int lvl_lo = EVAL ? P.eval_level : P.min_level;
+  for (int level = lvl_hi; level >= lvl_lo; --level) {
+    const int W = P.w[level], Hh = P.h[level];
+    const float scale = 1.0f / (float)(1 << level);
+    const double jscale = P.fx / (double)(1 << level);  // focal_length / (1<<level_)  (:140)
+    const uint8_t* ref_img = job.ref_lvl[level];
+    const uint8_t* cur_img = job.cur_lvl[level];
+
+    // ---- TMA: stage the current level image when it fits the staging region -----------------
+    const uint32_t img_bytes = ((uint32_t)(W * Hh) + 15u) & ~15u;
+    const bool staged = !EVAL && img_bytes + 16u <= (uint32_t)P.stage_cap;
+    if (staged && tid == 0) {
+      s.mbar_phase ^= 1u;
+      fence_proxy_async();
+      mbar_expect_tx(&s.mbar, img_bytes);
+      tma_bulk_g2s(stage, cur_img, img_bytes, &s.mbar);
+    }
+
+    // ---- precomputeReferencePatches (:84-145), one feature per thread -----------------------
+    double hsum[kPartK];
+#pragma unroll
+    for (int k = 0; k < kPartK; ++k) hsum[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < FPT; ++k) {
+      const int slot = tid + k * T;
+      const float u_ref = (float)(fpx_[k] * (double)scale);
+      const float v_ref = (float)(fpy_[k] * (double)scale);
+      const int ui = (int)floorf(u_ref), vi = (int)floorf(v_ref);
+      const bool ok = ((hp_mask >> k) & 1u) && ui - 3 >= 0 && vi - 3 >= 0 && ui + 3 < W && vi + 3 < Hh;
+      if (ok) {
+        vis_mask |= 1u << k;
+        float wtl, wtr, wbl, wbr;
+        bilin_weights(u_ref - (float)ui, v_ref - (float)vi, wtl, wtr, wbl, wbr);
+        // 7x7 footprint rows vi-3..vi+3, cols ui-3..ui+3 -> floats
+        float Pf[7][7];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+          uint32_t lo, hi;
+          fetch12<false>(ref_img, (vi - 3 + r) * W + (ui - 3), lo, hi);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) Pf[r][c] = byte_f(lo, c);
+#pragma unroll
+          for (int c = 4; c < 7; ++c) Pf[r][c] = byte_f(hi, c - 4);
+        }
+        // Bq[r][c] = bilinear blend with top-left tap P[r][c]; only the 32 needed ones are formed
+        float Bq[6][6];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int c = 0; c < 6; ++c) {
+            const bool corner = (r == 0 || r == 5) && (c == 0 || c == 5);
+            Bq[r][c] = corner ? 0.f
+                              : bilin(wtl, wtr, wbl, wbr, Pf[r][c], Pf[r][c + 1], Pf[r + 1][c], Pf[r + 1][c + 1]);
+          }
+        double sxx = 0, sxy = 0, syy = 0;
+#pragma unroll
+        for (int y = 0; y < 4; ++y)
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const int p = y * 4 + x;
+            const float val = Bq[y + 1][x + 1];
+            const float dx = __fmul_rn(0.5f, __fsub_rn(Bq[y + 1][x + 2], Bq[y + 1][x]));
+            const float dy = __fmul_rn(0.5f, __fsub_rn(Bq[y + 2][x + 1], Bq[y][x + 1]));
+            pat_ref[p * S + slot] = val;
+            pat_dx[p * S + slot] = dx;
+            pat_dy[p * S + slot] = dy;
+            sxx = fma((double)dx, (double)dx, sxx);
+            sxy = fma((double)dx, (double)dy, sxy);
+            syy = fma((double)dy, (double)dy, syy);
+          }
+        add_h(fx_[k], fy_[k], fzi_[k], sxx, sxy, syy, hsum);
+        hsum[21] += 1.0;
+      } else if ((vis_mask >> k) & 1u) {
+        // visible from a coarser level but failing here: the reference would keep the stale patch
+        // and a zeroed Jacobian (jacobian_cache_.setZero() per level, :64).  Unreachable for
+        // dyadic pyramids but kept bit-faithful.
+#pragma unroll
+        for (int p = 0; p < kPatchArea; ++p) { pat_dx[p * S + slot] = 0.f; pat_dy[p * S + slot] = 0.f; }
+        hsum[21] += 1.0;
+      }
+    }
+    block_sum_to_warp0<kPartK>(hsum, s, nwarps);
+    if (tid == 0) {
+      const double s2 = jscale * jscale;
+      int idx = 0;
+      for (int r = 0; r < 6; ++r)
+        for (int c = r; c < 6; ++c, ++idx) {
+          const double v = s.sums[idx] * s2;
+          s.Htot[r * 6 + c] = v;
+          s.Htot[c * 6 + r] = v;
+        }
+      for (int k = 0; k < 36; ++k) s.ldl_tot[k] = s.Htot[k];
+      ldlt6_factor(s.ldl_tot, s.tr_tot);
+      s.sum_vis += (int)s.sums[21];
+      s.done = 0;
+    }
+    if (staged) mbar_wait(&s.mbar, s.mbar_phase);
+    __syncthreads();
+
+    // ---- Gauss-Newton iterations at this level ---------------------------------------------
+    const int n_iter = EVAL ? 1 : P.n_iter;
+    for (int iter = 0; iter < n_iter; ++iter) {
+      double R[9], tt[3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[k] = s.R[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) tt[k] = s.t[k];
+
+      double acc[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+      in_mask = 0;
+#pragma unroll
+      for (int k = 0; k < FPT; ++k) {
+        if (!((vis_mask >> k) & 1u)) continue;
+        const int slot = tid + k * T;
+        const double x = fx_[k], y = fy_[k], z = fz_[k];
+        const double xc = fma(R[0], x, fma(R[1], y, fma(R[2], z, tt[0])));
+        const double yc = fma(R[3], x, fma(R[4], y, fma(R[5], z, tt[1])));
+        const double zc = fma(R[6], x, fma(R[7], y, fma(R[8], z, tt[2])));
+        const double ud = fma(P.fx, xc / zc, P.cx);  // [EXT] world2cam: fx * (x/z) + cx
+        const double vd = fma(P.fy, yc / zc, P.cy);
+        const float u_cur = __fmul_rn((float)ud, scale);  // .cast<float>() * scale (:183)
+        const float v_cur = __fmul_rn((float)vd, scale);
+        const bool finite = fabsf(u_cur) < 1e8f && fabsf(v_cur) < 1e8f;
+        const int ui = finite ? (int)floorf(u_cur) : -1, vi = finite ? (int)floorf(v_cur) : -1;
+        const bool in = ui >= 0 && vi >= 0 && ui - 3 >= 0 && vi - 3 >= 0 && ui + 3 < W && vi + 3 < Hh;  // :190
+        if (!in) {
+          acc[8] += 1.0;
+          if (EVAL) {
+            for (int p = 0; p < kPatchArea; ++p)
+              P.residuals_out[(size_t)slot * kPatchArea + p] = __int_as_float(0x7fc00000);
+          }
+          continue;
+        }
+        in_mask |= 1u << k;
+        float wtl, wtr, wbl, wbr;
+        bilin_weights(u_cur - (float)ui, v_cur - (float)vi, wtl, wtr, wbl, wbr);
+        float Q[5][5];
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+          uint32_t lo, hi;
+          const int off = (vi - 2 + r) * W + (ui - 2);
+          if (staged) fetch8<true>(stage, off, lo, hi);
+          else fetch8<false>(cur_img, off, lo, hi);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) Q[r][c] = byte_f(lo, c);
+          Q[r][4] = byte_f(hi, 0);
+        }
+        float c2 = 0.f, gx = 0.f, gy = 0.f;
+#pragma unroll
+        for (int yy = 0; yy < 4; ++yy)
+#pragma unroll
+          for (int xx = 0; xx < 4; ++xx) {
+            const int p = yy * 4 + xx;
+            const float I = bilin(wtl, wtr, wbl, wbr, Q[yy][xx], Q[yy][xx + 1], Q[yy + 1][xx], Q[yy + 1][xx + 1]);
+            const float res = __fsub_rn(I, pat_ref[p * S + slot]);
+            c2 = __fadd_rn(c2, __fmul_rn(res, res));  // chi2 += res*res*weight, weight == 1 (:222)
+            gx = fmaf(pat_dx[p * S + slot], res, gx);
+            gy = fmaf(pat_dy[p * S + slot], res, gy);
+            if (EVAL) P.residuals_out[(size_t)slot * kPatchArea + p] = res;
+          }
+        const double zi = fzi_[k], X = x * zi, Y = y * zi, dgx = (double)gx, dgy = (double)gy;
+        acc[0] = fma(-zi, dgx, acc[0]);
+        acc[1] = fma(-zi, dgy, acc[1]);
+        acc[2] = fma(zi, fma(X, dgx, Y * dgy), acc[2]);
+        acc[3] = fma(X * Y, dgx, fma(fma(Y, Y, 1.0), dgy, acc[3]));
+        acc[4] = fma(-fma(X, X, 1.0), dgx, fma(-(X * Y), dgy, acc[4]));
+        acc[5] = fma(Y, dgx, fma(-X, dgy, acc[5]));
+        acc[6] += (double)c2;
+        acc[7] += 1.0;
+      }
+      block_sum_to_warp0<9>(acc, s, nwarps);  // contains the first __syncthreads of the iteration
+      if (tid == 0) {
+        const int n_in = (int)s.sums[7], n_out = (int)s.sums[8];
+        for (int k = 0; k < 6; ++k) s.x[k] = -(s.sums[k] * jscale);  // Jres_ = -sum J r
+        s.sums[9] = s.sums[6];                                       // chi2 parked across the slow path
+        s.slow = (EVAL || (n_out > 0 && n_in > 0)) ? 1 : 0;
+        if (!s.slow) {
+          if (n_in == 0) {  // H_ == 0 exactly: Eigen's LDLT yields x = 0
+            for (int k = 0; k < 36; ++k) { s.Hs[k] = 0.0; s.ldl[k] = 0.0; }
+            for (int k = 0; k < 6; ++k) s.tr[k] = k;
+            gn_finish(s, P, s.ldl, s.tr, level, iter, s.sums[6], n_in);
+          } else {
+            for (int k = 0; k < 36; ++k) s.Hs[k] = s.Htot[k];
+            gn_finish(s, P, s.ldl_tot, s.tr_tot, level, iter, s.sums[6], n_in);
+          }
+        }
+      }
+      __syncthreads();
+      if (s.slow) {
+        // some visible patches fell outside the current image (or EVAL wants H): H_ = sum over the
+        // patches that contributed in this pass.
+        double hs2[kPartK];
+#pragma unroll
+        for (int k = 0; k < kPartK; ++k) hs2[k] = 0.0;
+#pragma unroll
+        for (int k = 0; k < FPT; ++k) {
+          if (!((in_mask >> k) & 1u)) continue;
+          const int slot = tid + k * T;
+          double sxx = 0, sxy = 0, syy = 0;
+#pragma unroll
+          for (int p = 0; p < kPatchArea; ++p) {
+            const double dx = (double)pat_dx[p * S + slot], dy = (double)pat_dy[p * S + slot];
+            sxx = fma(dx, dx, sxx);
+            sxy = fma(dx, dy, sxy);
+            syy = fma(dy, dy, syy);
+          }
+          add_h(fx_[k], fy_[k], fzi_[k], sxx, sxy, syy, hs2);
+        }
+        const double chi2_keep = s.sums[9];
+        const int n_in_keep = (int)s.sums[7];
+        __syncthreads();
+        block_sum_to_warp0<kPartK>(hs2, s, nwarps);
+        if (tid == 0) {
+          const double s2 = jscale * jscale;
+          int idx = 0;
+          for (int r = 0; r < 6; ++r)
+            for (int c = r; c < 6; ++c, ++idx) {
+              const double v = s.sums[idx] * s2;
+              s.Hs[r * 6 + c] = v;
+              s.Hs[c * 6 + r] = v;
+            }
+          if (EVAL) {
+            for (int k = 0; k < 6; ++k) P.Jres_out[k] = s.x[k];
+            const float chi2f = (float)chi2_keep;
+            *P.chi2_out = (double)(chi2f / (float)(n_in_keep * kPatchArea));
+            *P.n_meas_out = (long long)n_in_keep * kPatchArea;
+            s.n_in_last = n_in_keep;
+            s.done = 1;
+          } else {
+            for (int k = 0; k < 36; ++k) s.ldl[k] = s.Hs[k];
+            ldlt6_factor(s.ldl, s.tr);
+            gn_finish(s, P, s.ldl, s.tr, level, iter, chi2_keep, n_in_keep);
+          }
+        }
+        __syncthreads();
+      }
+      if (EVAL) {
+#pragma unroll
+        for (int k = 0; k < FPT; ++k) {
+          const int i = tid + k * T;
+          if (i < N) {
+            P.in_image_out[i] = (in_mask >> k) & 1u;
+            if (!((vis_mask >> k) & 1u))
+              for (int p = 0; p < kPatchArea; ++p)
+                P.residuals_out[(size_t)i * kPatchArea + p] = __int_as_float(0x7fc00000);
+            for (int p = 0; p < kPatchArea; ++p)
+              P.ref_patch_out[(size_t)i * kPatchArea + p] = pat_ref[p * S + i];
+          }
+        }
+      }
+      if (s.done) break;
+    }
+    __syncthreads();  // stage region / patches are rewritten by the next level
+  }
+
+  // ---- outputs ---------------------------------------------------------------------------------
+#pragma unroll
+  for (int k = 0; k < FPT; ++k) {
+    const int i = tid + k * T;
+    if (i < N && P.visible_out) P.visible_out[job.feat_off + i] = (vis_mask >> k) & 1u;
+  }
+  if (tid == 0) {
+    if (P.T_out) pose_to_rt12(s.model, P.T_out + 12 * (size_t)blockIdx.x);
+    if (P.H_out)
+      for (int k = 0; k < 36; ++k) P.H_out[36 * (size_t)blockIdx.x + k] = s.Hs[k];
+    if (P.stats) {
+      svo_b200_sia_stats st;
+      st.n_iters = s.n_iters; st.sum_visible = s.sum_vis; st.sum_in_image = s.sum_in;
+      st.n_tracked = s.n_in_last;  // n_meas_/patch_area_ of the last pass (:74)
+      P.stats[blockIdx.x] = st;
+    }
+    if (P.n_trace) *P.n_trace = s.n_trace;
+  }
+}
+
+// =============================================================================================
+// Host side
+// =============================================================================================
+struct SiaBatchState {
+  int B = 0;
+  int total_feat = 0;
+  int max_feat = 0;
+  SiaParams P;
+  size_t in_bytes = 0;
+  // device output offsets inside ctx->d_out
+  size_t o_T = 0, o_H = 0, o_vis = 0, o_stats = 0, out_bytes = 0;
+  int threads = 0, fpt = 1;
+  size_t smem = 0;
+  bool staged = false;
+};
+
+void sia_batch_free(svo_b200_ctx* ctx) {
+  delete ctx->sia;
+  ctx->sia = nullptr;
+}
+
+static int pick_launch(svo_b200_ctx* ctx, int max_feat, int& threads, int& fpt, int& stage_cap, size_t& smem) {
+  if (max_feat <= 512) fpt = 1;
+  else if (max_feat <= 1024) fpt = 2;
+  else if (max_feat <= 2048) fpt = 4;
+  else return set_err(ctx, SVO_B200_ELIMIT, "sparse_img_align: %d features per pair > 2048", max_feat);
+  threads = ((max_feat + fpt - 1) / fpt + 31) / 32 * 32;
+  if (threads < 32) threads = 32;
+  const size_t base = ((sizeof(SiaShared) + 15) & ~size_t(15)) + (size_t)3 * kPatchArea * threads * fpt * sizeof(float);
+  const size_t budget = (size_t)ctx->max_smem_optin;
+  if (base + 1024 > budget)
+    return set_err(ctx, SVO_B200_ELIMIT, "sparse_img_align: %d features need %zu B of shared memory", max_feat, base);
+  // staging region: feature blob (65 B / feature) and coarse level images; default 20 KB
+  size_t cap = 20480;
+  if (base + cap > budget) cap = (budget - base) & ~size_t(15);
+  stage_cap = (int)cap;
+  smem = base + cap;
+  return 0;
+}
+
+template <bool EVAL>
+static int launch_sia(svo_b200_ctx* ctx, const SiaParams& P, int B, int threads, int fpt, size_t smem) {
+  auto go = [&](auto kern) -> int {
+    SVO_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<B, threads, smem, ctx->stream>>>(P);
+    ctx->launches++;
+    SVO_CUDA_CHECK(ctx, cudaGetLastError());
+    return 0;
+  };
+  if (fpt == 1) return go(sia_kernel<1, EVAL>);
+  if (fpt == 2) return go(sia_kernel<2, EVAL>);
+  return go(sia_kernel<4, EVAL>);
+}
+
+static inline int pad16(int n) { return (n + 15) / 16 * 16; }
+
+// Pack one pair's features into the blob layout the kernel stages with TMA.
+static void pack_blob(uint8_t* dst, int n, int np, const double* px, const double* f, const double* pos,
+                      const uint8_t* hp) {
+  double* d = reinterpret_cast<double*>(dst);
+  memset(dst, 0, (size_t)np * 65);
+  memcpy(d, px, sizeof(double) * 2 * n);
+  memcpy(d + 2 * np, f, sizeof(double) * 3 * n);
+  memcpy(d + 5 * np, pos, sizeof(double) * 3 * n);
+  memcpy(dst + (size_t)np * 64, hp, n);
+}
+
+static int fill_common(svo_b200_ctx* ctx, SiaParams& P, const svo_b200_frame* fr, const svo_b200_camera* cam,
+                       const svo_b200_sia_options* opt) {
+  memset(&P, 0, sizeof(P));
+  if (opt->max_level < opt->min_level || opt->min_level < 0 || opt->max_level >= fr->n_levels)
+    return set_err(ctx, SVO_B200_EINVAL, "sparse_img_align: levels [%d,%d] outside the pyramid (%d levels)",
+                   opt->min_level, opt->max_level, fr->n_levels);
+  for (int l = 0; l < fr->n_levels; ++l) { P.w[l] = fr->w[l]; P.h[l] = fr->h[l]; }
+  P.fx = cam->fx; P.fy = cam->fy; P.cx = cam->cx; P.cy = cam->cy;
+  P.max_level = opt->max_level; P.min_level = opt->min_level; P.n_iter = opt->n_iter; P.eps = opt->eps;
+  return 0;
+}
+
+}  // namespace svo
+
+using namespace svo;
+
+extern "C" {
+
+int svo_b200_sia_batch_stage(svo_b200_ctx* ctx, int B, const svo_b200_frame* const* ref,
+                             const svo_b200_frame* const* cur, const svo_b200_camera* cam,
+                             const svo_b200_sia_options* opt, const double* T, const int* feat_offset,
+                             const double* px, const double* f, const double* point_pos,
+                             const uint8_t* has_point, const double* ref_pos) {
+  if (!ctx || B <= 0 || !ref || !cur || !cam || !opt || !T || !feat_offset || !ref_pos)
+    return set_err(ctx, SVO_B200_EINVAL, "sia_batch_stage: bad arguments");
+  cudaSetDevice(ctx->device);
+  if (!ctx->sia) ctx->sia = new SiaBatchState();
+  SiaBatchState& st = *ctx->sia;
+  st.staged = false;
+  st.B = B;
+  st.total_feat = feat_offset[B] - feat_offset[0];
+  st.max_feat = 0;
+  for (int b = 0; b < B; ++b) {
+    const int n = feat_offset[b + 1] - feat_offset[b];
+    if (n < 0) return set_err(ctx, SVO_B200_EINVAL, "sia_batch_stage: feat_offset not monotone");
+    if (n > st.max_feat) st.max_feat = n;
+    if (!ref[b] || !cur[b] || ref[b]->n_levels != ref[0]->n_levels || ref[b]->width != ref[0]->width ||
+        ref[b]->height != ref[0]->height || cur[b]->width != ref[0]->width ||
+        cur[b]->height != ref[0]->height || cur[b]->n_levels != ref[0]->n_levels)
+      return set_err(ctx, SVO_B200_EINVAL, "sia_batch_stage: all frames of a batch must share one geometry");
+  }
+  if (st.total_feat > 0 && (!px || !f || !point_pos || !has_point))
+    return set_err(ctx, SVO_B200_EINVAL, "sia_batch_stage: NULL feature arrays");
+  int rc = fill_common(ctx, st.P, ref[0], cam, opt);
+  if (rc) return rc;
+  int stage_cap = 0;
+  rc = pick_launch(ctx, st.max_feat, st.threads, st.fpt, stage_cap, st.smem);
+  if (rc) return rc;
+  st.P.stage_cap = stage_cap;
+  st.P.slots = st.threads * st.fpt;
+
+  // input staging: [jobs B][blobs]
+  Carver cin;
+  const size_t o_jobs = cin.take(sizeof(SiaJob) * (size_t)B);
+  std::vector<size_t> o_blob(B);
+  for (int b = 0; b < B; ++b) {
+    const int n = feat_offset[b + 1] - feat_offset[b];
+    o_blob[b] = cin.take((size_t)pad16(n) * 65 + 16, 128);
+  }
+  st.in_bytes = cin.off;
+  if ((rc = ensure_host(ctx, ctx->h_in, st.in_bytes))) return rc;
+  if ((rc = ensure_dev(ctx, ctx->d_in, st.in_bytes))) return rc;
+  // a previous async copy out of the pinned buffer must be finished before it is rewritten
+  SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  uint8_t* hin = static_cast<uint8_t*>(ctx->h_in.p);
+  uint8_t* din = static_cast<uint8_t*>(ctx->d_in.p);
+  SiaJob* jobs = reinterpret_cast<SiaJob*>(hin + o_jobs);
+  for (int b = 0; b < B; ++b) {
+    SiaJob& j = jobs[b];
+    memset(&j, 0, sizeof(j));
+    for (int l = 0; l < ref[b]->n_levels; ++l) { j.ref_lvl[l] = ref[b]->lvl(l); j.cur_lvl[l] = cur[b]->lvl(l); }
+    const int o = feat_offset[b], n = feat_offset[b + 1] - o;
+    j.n_feat = n;
+    j.n_pad = pad16(n);
+    j.feat_off = o - feat_offset[0];
+    j.blob = din + o_blob[b];
+    memcpy(j.T, T + 12 * (size_t)b, sizeof(double) * 12);
+    memcpy(j.ref_pos, ref_pos + 3 * (size_t)b, sizeof(double) * 3);
+    if (n > 0) pack_blob(hin + o_blob[b], n, j.n_pad, px + 2 * (size_t)o, f + 3 * (size_t)o,
+                         point_pos + 3 * (size_t)o, has_point + o);
+  }
+  SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(din, hin, st.in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+
+  Carver co;
+  st.o_T = co.take(sizeof(double) * 12 * (size_t)B);
+  st.o_H = co.take(sizeof(double) * 36 * (size_t)B);
+  st.o_stats = co.take(sizeof(svo_b200_sia_stats) * (size_t)B);
+  st.o_vis = co.take((size_t)st.total_feat + 16);
+  st.out_bytes = co.off;
+  if ((rc = ensure_dev(ctx, ctx->d_out, st.out_bytes))) return rc;
+  if ((rc = ensure_host(ctx, ctx->h_out, st.out_bytes))) return rc;
+  uint8_t* dout = static_cast<uint8_t*>(ctx->d_out.p);
+  st.P.jobs = reinterpret_cast<const SiaJob*>(din + o_jobs);
+  st.P.T_out = reinterpret_cast<double*>(dout + st.o_T);
+  st.P.H_out = reinterpret_cast<double*>(dout + st.o_H);
+  st.P.stats = reinterpret_cast<svo_b200_sia_stats*>(dout + st.o_stats);
+  st.P.visible_out = dout + st.o_vis;
+  st.staged = true;
+  return 0;
+}
+
+int svo_b200_sia_batch_run(svo_b200_ctx* ctx) {
+  if (!ctx || !ctx->sia || !ctx->sia->staged) return set_err(ctx, SVO_B200_EINVAL, "sia_batch_run: nothing staged");
+  cudaSetDevice(ctx->device);
+  SiaBatchState& st = *ctx->sia;
+  return launch_sia<false>(ctx, st.P, st.B, st.threads, st.fpt, st.smem);
+}
+
+int svo_b200_sia_batch_fetch(svo_b200_ctx* ctx, double* T_out, uint8_t* visible_out, double* H_out,
+                             svo_b200_sia_stats* stats_out) {
+  if (!ctx || !ctx->sia || !ctx->sia->staged) return set_err(ctx, SVO_B200_EINVAL, "sia_batch_fetch: nothing staged");
+  cudaSetDevice(ctx->device);
+  SiaBatchState& st = *ctx->sia;
+  SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, st.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  const uint8_t* h = static_cast<const uint8_t*>(ctx->h_out.p);
+  if (T_out) memcpy(T_out, h + st.o_T, sizeof(double) * 12 * (size_t)st.B);
+  if (H_out) memcpy(H_out, h + st.o_H, sizeof(double) * 36 * (size_t)st.B);
+  if (stats_out) memcpy(stats_out, h + st.o_stats, sizeof(svo_b200_sia_stats) * (size_t)st.B);
+  if (visible_out) memcpy(visible_out, h + st.o_vis, (size_t)st.total_feat);
+  return 0;
+}
+
+int svo_b200_sparse_img_align(svo_b200_ctx* ctx, const svo_b200_frame* ref, const svo_b200_frame* cur,
+                              const svo_b200_camera* cam, const svo_b200_sia_options* opt,
+                              double* T_io, const double* px, const double* f, const double* point_pos,
+                              const uint8_t* has_point, const double* ref_pos, int N,
+                              uint8_t* visible_out, double* H_out, svo_b200_sia_stats* stats_out,
+                              svo_b200_sia_iter* trace_out, int trace_cap, int* n_trace_out) {
+  if (!ctx || !ref || !cur || !cam || !opt || !T_io || !ref_pos || N < 0)
+    return set_err(ctx, SVO_B200_EINVAL, "sparse_img_align: bad arguments");
+  if (N == 0) {  // "SparseImgAlign: no features to track!" -> return 0 (sparse_img_align.cpp:47-51)
+    if (stats_out) memset(stats_out, 0, sizeof(*stats_out));
+    if (H_out) memset(H_out, 0, sizeof(double) * 36);
+    if (n_trace_out) *n_trace_out = 0;
+    return 0;
+  }
+  const int off[2] = {0, N};
+  int rc = svo_b200_sia_batch_stage(ctx, 1, &ref, &cur, cam, opt, T_io, off, px, f, point_pos, has_point, ref_pos);
+  if (rc) return rc;
+  SiaBatchState& st = *ctx->sia;
+  size_t o_tr = 0, o_ntr = 0;
+  if (trace_out && trace_cap > 0) {
+    Carver c;
+    o_tr = c.take(sizeof(svo_b200_sia_iter) * (size_t)trace_cap);
+    o_ntr = c.take(sizeof(int));
+    if ((rc = ensure_dev(ctx, ctx->d_scratch, c.off))) return rc;
+    uint8_t* ds = static_cast<uint8_t*>(ctx->d_scratch.p);
+    st.P.trace = reinterpret_cast<svo_b200_sia_iter*>(ds + o_tr);
+    st.P.trace_cap = trace_cap;
+    st.P.n_trace = reinterpret_cast<int*>(ds + o_ntr);
+  }
+  if ((rc = svo_b200_sia_batch_run(ctx))) return rc;
+  if ((rc = svo_b200_sia_batch_fetch(ctx, T_io, visible_out, H_out, stats_out))) return rc;
+  if (trace_out && trace_cap > 0) {
+    int ntr = 0;
+    uint8_t* ds = static_cast<uint8_t*>(ctx->d_scratch.p);
+    SVO_CUDA_CHECK(ctx, cudaMemcpy(&ntr, ds + o_ntr, sizeof(int), cudaMemcpyDeviceToHost));
+    const int ncopy = ntr < trace_cap ? ntr : trace_cap;
+    if (ncopy > 0)
+      SVO_CUDA_CHECK(ctx, cudaMemcpy(trace_out, ds + o_tr, sizeof(svo_b200_sia_iter) * (size_t)ncopy, cudaMemcpyDeviceToHost));
+    if (n_trace_out) *n_trace_out = ntr;
+  } else if (n_trace_out) {
+    *n_trace_out = 0;
+  }
+  st.P.trace = nullptr;
+  st.P.n_trace = nullptr;
+  return 0;
+}
+
+int svo_b200_sparse_residuals(svo_b200_ctx* ctx, const svo_b200_frame* ref, const svo_b200_frame* cur,
+                              const svo_b200_camera* cam, int level, const double* T, const double* px,
+                              const double* f, const double* point_pos, const uint8_t* has_point,
+                              const double* ref_pos, int N, uint8_t* visible_io, float* ref_patch_out,
+                              float* residuals_out, uint8_t* in_image_out, double* H_out, double* Jres_out,
+                              double* chi2_out, int64_t* n_meas_out) {
+  if (!ctx || !ref || !cur || !cam || !T || !ref_pos || N <= 0 || !visible_io)
+    return set_err(ctx, SVO_B200_EINVAL, "sparse_residuals: bad arguments");
+  svo_b200_sia_options opt = {level, level, 1, 1e-6};
+  const int off[2] = {0, N};
+  int rc = svo_b200_sia_batch_stage(ctx, 1, &ref, &cur, cam, &opt, T, off, px, f, point_pos, has_point, ref_pos);
+  if (rc) return rc;
+  SiaBatchState& st = *ctx->sia;
+  Carver c;
+  const size_t o_vin = c.take(N), o_rp = c.take(sizeof(float) * 16 * (size_t)st.P.slots),
+               o_res = c.take(sizeof(float) * 16 * (size_t)st.P.slots), o_in = c.take(N),
+               o_j = c.take(sizeof(double) * 6), o_c = c.take(sizeof(double)), o_n = c.take(sizeof(long long));
+  if ((rc = ensure_dev(ctx, ctx->d_scratch, c.off))) return rc;
+  uint8_t* ds = static_cast<uint8_t*>(ctx->d_scratch.p);
+  SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(ds + o_vin, visible_io, N, cudaMemcpyHostToDevice, ctx->stream));
+  SVO_CUDA_CHECK(ctx, cudaMemsetAsync(ds + o_res, 0xff, sizeof(float) * 16 * (size_t)st.P.slots, ctx->stream));
+  st.P.eval_level = level;
+  st.P.visible_in = ds + o_vin;
+  st.P.ref_patch_out = reinterpret_cast<float*>(ds + o_rp);
+  st.P.residuals_out = reinterpret_cast<float*>(ds + o_res);
+  st.P.in_image_out = ds + o_in;
+  st.P.Jres_out = reinterpret_cast<double*>(ds + o_j);
+  st.P.chi2_out = reinterpret_cast<double*>(ds + o_c);
+  st.P.n_meas_out = reinterpret_cast<long long*>(ds + o_n);
+  if ((rc = launch_sia<true>(ctx, st.P, 1, st.threads, st.fpt, st.smem))) return rc;
+  double Tdummy[12];
+  if ((rc = svo_b200_sia_batch_fetch(ctx, Tdummy, visible_io, H_out, nullptr))) return rc;
+  if (ref_patch_out) SVO_CUDA_CHECK(ctx, cudaMemcpy(ref_patch_out, ds + o_rp, sizeof(float) * 16 * (size_t)N, cudaMemcpyDeviceToHost));
+  if (residuals_out) SVO_CUDA_CHECK(ctx, cudaMemcpy(residuals_out, ds + o_res, sizeof(float) * 16 * (size_t)N, cudaMemcpyDeviceToHost));
+  if (in_image_out) SVO_CUDA_CHECK(ctx, cudaMemcpy(in_image_out, ds + o_in, N, cudaMemcpyDeviceToHost));
+  if (Jres_out) SVO_CUDA_CHECK(ctx, cudaMemcpy(Jres_out, ds + o_j, sizeof(double) * 6, cudaMemcpyDeviceToHost));
+  if (chi2_out) SVO_CUDA_CHECK(ctx, cudaMemcpy(chi2_out, ds + o_c, sizeof(double), cudaMemcpyDeviceToHost));
+  if (n_meas_out) {
+    long long nm = 0;
+    SVO_CUDA_CHECK(ctx, cudaMemcpy(&nm, ds + o_n, sizeof(long long), cudaMemcpyDeviceToHost));
+    *n_meas_out = nm;
+  }
+  st.staged = false;
+  return 0;
+}
+
+}  // extern "C"

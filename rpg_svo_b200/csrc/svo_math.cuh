@@ -1,0 +1,287 @@
+// rpg_svo_b200/csrc/svo_math.cuh -- device-side small math for the sm_100a kernels.
+//
+// SE3 as unit quaternion + translation (the storage the reference's Sophus::SE3 uses, so the two
+// sides drift the same way), Rodrigues/expmap, a 6x6 LDL^T with symmetric pivoting (the behaviour
+// of Eigen::LDLT that svo::SparseImgAlign::solve and pose_optimizer rely on:
+// svo/src/sparse_img_align.cpp:245-251, svo/src/pose_optimizer.cpp:97), and block reductions.
+// All files in csrc/ are compiled with -fmad=false: every fused multiply-add below is explicit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace svo {
+
+struct Quat {
+  double w, x, y, z;
+};
+struct Pose {  // T = [R(q) | t]
+  Quat q;
+  double t[3];
+};
+
+__device__ __forceinline__ Quat qmul(const Quat& a, const Quat& b) {
+  Quat r;
+  r.w = a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z;
+  r.x = a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y;
+  r.y = a.w * b.y + a.y * b.w + a.z * b.x - a.x * b.z;
+  r.z = a.w * b.z + a.z * b.w + a.x * b.y - a.y * b.x;
+  return r;
+}
+__device__ __forceinline__ Quat qnormalized(const Quat& q) {
+  const double n = sqrt(q.w * q.w + q.x * q.x + q.y * q.y + q.z * q.z);
+  Quat r = {q.w / n, q.x / n, q.y / n, q.z / n};
+  return r;
+}
+__device__ __forceinline__ void qmatrix(const Quat& q, double* R /*9 row-major*/) {
+  const double tx = 2 * q.x, ty = 2 * q.y, tz = 2 * q.z;
+  const double twx = tx * q.w, twy = ty * q.w, twz = tz * q.w;
+  const double txx = tx * q.x, txy = ty * q.x, txz = tz * q.x;
+  const double tyy = ty * q.y, tyz = tz * q.y, tzz = tz * q.z;
+  R[0] = 1 - (tyy + tzz); R[1] = txy - twz;       R[2] = txz + twy;
+  R[3] = txy + twz;       R[4] = 1 - (txx + tzz); R[5] = tyz - twx;
+  R[6] = txz - twy;       R[7] = tyz + twx;       R[8] = 1 - (txx + tyy);
+}
+__device__ inline Quat qfrommatrix(const double* R /*9 row-major*/) {
+  Quat q;
+  double t = R[0] + R[4] + R[8];
+  if (t > 0) {
+    t = sqrt(t + 1.0);
+    q.w = 0.5 * t;
+    t = 0.5 / t;
+    q.x = (R[7] - R[5]) * t;
+    q.y = (R[2] - R[6]) * t;
+    q.z = (R[3] - R[1]) * t;
+  } else if (R[0] >= R[4] && R[0] >= R[8]) {
+    t = sqrt(R[0] - R[4] - R[8] + 1.0);
+    q.x = 0.5 * t;
+    t = 0.5 / t;
+    q.w = (R[7] - R[5]) * t;
+    q.y = (R[3] + R[1]) * t;
+    q.z = (R[6] + R[2]) * t;
+  } else if (R[4] >= R[8]) {
+    t = sqrt(R[4] - R[8] - R[0] + 1.0);
+    q.y = 0.5 * t;
+    t = 0.5 / t;
+    q.w = (R[2] - R[6]) * t;
+    q.z = (R[7] + R[5]) * t;
+    q.x = (R[1] + R[3]) * t;
+  } else {
+    t = sqrt(R[8] - R[0] - R[4] + 1.0);
+    q.z = 0.5 * t;
+    t = 0.5 / t;
+    q.w = (R[3] - R[1]) * t;
+    q.x = (R[6] + R[2]) * t;
+    q.y = (R[7] + R[5]) * t;
+  }
+  return qnormalized(q);
+}
+__device__ __forceinline__ void qrotate(const Quat& q, const double* v, double* out) {
+  // v + 2w (qv x v) + 2 qv x (qv x v)
+  double ux = q.y * v[2] - q.z * v[1], uy = q.z * v[0] - q.x * v[2], uz = q.x * v[1] - q.y * v[0];
+  ux += ux; uy += uy; uz += uz;
+  out[0] = v[0] + q.w * ux + (q.y * uz - q.z * uy);
+  out[1] = v[1] + q.w * uy + (q.z * ux - q.x * uz);
+  out[2] = v[2] + q.w * uz + (q.x * uy - q.y * ux);
+}
+
+// SE3 exponential, tangent = [upsilon, omega] (translation first).
+__device__ inline Pose se3_exp(const double* u) {
+  const double wx = u[3], wy = u[4], wz = u[5];
+  const double th2 = wx * wx + wy * wy + wz * wz;
+  const double th = sqrt(th2);
+  double imag, real, a, b;  // a = (1-cos)/th^2, b = (th - sin)/th^3
+  if (th < 1e-10) {
+    real = 1.0 - 0.125 * th2;
+    imag = 0.5 - th2 * (1.0 / 48.0);
+    a = 0.5;
+    b = 1.0 / 6.0;
+  } else {
+    double sh, ch;
+    sincos(0.5 * th, &sh, &ch);
+    real = ch;
+    imag = sh / th;
+    if (th < 1e-2) {  // series keep full precision where the closed forms cancel
+      a = 0.5 - th2 * (1.0 / 24.0) * (1.0 - th2 * (1.0 / 30.0) * (1.0 - th2 * (1.0 / 56.0)));
+      b = (1.0 / 6.0) - th2 * (1.0 / 120.0) * (1.0 - th2 * (1.0 / 42.0) * (1.0 - th2 * (1.0 / 72.0)));
+    } else {
+      double s, c;
+      sincos(th, &s, &c);
+      a = (1.0 - c) / th2;
+      b = (th - s) / (th2 * th);
+    }
+  }
+  Pose P;
+  P.q.w = real; P.q.x = imag * wx; P.q.y = imag * wy; P.q.z = imag * wz;
+  // V = I + a*W + b*W^2,  t = V * upsilon ;  W v = w x v
+  const double cx = wy * u[2] - wz * u[1], cy = wz * u[0] - wx * u[2], cz = wx * u[1] - wy * u[0];
+  const double ccx = wy * cz - wz * cy, ccy = wz * cx - wx * cz, ccz = wx * cy - wy * cx;
+  P.t[0] = u[0] + a * cx + b * ccx;
+  P.t[1] = u[1] + a * cy + b * ccy;
+  P.t[2] = u[2] + a * cz + b * ccz;
+  return P;
+}
+
+__device__ inline Pose pose_mul(const Pose& A, const Pose& B) {
+  Pose C;
+  double r[3];
+  qrotate(A.q, B.t, r);
+  C.t[0] = A.t[0] + r[0]; C.t[1] = A.t[1] + r[1]; C.t[2] = A.t[2] + r[2];
+  C.q = qnormalized(qmul(A.q, B.q));
+  return C;
+}
+__device__ inline Pose pose_inv(const Pose& A) {
+  Pose I;
+  I.q.w = A.q.w; I.q.x = -A.q.x; I.q.y = -A.q.y; I.q.z = -A.q.z;
+  double nt[3] = {-A.t[0], -A.t[1], -A.t[2]};
+  qrotate(I.q, nt, I.t);
+  return I;
+}
+__device__ inline Pose pose_from_rt12(const double* T) {
+  double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
+  Pose P;
+  P.q = qfrommatrix(R);
+  P.t[0] = T[3]; P.t[1] = T[7]; P.t[2] = T[11];
+  return P;
+}
+__device__ inline void pose_to_rt12(const Pose& P, double* T) {
+  double R[9];
+  qmatrix(P.q, R);
+  T[0] = R[0]; T[1] = R[1]; T[2] = R[2];  T[3] = P.t[0];
+  T[4] = R[3]; T[5] = R[4]; T[6] = R[5];  T[7] = P.t[1];
+  T[8] = R[6]; T[9] = R[7]; T[10] = R[8]; T[11] = P.t[2];
+}
+
+// ------------------------------------------------------------------------------------------
+// 6x6 LDL^T with symmetric pivoting (largest remaining |diagonal|), in place on a row-major
+// 6x6 buffer `m` (lower triangle used) that may live in shared memory, plus a solve with the
+// pseudo-inverse of D.  One thread executes these; they run once per pyramid level.
+// ------------------------------------------------------------------------------------------
+__device__ inline void ldlt6_factor(double* m, int* tr) {
+  for (int k = 0; k < 6; ++k) {
+    int big = k;
+    double bigv = fabs(m[k * 6 + k]);
+    for (int i = k + 1; i < 6; ++i)
+      if (fabs(m[i * 6 + i]) > bigv) { bigv = fabs(m[i * 6 + i]); big = i; }
+    tr[k] = big;
+    if (big != k) {
+      for (int j = 0; j < k; ++j) { double s = m[k * 6 + j]; m[k * 6 + j] = m[big * 6 + j]; m[big * 6 + j] = s; }
+      for (int i = big + 1; i < 6; ++i) { double s = m[i * 6 + k]; m[i * 6 + k] = m[i * 6 + big]; m[i * 6 + big] = s; }
+      { double s = m[k * 6 + k]; m[k * 6 + k] = m[big * 6 + big]; m[big * 6 + big] = s; }
+      for (int i = k + 1; i < big; ++i) { double s = m[i * 6 + k]; m[i * 6 + k] = m[big * 6 + i]; m[big * 6 + i] = s; }
+    }
+    if (k > 0) {
+      double temp[6];
+      double acc = 0;
+      for (int j = 0; j < k; ++j) {
+        temp[j] = m[j * 6 + j] * m[k * 6 + j];
+        acc += m[k * 6 + j] * temp[j];
+      }
+      m[k * 6 + k] -= acc;
+      for (int i = k + 1; i < 6; ++i) {
+        double a2 = 0;
+        for (int j = 0; j < k; ++j) a2 += m[i * 6 + j] * temp[j];
+        m[i * 6 + k] -= a2;
+      }
+    }
+    const double akk = m[k * 6 + k];
+    const bool ok = fabs(akk) > 0.0;
+    if (k == 0 && !ok) {
+      for (int j = 0; j < 6; ++j) tr[j] = j;
+      return;
+    }
+    if (ok)
+      for (int i = k + 1; i < 6; ++i) m[i * 6 + k] /= akk;
+  }
+}
+// x (in/out) holds b on entry.  x may be in shared memory (dynamic indexing).
+__device__ inline void ldlt6_solve(const double* m, const int* tr, double* x) {
+  for (int i = 0; i < 6; ++i) { const int j = tr[i]; double s = x[i]; x[i] = x[j]; x[j] = s; }
+  for (int i = 1; i < 6; ++i) {
+    double s = x[i];
+    for (int j = 0; j < i; ++j) s = fma(-m[i * 6 + j], x[j], s);
+    x[i] = s;
+  }
+  for (int i = 0; i < 6; ++i) {
+    const double d = m[i * 6 + i];
+    x[i] = (fabs(d) > 5.562684646268003e-309) ? x[i] / d : 0.0;  // 1/DBL_MAX
+  }
+  for (int i = 4; i >= 0; --i) {
+    double s = x[i];
+    for (int j = i + 1; j < 6; ++j) s = fma(-m[j * 6 + i], x[j], s);
+    x[i] = s;
+  }
+  for (int i = 5; i >= 0; --i) { const int j = tr[i]; double s = x[i]; x[i] = x[j]; x[j] = s; }
+}
+
+// ------------------------------------------------------------------------------------------
+// Reductions: each warp folds its K doubles with __shfl_down, lane 0 parks them in shared memory.
+// ------------------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ void warp_sum(double (&v)[K]) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] += __shfl_down_sync(0xffffffffu, v[k], off);
+  }
+}
+
+// Canonical bilinear blend shared with the oracle (oracle/svo_oracle.cpp `bilin`):
+// fma(wbr,d, fma(wbl,c, fma(wtl,a, wtr*b))).
+__device__ __forceinline__ float bilin(float wtl, float wtr, float wbl, float wbr, float a, float b,
+                                       float c, float d) {
+  return fmaf(wbr, d, fmaf(wbl, c, fmaf(wtl, a, __fmul_rn(wtr, b))));
+}
+
+// Bilinear weights exactly as the reference forms them: (1.0 - su) promotes to double, the
+// product is rounded once to float (svo/src/sparse_img_align.cpp:115-120,194-199).
+__device__ __forceinline__ void bilin_weights(float su, float sv, float& wtl, float& wtr, float& wbl,
+                                              float& wbr) {
+  const double omu = 1.0 - (double)su, omv = 1.0 - (double)sv;
+  wtl = (float)(omu * omv);
+  wtr = (float)((double)su * omv);
+  wbl = (float)(omu * (double)sv);
+  wbr = __fmul_rn(su, sv);
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA (bulk async copy) + mbarrier primitives, sm_90+/sm_100a PTX.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                             uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+}  // namespace svo

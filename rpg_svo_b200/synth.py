@@ -1,0 +1,275 @@
+"""Seeded synthetic inputs for the direct-tracking hot path.
+
+A textured plane seen by a pinhole camera: both images of a frame-pair are rendered from the same
+float texture through the exact ray/plane geometry, so the ground-truth relative pose is known.
+Nothing here is part of the measured path; it only manufactures inputs of the shapes BASELINE.json
+names (there is no dataset: the reference's `sin2_tex2_h1_v8_d` cannot be downloaded).
+
+Conventions: SE3 as 3x4 row-major [R|t] float64 arrays; `T_f_w` maps world -> frame like the
+reference's `Frame::T_f_w_` (svo/include/svo/frame.h:51).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from functools import lru_cache
+
+import numpy as np
+
+
+@dataclass(frozen=True)
+class Camera:
+    """[EXT] vk::PinholeCamera without distortion."""
+
+    fx: float
+    fy: float
+    cx: float
+    cy: float
+    width: int
+    height: int
+
+    def cam2world(self, px: np.ndarray) -> np.ndarray:
+        """Pixel -> unit bearing vector (normalised), rows of px are (u, v)."""
+        px = np.asarray(px, dtype=np.float64)
+        xyz = np.stack([(px[..., 0] - self.cx) / self.fx, (px[..., 1] - self.cy) / self.fy,
+                        np.ones(px.shape[:-1])], axis=-1)
+        return xyz / np.linalg.norm(xyz, axis=-1, keepdims=True)
+
+    def world2cam(self, xyz: np.ndarray) -> np.ndarray:
+        xyz = np.asarray(xyz, dtype=np.float64)
+        return np.stack([self.fx * xyz[..., 0] / xyz[..., 2] + self.cx,
+                         self.fy * xyz[..., 1] / xyz[..., 2] + self.cy], axis=-1)
+
+
+def camera_for(width: int, height: int) -> Camera:
+    """Cameras of SURVEY.md 8d: 640x480 f=320; 752x480 as the reference tests; 1080p f=960."""
+    if (width, height) == (752, 480):
+        return Camera(315.5, 315.5, 376.0, 240.0, 752, 480)  # svo/test/test_sparse_img_align.cpp:50
+    f = width / 2.0
+    return Camera(f, f, width / 2.0, height / 2.0, width, height)
+
+
+# ------------------------------------------------------------------------------------------ SE3
+def hat(w: np.ndarray) -> np.ndarray:
+    return np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]], dtype=np.float64)
+
+
+def se3_exp(x: np.ndarray) -> np.ndarray:
+    """Tangent [upsilon, omega] (translation first, as Sophus) -> 3x4 [R|t] (numpy re-derivation)."""
+    x = np.asarray(x, dtype=np.float64)
+    ups, om = x[:3], x[3:]
+    th = np.linalg.norm(om)
+    O = hat(om)
+    if th < 1e-12:
+        R = np.eye(3) + O
+        V = np.eye(3) + 0.5 * O
+    else:
+        a = np.sin(th) / th
+        b = (1 - np.cos(th)) / th ** 2
+        c = (th - np.sin(th)) / th ** 3
+        R = np.eye(3) + a * O + b * O @ O
+        V = np.eye(3) + b * O + c * O @ O
+    T = np.zeros((3, 4))
+    T[:, :3] = R
+    T[:, 3] = V @ ups
+    return T
+
+
+def se3_mul(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    C = np.zeros((3, 4))
+    C[:, :3] = A[:, :3] @ B[:, :3]
+    C[:, 3] = A[:, :3] @ B[:, 3] + A[:, 3]
+    return C
+
+
+def se3_inv(A: np.ndarray) -> np.ndarray:
+    C = np.zeros((3, 4))
+    C[:, :3] = A[:, :3].T
+    C[:, 3] = -A[:, :3].T @ A[:, 3]
+    return C
+
+
+def se3_identity() -> np.ndarray:
+    return np.hstack([np.eye(3), np.zeros((3, 1))])
+
+
+def pose_error(T_a: np.ndarray, T_b: np.ndarray) -> tuple[float, float]:
+    """(|t_a - t_b|, rotation angle of R_a R_b^T) -- the pose metric of SURVEY.md 8d."""
+    dt = float(np.linalg.norm(T_a[:, 3] - T_b[:, 3]))
+    R = T_a[:, :3] @ T_b[:, :3].T
+    c = np.clip((np.trace(R) - 1) / 2, -1.0, 1.0)
+    s = np.linalg.norm([R[2, 1] - R[1, 2], R[0, 2] - R[2, 0], R[1, 0] - R[0, 1]]) / 2
+    return dt, float(np.arctan2(s, c))
+
+
+# ------------------------------------------------------------------------------------- texture
+TEXELS_PER_M = 320.0  # 1 texel = 3.125 mm; at 2 m and f=320 one level-0 pixel = 2 texels
+TEX_SIZE = 2560       # 8 m x 8 m of plane
+
+
+@lru_cache(maxsize=4)
+def make_texture(seed: int) -> np.ndarray:
+    """Band-limited noise with energy in every octave a 5-6 level pyramid can see."""
+    from scipy.ndimage import gaussian_filter
+
+    from scipy.ndimage import zoom
+
+    rng = np.random.default_rng(seed)
+    tex = np.zeros((TEX_SIZE, TEX_SIZE), dtype=np.float32)
+    for sigma, amp in ((2.0, 1.0), (5.0, 1.0), (12.0, 1.2), (30.0, 1.4), (70.0, 1.6)):
+        # large octaves are synthesised at reduced resolution and bilinearly upsampled (cheap, and
+        # still band-limited): sigma_lowres stays ~2.5 texels
+        k = max(1, int(sigma // 2.5))
+        m = TEX_SIZE // k + 2
+        n = rng.standard_normal((m, m) if k > 1 else (TEX_SIZE, TEX_SIZE)).astype(np.float32)
+        g = gaussian_filter(n, sigma / k, mode="wrap")
+        if k > 1:
+            g = zoom(g, k, order=1)[:TEX_SIZE, :TEX_SIZE]
+        tex += amp * g / g.std()
+    tex -= tex.min()
+    tex *= 255.0 / tex.max()
+    return tex
+
+
+@dataclass(frozen=True)
+class Plane:
+    """World plane n.X = d with an in-plane orthonormal basis for texture lookup."""
+
+    n: np.ndarray
+    d: float
+    e1: np.ndarray
+    e2: np.ndarray
+
+    @staticmethod
+    def tilted(tilt_x: float = 0.03, tilt_y: float = -0.02) -> "Plane":
+        n = np.array([np.sin(tilt_y), -np.sin(tilt_x), 1.0])
+        n /= np.linalg.norm(n)
+        e1 = np.cross([0.0, 1.0, 0.0], n)
+        e1 /= np.linalg.norm(e1)
+        e2 = np.cross(n, e1)
+        return Plane(n, 0.0, e1, e2)
+
+
+def intersect(plane: Plane, T_f_w: np.ndarray, bearing: np.ndarray) -> np.ndarray:
+    """World points where rays (frame bearings, any scale) hit the plane."""
+    R, t = T_f_w[:, :3], T_f_w[:, 3]
+    o = -R.T @ t
+    d = bearing @ R  # rows: R^T f
+    lam = (plane.d - plane.n @ o) / (d @ plane.n)
+    return o[None, :] + lam[:, None] * d
+
+
+def render(cam: Camera, T_f_w: np.ndarray, plane: Plane, tex: np.ndarray) -> np.ndarray:
+    """Exact plane render (bilinear texture lookup, rounded to u8)."""
+    u, v = np.meshgrid(np.arange(cam.width, dtype=np.float64), np.arange(cam.height, dtype=np.float64))
+    rays = np.stack([(u.ravel() - cam.cx) / cam.fx, (v.ravel() - cam.cy) / cam.fy,
+                     np.ones(u.size)], axis=1)
+    X = intersect(plane, T_f_w, rays)
+    s = (X @ plane.e1) * TEXELS_PER_M + TEX_SIZE / 2
+    t = (X @ plane.e2) * TEXELS_PER_M + TEX_SIZE / 2
+    s = np.clip(s, 0, TEX_SIZE - 1.001)
+    t = np.clip(t, 0, TEX_SIZE - 1.001)
+    s0 = np.floor(s).astype(np.int64)
+    t0 = np.floor(t).astype(np.int64)
+    fs = (s - s0).astype(np.float32)
+    ft = (t - t0).astype(np.float32)
+    a = tex[t0, s0]
+    b = tex[t0, s0 + 1]
+    c = tex[t0 + 1, s0]
+    d = tex[t0 + 1, s0 + 1]
+    val = (a * (1 - fs) + b * fs) * (1 - ft) + (c * (1 - fs) + d * fs) * ft
+    return np.clip(np.rint(val), 0, 255).astype(np.uint8).reshape(cam.height, cam.width)
+
+
+def half_sample(img: np.ndarray) -> np.ndarray:
+    """[EXT] vk::halfSample scalar rule (a+b+c+d)/4, integer division (svo/src/frame.cpp:156-165)."""
+    h, w = img.shape[0] // 2, img.shape[1] // 2
+    i = img[: 2 * h, : 2 * w].astype(np.uint16)
+    return ((i[0::2, 0::2] + i[0::2, 1::2] + i[1::2, 0::2] + i[1::2, 1::2]) // 4).astype(np.uint8)
+
+
+def build_pyramid(img: np.ndarray, n_levels: int) -> list[np.ndarray]:
+    pyr = [np.ascontiguousarray(img)]
+    for _ in range(1, n_levels):
+        pyr.append(np.ascontiguousarray(half_sample(pyr[-1])))
+    return pyr
+
+
+# ------------------------------------------------------------------------------------ datasets
+def base_pose() -> np.ndarray:
+    """Camera 2 m above the plane looking down (as test scenes: t_w=(0.11,0.11,2.0),
+    svo/test/test_matcher.cpp:52), slightly rotated."""
+    R_w_f = np.diag([1.0, -1.0, -1.0]) @ se3_exp(np.array([0, 0, 0, 0.02, -0.03, 0.05]))[:, :3]
+    T_w_f = np.hstack([R_w_f, np.array([[0.11], [0.11], [2.0]])])
+    return se3_inv(T_w_f)
+
+
+def jittered_features(rng: np.random.Generator, cam: Camera, n: int, margin: float) -> np.ndarray:
+    """n sub-pixel feature positions on a jittered grid inside `margin` px from the border."""
+    w, h = cam.width - 2 * margin, cam.height - 2 * margin
+    nx = max(1, int(round(np.sqrt(n * w / h))))
+    ny = int(np.ceil(n / nx))
+    cw, ch = w / nx, h / ny
+    idx = np.arange(nx * ny)
+    rng.shuffle(idx)
+    idx = np.sort(idx[:n])
+    gx, gy = idx % nx, idx // nx
+    px = np.stack([margin + (gx + rng.uniform(0.05, 0.95, n)) * cw,
+                   margin + (gy + rng.uniform(0.05, 0.95, n)) * ch], axis=1)
+    return px
+
+
+def features_for(rng, cam: Camera, T_f_w: np.ndarray, plane: Plane, n: int, max_level: int,
+                 null_fraction: float = 0.02) -> dict:
+    px = jittered_features(rng, cam, n, margin=4.0 * (1 << max_level))
+    f = cam.cam2world(px)
+    pos = intersect(plane, T_f_w, f)
+    has_point = np.ones(n, dtype=np.uint8)
+    k = int(round(null_fraction * n))
+    if k:
+        has_point[rng.choice(n, size=k, replace=False)] = 0
+    return dict(px=np.ascontiguousarray(px), f=np.ascontiguousarray(f),
+                pos=np.ascontiguousarray(pos), has_point=has_point)
+
+
+def make_frame_pair(seed: int, width: int = 640, height: int = 480, n_feat: int = 300,
+                    n_levels: int = 5, trans: float = 0.03, rot_deg: float = 0.5,
+                    tex_seed: int = 7) -> dict:
+    """One (ref, cur) pair of SURVEY.md 8d: GT motion uniform in +-trans m, +-rot_deg degrees."""
+    rng = np.random.default_rng(seed)
+    cam = camera_for(width, height)
+    plane = Plane.tilted()
+    tex = make_texture(tex_seed)
+    T_ref_w = se3_mul(se3_exp(np.concatenate([rng.uniform(-0.2, 0.2, 3), rng.uniform(-0.03, 0.03, 3)])),
+                      base_pose())
+    xi = np.concatenate([rng.uniform(-trans, trans, 3), np.deg2rad(rng.uniform(-rot_deg, rot_deg, 3))])
+    T_cur_ref = se3_exp(xi)
+    T_cur_w = se3_mul(T_cur_ref, T_ref_w)
+    ref_pyr = build_pyramid(render(cam, T_ref_w, plane, tex), n_levels)
+    cur_pyr = build_pyramid(render(cam, T_cur_w, plane, tex), n_levels)
+    feats = features_for(rng, cam, T_ref_w, plane, n_feat, n_levels - 1)
+    ref_pos = se3_inv(T_ref_w)[:, 3].copy()
+    return dict(cam=cam, ref_pyr=ref_pyr, cur_pyr=cur_pyr, T_ref_w=T_ref_w, T_cur_w=T_cur_w,
+                T_cur_ref_gt=T_cur_ref, ref_pos=ref_pos, n_levels=n_levels, seed=seed, **feats)
+
+
+def make_stream(seed: int, n_frames: int, width: int = 640, height: int = 480, n_feat: int = 300,
+                n_levels: int = 5, trans: float = 0.02, rot_deg: float = 0.35, tex_seed: int = 7) -> dict:
+    """One synthetic camera stream: n_frames poses on a bounded random walk; frame k is the
+    reference of pair k and the current frame of pair k-1 (as in FrameHandlerMono::processFrame,
+    svo/src/frame_handler_mono.cpp:129-139, where last_frame_ is the reference)."""
+    rng = np.random.default_rng(seed)
+    cam = camera_for(width, height)
+    plane = Plane.tilted()
+    tex = make_texture(tex_seed)
+    T = base_pose()
+    frames, poses, feats = [], [], []
+    drift = np.zeros(6)
+    for k in range(n_frames):
+        poses.append(T)
+        frames.append(build_pyramid(render(cam, T, plane, tex), n_levels))
+        feats.append(features_for(rng, cam, T, plane, n_feat, n_levels - 1))
+        xi = np.concatenate([rng.uniform(-trans, trans, 3), np.deg2rad(rng.uniform(-rot_deg, rot_deg, 3))])
+        xi -= 0.2 * drift  # pull back towards the start so the walk stays over the texture
+        drift += xi
+        T = se3_mul(se3_exp(xi), T)
+    return dict(cam=cam, frames=frames, poses=poses, feats=feats, n_levels=n_levels, seed=seed)
