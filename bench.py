@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py -- SparseImgAlign frames/sec on the BASELINE.json workload (C1), one process per GPU.
+
+Workload (config.workload): one synthetic 640x480 camera stream per GPU, 300 features per frame,
+pyramid levels 4..0, <=30 Gauss-Newton iterations per level (BASELINE.json configs[1]).  A *step* is
+one pass of svo::SparseImgAlign::run over a window of `pairs_per_gpu` consecutive frame pairs of the
+stream (frame k is the reference of pair k and the current frame of pair k-1); every pair starts from
+the identity relative pose, so the pairs of a window are independent and map to one CTA each.
+
+Two timed legs per run (CUDA events on the library's stream, barrier + sync on both sides, max over
+ranks):
+  value : pyramids + feature records already resident in HBM; K launches of the alignment kernel.
+  e2e   : through the C ABI with HOST (pinned) buffers: per step every frame's level-0 image is
+          copied host->device and its pyramid built on the GPU, features are packed + copied, the
+          kernel runs, poses / masks / counters are copied back.
+`--impl reference` times the CPU oracle port (the reference cannot be built here: Eigen, OpenCV,
+Sophus, vikit, Boost are absent) on all host cores, on a bounded sample of the same pairs.
+
+L2 policy: inputs larger than L2 (592 pairs x 2 pyramids ~ 243 MB of distinct images per step vs
+126 MB of L2); no explicit flush.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SparseImgAlign frames/sec at 640x480/300 feats/5 lvls; pose RMSE vs ref"
+UNIT = "frames/s"
+W, H, NFEAT, NLEVELS, MAX_LEVEL, MIN_LEVEL, NITER = 640, 480, 300, 5, 4, 0, 30
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs-per-gpu", type=int, default=592)
+    ap.add_argument("--cpu-sample", type=int, default=256, help="pairs timed by the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, val in zip(names, r[3:7]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def algorithmic_bytes(stats, n_feat: int) -> float:
+    """Compulsory bytes of one frame pair (DESIGN.md 'algorithmic bytes'; SURVEY.md 8d adapted to
+    this kernel's records): 49 B ref footprint per visible patch per level, 65 B feature record once,
+    25 B current-image footprint per in-image patch per residual pass, pose in/out + H + counters +
+    visibility mask out."""
+    return (49.0 * float(stats["sum_visible"]) + 65.0 * n_feat + 25.0 * float(stats["sum_in_image"]) +
+            96 + 96 + 288 + 16 + n_feat)
+
+
+def make_inputs(rank: int, B: int, device: str):
+    from rpg_svo_b200 import synth
+
+    st = synth.make_stream_fast(1000 + rank, B + 1, W, H, NFEAT, NLEVELS, device=device)
+    feats = st["feats"]
+    px = np.concatenate([feats[k]["px"] for k in range(B)])
+    f = np.concatenate([feats[k]["f"] for k in range(B)])
+    pos = np.concatenate([feats[k]["pos"] for k in range(B)])
+    hp = np.concatenate([feats[k]["has_point"] for k in range(B)])
+    off = np.arange(B + 1, dtype=np.int32) * NFEAT
+    ref_pos = np.stack([synth.se3_inv(st["poses"][k])[:, 3] for k in range(B)])
+    T0 = np.tile(synth.se3_identity()[None], (B, 1, 1))
+    T_gt = np.stack([synth.se3_mul(st["poses"][k + 1], synth.se3_inv(st["poses"][k])) for k in range(B)])
+    return dict(cam=st["cam"], level0=st["level0"], px=px, f=f, pos=pos, hp=hp, off=off, ref_pos=ref_pos,
+                T0=T0, T_gt=T_gt)
+
+
+def oracle_pair(ob, synth, inp, pyr_cache, k):
+    def pyr(i):
+        if i not in pyr_cache:
+            pyr_cache[i] = synth.build_pyramid(inp["level0"][i].numpy(), NLEVELS)
+        return pyr_cache[i]
+
+    s = slice(k * NFEAT, (k + 1) * NFEAT)
+    return pyr(k), pyr(k + 1), s
+
+
+def run_reference(args, rank: int, world: int):
+    """CPU arm: the oracle port on all host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import binding as ob
+    from rpg_svo_b200 import synth
+
+    ob.build()
+    cores = os.cpu_count() or 1
+    sample = min(args.pairs_per_gpu, max(cores, 128))
+    inp = make_inputs(0, sample, "cuda" if _has_cuda() else "cpu")
+    pyrs = [synth.build_pyramid(inp["level0"][i].numpy(), NLEVELS) for i in range(sample + 1)]
+
+    def one(k):
+        s = slice(k * NFEAT, (k + 1) * NFEAT)
+        r = ob.sparse_img_align(pyrs[k], pyrs[k + 1], inp["cam"], inp["T0"][k], inp["px"][s], inp["f"][s],
+                                inp["pos"][s], inp["hp"][s], inp["ref_pos"][k], MAX_LEVEL, MIN_LEVEL, NITER,
+                                want_trace=False)
+        return r["T"]
+
+    with ThreadPoolExecutor(max_workers=cores) as ex:
+        for _ in range(args.warmup):
+            list(ex.map(one, range(sample)))
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            list(ex.map(one, range(sample)))
+        dt = time.perf_counter() - t0
+    fps = sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64",
+            "data": "synthetic",
+            "config": {"workload": "C1 single stream 640x480 / 300 feats / levels 4..0 / 30 GN iters",
+                       "pairs_per_step": sample, "note": "CPU oracle port of svo::SparseImgAlign::run; the "
+                       "reference itself cannot be built here (Eigen/OpenCV/Sophus/vikit absent)"},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} frame pairs of the step x {args.steps} steps, {cores} threads"},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def _has_cuda() -> bool:
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from rpg_svo_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the CUDA path is the only path (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B, K, Wm = args.pairs_per_gpu, args.steps, args.warmup
+
+    inp = make_inputs(rank, B, f"cuda:{local_rank}")
+    ctx = capi.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
+    host_l0 = inp["level0"].pin_memory()  # [B+1, H, W] uint8, the HOST buffers of the e2e leg
+    pool = capi.FramePool(ctx, W, H, NLEVELS, B + 1)  # one slab: one strided H2D copy per window
+    frames = pool.frames
+    frame_bytes = W * H
+
+    def upload_all():
+        pool.upload(0, B + 1, host_l0.data_ptr(), frame_bytes)
+
+    def stage():
+        ctx.sia_batch_stage(frames[:B], frames[1:], inp["cam"], inp["T0"], inp["off"], inp["px"], inp["f"],
+                            inp["pos"], inp["hp"], inp["ref_pos"], MAX_LEVEL, MIN_LEVEL, NITER)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ctx.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- leg 1: device-resident (value) ----------------
+    upload_all()
+    stage()
+    for _ in range(max(Wm, 3)):
+        ctx.sia_batch_run()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        ctx.sia_batch_run()
+    e1.record(stream)
+    barrier()
+    launches = ctx.launch_count() - l0
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    res = ctx.sia_batch_fetch()
+    stats = res["stats"]
+    alg_bytes = sum(algorithmic_bytes(stats[b], NFEAT) for b in range(B))
+    kernel_ms = ms_dev / K
+    value = world * B * K / (ms_dev * 1e-3)
+
+    # ---------------- pose RMSE vs the oracle on a sample (not timed) ----------------
+    rmse = None
+    if rank == 0:
+        from oracle import binding as ob  # checker only
+        from rpg_svo_b200 import synth
+
+        ob.build()
+        idx = list(range(0, B, max(1, B // 16)))[:16]
+        et, er, gt_t = [], [], []
+        for k in idx:
+            s = slice(k * NFEAT, (k + 1) * NFEAT)
+            pr = synth.build_pyramid(inp["level0"][k].numpy(), NLEVELS)
+            pc = synth.build_pyramid(inp["level0"][k + 1].numpy(), NLEVELS)
+            o = ob.sparse_img_align(pr, pc, inp["cam"], inp["T0"][k], inp["px"][s], inp["f"][s], inp["pos"][s],
+                                    inp["hp"][s], inp["ref_pos"][k], MAX_LEVEL, MIN_LEVEL, NITER, want_trace=False)
+            a, b_ = synth.pose_error(res["T"][k], o["T"])
+            et.append(a); er.append(b_)
+            gt_t.append(synth.pose_error(res["T"][k], inp["T_gt"][k])[0])
+        rmse = {"trans_m": float(np.sqrt(np.mean(np.square(et)))), "rot_rad": float(np.sqrt(np.mean(np.square(er)))),
+                "pairs": len(idx), "gpu_vs_ground_truth_trans_m": float(np.sqrt(np.mean(np.square(gt_t))))}
+
+    # ---------------- leg 2: end to end through the C ABI with host buffers ----------------
+    e2e = None
+    if not args.no_e2e:
+        def e2e_step():
+            upload_all()
+            stage()
+            ctx.sia_batch_run()
+            return ctx.sia_batch_fetch()
+
+        for _ in range(max(Wm, 3)):
+            e2e_step()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(K):
+            out = e2e_step()
+        s1.record(stream)
+        barrier()
+        ms_e2e = max_over_ranks(s0.elapsed_time(s1))
+        # level-0 images + per-pair job descriptor (272 B) + packed feature blob (65 B x padded N)
+        h2d = (B + 1) * frame_bytes + B * (272 + ((NFEAT + 15) // 16 * 16) * 65)
+        d2h = B * (96 + 288 + 16) + B * NFEAT
+        e2e = {"value": world * B * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / K}
+
+    # ---------------- CPU baseline (rank 0, N == 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import binding as ob
+        from rpg_svo_b200 import synth
+
+        n = min(args.cpu_sample, B)
+        pyrs = [synth.build_pyramid(inp["level0"][i].numpy(), NLEVELS) for i in range(n + 1)]
+
+        def one(k):
+            s = slice(k * NFEAT, (k + 1) * NFEAT)
+            ob.sparse_img_align(pyrs[k], pyrs[k + 1], inp["cam"], inp["T0"][k], inp["px"][s], inp["f"][s],
+                                inp["pos"][s], inp["hp"][s], inp["ref_pos"][k], MAX_LEVEL, MIN_LEVEL, NITER,
+                                want_trace=False)
+
+        for k in range(min(8, n)):
+            one(k)
+        reps = 0
+        t0 = time.perf_counter()
+        while True:
+            for k in range(n):
+                one(k)
+            reps += 1
+            if time.perf_counter() - t0 > 10.0 or reps >= 20:
+                break
+        dt = time.perf_counter() - t0
+        cpu = {"value": n * reps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"first {n} frame pairs of the step x {reps} passes, single thread, {os.cpu_count()} host cores present"}
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+        traffic = None
+        prof = os.path.join(ROOT, "profiles", "sia_kernel_dram.json")
+        if os.path.exists(prof):
+            pj = json.load(open(prof))
+            if pj.get("pairs_per_launch") == B:
+                traffic = pj.get("dram_bytes_per_launch")
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": max(Wm, 3),
+                "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32 interpolation/residuals + f64 geometry/normal equations (as the reference)",
+                "data": "synthetic",
+                "config": {"workload": "C1 single stream 640x480 / 300 feats / levels 4..0 / 30 GN iters",
+                           "pairs_per_step_per_gpu": B, "parallelism": f"{world} independent streams, no collective",
+                           "l2_policy": "inputs larger than L2 (distinct pyramids per pair, ~%d MB/step/GPU)" % ((B + 1) * 409200 // 1000000)},
+                "pose_rmse_vs_ref": rmse,
+                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "svo::sia_kernel<1,false>",
+                             "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
+                             "mean_gn_iterations_per_pair": float(np.mean(stats["n_iters"]))},
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    pool.destroy()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -75,6 +75,21 @@ int svo_b200_frame_download_level(svo_b200_ctx* ctx, const svo_b200_frame* frame
                                   uint8_t* out);
 void svo_b200_frame_destroy(svo_b200_ctx* ctx, svo_b200_frame* frame);
 
+/* A pool = `count` frames of one geometry in ONE device slab (constant stride), so that a window of
+ * a camera stream is uploaded with a single strided host->device copy and its pyramids are built by a
+ * single fused kernel (levels 1..4 from one read of level 0).  Frames obtained from a pool are
+ * borrowed handles: valid until the pool is destroyed, never passed to svo_b200_frame_destroy. */
+typedef struct svo_b200_frame_pool svo_b200_frame_pool;
+int svo_b200_frame_pool_create(svo_b200_ctx* ctx, int width, int height, int n_levels, int count,
+                               svo_b200_frame_pool** pool_out);
+svo_b200_frame* svo_b200_frame_pool_get(svo_b200_frame_pool* pool, int index);
+/* Upload level 0 of frames [first, first+count) from host memory (image i at level0_host +
+ * i*host_stride_bytes, row pitch == width) and build their pyramids.  Asynchronous on the context
+ * stream when the host memory is pinned. */
+int svo_b200_frame_pool_upload(svo_b200_ctx* ctx, svo_b200_frame_pool* pool, int first, int count,
+                               const uint8_t* level0_host, size_t host_stride_bytes);
+void svo_b200_frame_pool_destroy(svo_b200_ctx* ctx, svo_b200_frame_pool* pool);
+
 /* ------------------------------------------------------------------ SparseImgAlign ------ */
 typedef struct {
   int max_level, min_level; /* coarsest / finest pyramid level (ctor args) */

@@ -75,6 +75,10 @@ def load() -> C.CDLL:
             getattr(_lib, name).argtypes = [C.c_void_p]
         _lib.svo_b200_frame_destroy.argtypes = [C.c_void_p, C.c_void_p]
         _lib.svo_b200_frame_destroy.restype = None
+        _lib.svo_b200_frame_pool_destroy.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.svo_b200_frame_pool_destroy.restype = None
+        _lib.svo_b200_frame_pool_get.argtypes = [C.c_void_p, C.c_int]
+        _lib.svo_b200_frame_pool_get.restype = C.c_void_p
         _lib.svo_b200_destroy.restype = None
     return _lib
 
@@ -127,9 +131,9 @@ class Frame:
         return out
 
     def destroy(self):
-        if self.h:
+        if self.h and not getattr(self, "borrowed", False):
             self.ctx.lib.svo_b200_frame_destroy(self.ctx.h, self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:
@@ -137,6 +141,42 @@ class Frame:
                 self.destroy()
         except Exception:
             pass
+
+
+class FramePool:
+    """`count` frames of one geometry in one device slab: one strided H2D copy + one fused pyramid
+    kernel per upload (svo_b200_frame_pool_*)."""
+
+    def __init__(self, ctx: "Context", width: int, height: int, n_levels: int, count: int):
+        self.ctx, self.width, self.height, self.n_levels, self.count = ctx, width, height, n_levels, count
+        h = C.c_void_p()
+        ctx._check(ctx.lib.svo_b200_frame_pool_create(ctx.h, width, height, n_levels, count, C.byref(h)))
+        self.h = h
+        self.frames = []
+        for i in range(count):
+            f = Frame.__new__(Frame)
+            f.ctx, f.width, f.height, f.n_levels = ctx, width, height, n_levels
+            f.h = C.c_void_p(ctx.lib.svo_b200_frame_pool_get(self.h, i))
+            f.borrowed = True
+            self.frames.append(f)
+
+    def upload(self, first: int, count: int, host_ptr: int, host_stride: int) -> None:
+        """Asynchronous when `host_ptr` is pinned memory; the caller keeps it alive."""
+        self.ctx._check(self.ctx.lib.svo_b200_frame_pool_upload(self.ctx.h, self.h, first, count,
+                                                                C.c_void_p(host_ptr), C.c_size_t(host_stride)))
+
+    def upload_array(self, imgs: np.ndarray, first: int = 0) -> None:
+        imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
+        assert imgs.shape[1:] == (self.height, self.width)
+        self.upload(first, imgs.shape[0], imgs.ctypes.data, self.height * self.width)
+        self.ctx.synchronize()
+
+    def destroy(self):
+        if self.h:
+            for f in self.frames:
+                f.h = None
+            self.ctx.lib.svo_b200_frame_pool_destroy(self.ctx.h, self.h)
+            self.h = None
 
 
 class Context:

@@ -80,6 +80,92 @@ __global__ void half_sample_kernel(const uint8_t* __restrict__ in, int in_w, int
   }
 }
 
+
+// Fused pyramid build for a batch of frames laid out with a constant stride: one CTA turns a
+// 128x16 tile of level 0 into the matching 64x8 / 32x4 / 16x2 / 8x1 tiles of levels 1..4 (as many as
+// the frame has), reading level 0 from HBM exactly once.  Same arithmetic as half_sample_kernel
+// (level l+1 = (a+b+c+d)/4 of level l), so the result is identical to the level-by-level build.
+struct PyrGeom {
+  int w[SVO_B200_MAX_LEVELS], h[SVO_B200_MAX_LEVELS];
+  unsigned long long off[SVO_B200_MAX_LEVELS];
+  int n_levels;
+  int tiles_x;
+};
+__global__ void __launch_bounds__(128) pyramid_fused_kernel(uint8_t* __restrict__ slab, size_t stride, int first,
+                                                            PyrGeom g) {
+  __shared__ __align__(16) uint8_t t0[16][128];
+  __shared__ __align__(16) uint8_t t1[8][64];
+  __shared__ __align__(16) uint8_t t2[4][32];
+  __shared__ __align__(16) uint8_t t3[2][16];
+  uint8_t* fr = slab + (size_t)(first + blockIdx.y) * stride;
+  const int tx = blockIdx.x % g.tiles_x, ty = blockIdx.x / g.tiles_x;
+  const int t = threadIdx.x;
+  const int W0 = g.w[0], H0 = g.h[0];
+  {  // level-0 tile -> shared (16 B per thread)
+    const int r = t >> 3, c = (t & 7) * 16;
+    const int y = ty * 16 + r, x = tx * 128 + c;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y < H0) {
+      const uint8_t* src = fr + g.off[0] + (size_t)y * W0 + x;
+      if (x + 16 <= W0 && ((W0 & 15) == 0)) {
+        v = *reinterpret_cast<const uint4*>(src);
+      } else {
+        uint8_t tmp[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) tmp[k] = (x + k < W0) ? src[k] : 0;
+        v = *reinterpret_cast<uint4*>(tmp);
+      }
+    }
+    *reinterpret_cast<uint4*>(&t0[r][c]) = v;
+  }
+  __syncthreads();
+  if (g.n_levels > 1) {  // level 1: 8 x 64, four pixels per thread
+    const int r = t >> 4, c = (t & 15) * 4;
+    const uint2 a = *reinterpret_cast<const uint2*>(&t0[2 * r][2 * c]);
+    const uint2 b = *reinterpret_cast<const uint2*>(&t0[2 * r + 1][2 * c]);
+    const uint32_t aw[2] = {a.x, a.y}, bw[2] = {b.x, b.y};
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t tt = aw[k >> 1] >> ((k & 1) * 16), bb = bw[k >> 1] >> ((k & 1) * 16);
+      o |= (((tt & 0xff) + ((tt >> 8) & 0xff) + (bb & 0xff) + ((bb >> 8) & 0xff)) >> 2) << (8 * k);
+    }
+    *reinterpret_cast<uint32_t*>(&t1[r][c]) = o;
+    const int y = ty * 8 + r, x = tx * 64 + c, W1 = g.w[1];
+    if (y < g.h[1]) {
+      uint8_t* dst = fr + g.off[1] + (size_t)y * W1 + x;
+      if (x + 4 <= W1 && ((W1 & 3) == 0)) *reinterpret_cast<uint32_t*>(dst) = o;
+      else
+        for (int k = 0; k < 4; ++k)
+          if (x + k < W1) dst[k] = (uint8_t)(o >> (8 * k));
+    }
+  }
+  __syncthreads();
+  if (g.n_levels > 2) {  // level 2: 4 x 32
+    const int r = t >> 5, c = t & 31;
+    const uint32_t sum = (uint32_t)t1[2 * r][2 * c] + t1[2 * r][2 * c + 1] + t1[2 * r + 1][2 * c] + t1[2 * r + 1][2 * c + 1];
+    const uint8_t o = (uint8_t)(sum >> 2);
+    t2[r][c] = o;
+    const int y = ty * 4 + r, x = tx * 32 + c;
+    if (y < g.h[2] && x < g.w[2]) fr[g.off[2] + (size_t)y * g.w[2] + x] = o;
+  }
+  __syncthreads();
+  if (g.n_levels > 3 && t < 32) {  // level 3: 2 x 16
+    const int r = t >> 4, c = t & 15;
+    const uint32_t sum = (uint32_t)t2[2 * r][2 * c] + t2[2 * r][2 * c + 1] + t2[2 * r + 1][2 * c] + t2[2 * r + 1][2 * c + 1];
+    const uint8_t o = (uint8_t)(sum >> 2);
+    t3[r][c] = o;
+    const int y = ty * 2 + r, x = tx * 16 + c;
+    if (y < g.h[3] && x < g.w[3]) fr[g.off[3] + (size_t)y * g.w[3] + x] = o;
+  }
+  __syncthreads();
+  if (g.n_levels > 4 && t < 8) {  // level 4: 1 x 8
+    const uint32_t sum = (uint32_t)t3[0][2 * t] + t3[0][2 * t + 1] + t3[1][2 * t] + t3[1][2 * t + 1];
+    const int y = ty, x = tx * 8 + t;
+    if (y < g.h[4] && x < g.w[4]) fr[g.off[4] + (size_t)y * g.w[4] + x] = (uint8_t)(sum >> 2);
+  }
+}
+
 static int build_levels(svo_b200_ctx* ctx, svo_b200_frame* fr, int from_level) {
   for (int l = from_level; l < fr->n_levels; ++l) {
     const int total = ((fr->w[l] + 3) / 4) * fr->h[l];
@@ -219,8 +305,89 @@ void svo_b200_frame_destroy(svo_b200_ctx* ctx, svo_b200_frame* fr) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
   }
+  if (fr->pooled) return;  // borrowed handle of a pool
   if (fr->base) cudaFree(fr->base);
   delete fr;
+}
+
+
+int svo_b200_frame_pool_create(svo_b200_ctx* ctx, int width, int height, int n_levels, int count,
+                               svo_b200_frame_pool** pool_out) {
+  if (!ctx || !pool_out || width <= 0 || height <= 0 || n_levels < 1 || n_levels > SVO_B200_MAX_LEVELS || count <= 0)
+    return set_err(ctx, SVO_B200_EINVAL, "frame_pool_create: bad arguments");
+  cudaSetDevice(ctx->device);
+  svo_b200_frame proto;
+  proto.width = width; proto.height = height; proto.n_levels = n_levels; proto.pooled = true;
+  size_t off = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    proto.w[l] = l ? proto.w[l - 1] / 2 : width;
+    proto.h[l] = l ? proto.h[l - 1] / 2 : height;
+    if (proto.w[l] <= 0 || proto.h[l] <= 0) return set_err(ctx, SVO_B200_EINVAL, "frame_pool_create: level %d is empty", l);
+    proto.off[l] = off;
+    off += ((size_t)proto.w[l] * proto.h[l] + 255 + 16) / 256 * 256;
+  }
+  proto.bytes = off;
+  svo_b200_frame_pool* pool = new svo_b200_frame_pool();
+  pool->count = count;
+  pool->stride = off;
+  cudaError_t e = cudaMalloc((void**)&pool->slab, off * (size_t)count);
+  if (e != cudaSuccess) {
+    delete pool;
+    return set_err(ctx, SVO_B200_ENOMEM, "frame_pool_create: cudaMalloc(%zu): %s", off * (size_t)count, cudaGetErrorString(e));
+  }
+  cudaMemsetAsync(pool->slab, 0, off * (size_t)count, ctx->stream);
+  pool->frames.assign(count, proto);
+  for (int i = 0; i < count; ++i) pool->frames[i].base = pool->slab + (size_t)i * off;
+  *pool_out = pool;
+  return 0;
+}
+
+svo_b200_frame* svo_b200_frame_pool_get(svo_b200_frame_pool* pool, int index) {
+  if (!pool || index < 0 || index >= pool->count) return nullptr;
+  return &pool->frames[index];
+}
+
+int svo_b200_frame_pool_upload(svo_b200_ctx* ctx, svo_b200_frame_pool* pool, int first, int count,
+                               const uint8_t* level0_host, size_t host_stride_bytes) {
+  if (!ctx || !pool || !level0_host || first < 0 || count <= 0 || first + count > pool->count)
+    return set_err(ctx, SVO_B200_EINVAL, "frame_pool_upload: bad arguments");
+  cudaSetDevice(ctx->device);
+  const svo_b200_frame& f0 = pool->frames[0];
+  const size_t img = (size_t)f0.w[0] * f0.h[0];
+  if (host_stride_bytes < img) return set_err(ctx, SVO_B200_EINVAL, "frame_pool_upload: host stride < image size");
+  // ONE strided copy: row i = level 0 of frame first+i
+  SVO_CUDA_CHECK(ctx, cudaMemcpy2DAsync(pool->slab + (size_t)first * pool->stride, pool->stride, level0_host,
+                                        host_stride_bytes, img, (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+  if (f0.n_levels > 1) {
+    PyrGeom g;
+    memset(&g, 0, sizeof(g));
+    g.n_levels = f0.n_levels < 5 ? f0.n_levels : 5;
+    for (int l = 0; l < f0.n_levels; ++l) { g.w[l] = f0.w[l]; g.h[l] = f0.h[l]; g.off[l] = f0.off[l]; }
+    g.tiles_x = (f0.w[0] + 127) / 128;
+    const int tiles_y = (f0.h[0] + 15) / 16;
+    for (int done = 0; done < count; done += 32768) {  // gridDim.y limit 65535
+      const int n = count - done < 32768 ? count - done : 32768;
+      dim3 grid(g.tiles_x * tiles_y, n);
+      pyramid_fused_kernel<<<grid, 128, 0, ctx->stream>>>(pool->slab, pool->stride, first + done, g);
+      ctx->launches++;
+    }
+    SVO_CUDA_CHECK(ctx, cudaGetLastError());
+    for (int i = 0; i < count && f0.n_levels > 5; ++i) {  // levels 5.. : plain per-level kernel
+      int rc = build_levels(ctx, &pool->frames[first + i], 5);
+      if (rc) return rc;
+    }
+  }
+  return 0;
+}
+
+void svo_b200_frame_pool_destroy(svo_b200_ctx* ctx, svo_b200_frame_pool* pool) {
+  if (!pool) return;
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  if (pool->slab) cudaFree(pool->slab);
+  delete pool;
 }
 
 }  // extern "C"

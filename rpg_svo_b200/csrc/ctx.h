@@ -14,7 +14,15 @@ struct svo_b200_frame {
   uint8_t* base = nullptr;  // one allocation, levels at 256-byte aligned offsets
   size_t off[SVO_B200_MAX_LEVELS] = {0};
   size_t bytes = 0;
+  bool pooled = false;  // memory belongs to a svo_b200_frame_pool
   uint8_t* lvl(int l) const { return base + off[l]; }
+};
+
+struct svo_b200_frame_pool {
+  int count = 0;
+  size_t stride = 0;  // bytes between consecutive frames in the slab
+  uint8_t* slab = nullptr;
+  std::vector<svo_b200_frame> frames;
 };
 
 // Grow-only device / pinned-host buffers owned by the context.

@@ -35,7 +35,27 @@ namespace svo {
 
 constexpr int kPatchArea = 16;
 constexpr int kPartK = 22;  // widest block reduction: 21 unique H entries + 1 count
-constexpr int kMaxWarps = 32;
+constexpr int kMaxWarps = 16;  // blockDim <= 512
+
+// LDL^T of the 6x6 normal matrix: the register-resident unpivoted factorisation when H is safely
+// positive definite (always, outside degenerate inputs), else the pivoted Eigen-like routine.
+struct Solver6 {
+  Fact6 F;
+  double ldl[36];
+  int tr[8];
+  int pivoted;
+};
+__device__ inline void solver_factor(Solver6& S, const double* H) {
+  Fact6 F;
+  if (fact6_compute(H, F)) {
+    S.F = F;
+    S.pivoted = 0;
+  } else {
+    for (int k = 0; k < 36; ++k) S.ldl[k] = H[k];
+    ldlt6_factor(S.ldl, S.tr);
+    S.pivoted = 1;
+  }
+}
 
 struct SiaJob {  // one frame pair; array lives in device memory
   const uint8_t* ref_lvl[SVO_B200_MAX_LEVELS];
@@ -81,14 +101,13 @@ struct SiaShared {
   double part[kMaxWarps * kPartK];
   double Hs[36];       // H_ of the current pass (scaled), full symmetric
   double Htot[36];     // sum over the level's visible set (scaled)
-  double ldl[36];      // factorisation used for the current solve
-  double ldl_tot[36];  // factorisation of Htot
+  Solver6 sol_cur;     // factorisation used for the current solve (slow path)
+  Solver6 sol_tot;     // factorisation of Htot
   double x[8];
   double sums[kPartK];
   Pose model, old_model;
   double chi2_prev;
-  int tr[8], tr_tot[8];
-  int stop, done, slow, n_in_last;
+  int stop, done, slow, n_in_last, h_is_tot;
   int n_iters, sum_vis, sum_in, n_trace;
   unsigned mbar_phase;
 };
@@ -166,52 +185,73 @@ __device__ inline void publish_model(SiaShared& s) {
   s.t[0] = s.model.t[0]; s.t[1] = s.model.t[1]; s.t[2] = s.model.t[2];
 }
 
-// Thread 0: given Jres in s.x (already scaled/negated) and the factorisation in (ldl, tr), run the
-// tail of one NLLSSolver::optimizeGaussNewton iteration [EXT]: solve, accept/rollback, update.
-__device__ inline void gn_finish(SiaShared& s, const SiaParams& P, const double* ldl, const int* tr,
-                                 int level, int iter, double chi2sum, int n_in) {
+// Thread 0: given Jres in s.x (already scaled/negated) and a factorisation of H_ (or S == nullptr
+// when H_ is exactly zero), run the tail of one NLLSSolver::optimizeGaussNewton iteration [EXT]:
+// solve, accept/rollback, update.  Everything is pulled into registers first (independent loads),
+// the dependent chain is FMAs only.
+__device__ __forceinline__ void gn_finish(SiaShared& s, const SiaParams& P, const Solver6* S, int level,
+                                          int iter, double chi2sum, int n_in) {
   const int n_meas = n_in * kPatchArea;
   const float chi2f = (float)chi2sum;
   const double new_chi2 = (double)(chi2f / (float)n_meas);  // sparse_img_align.cpp:242 (NaN if 0)
-  double Jres[6];
-  for (int k = 0; k < 6; ++k) Jres[k] = s.x[k];
-  ldlt6_solve(ldl, tr, s.x);
-  if (isnan(s.x[0])) s.stop = 1;  // solve() == 0 (:248-250)
-  int accepted;
-  if ((iter > 0 && new_chi2 > s.chi2_prev) || s.stop) {
-    s.model = s.old_model;  // rollback
-    s.done = 1;
+  double x[6];
+  if (S == nullptr) {  // Eigen's LDLT of an all-zero matrix solves to x = 0
+#pragma unroll
+    for (int k = 0; k < 6; ++k) x[k] = 0.0;
+  } else if (!S->pivoted) {
+    const Fact6 F = S->F;
+    double b[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) b[k] = s.x[k];
+    fact6_solve(F, b, x);
+  } else {
+    ldlt6_solve(S->ldl, S->tr, s.x);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) x[k] = s.x[k];
+  }
+  const Pose model = s.model;
+  int stop = s.stop;
+  if (isnan(x[0])) stop = 1;  // solve() == 0 (:248-250)
+  int accepted, done = 0;
+  Pose out;
+  if ((iter > 0 && new_chi2 > s.chi2_prev) || stop) {
+    out = s.old_model;  // rollback
+    done = 1;
     accepted = 0;
   } else {
     double mx[6];
-    for (int k = 0; k < 6; ++k) mx[k] = -s.x[k];
-    const Pose nm = pose_mul(s.model, se3_exp(mx));  // T_new = T_old * exp(-x)  (:257)
-    s.old_model = s.model;
-    s.model = nm;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) mx[k] = -x[k];
+    out = pose_mul_fast(model, se3_exp_fast(mx));  // T_new = T_old * exp(-x)  (:257)
+    s.old_model = model;
     s.chi2_prev = new_chi2;
     accepted = 1;
     double m = 0;
-    for (int k = 0; k < 6; ++k) m = fmax(m, fabs(s.x[k]));
-    if (m <= P.eps) s.done = 1;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) m = fmax(m, fabs(x[k]));
+    if (m <= P.eps) done = 1;
   }
+  s.model = out;
+  qmatrix(out.q, s.R);
+  s.t[0] = out.t[0]; s.t[1] = out.t[1]; s.t[2] = out.t[2];
+  s.stop = stop;
+  s.done = done;
   s.n_in_last = n_in;
   s.n_iters++;
   s.sum_in += n_in;
-  publish_model(s);
   if (P.trace) {
     if (s.n_trace < P.trace_cap) {
       svo_b200_sia_iter& r = P.trace[s.n_trace];
       r.level = level; r.iter = iter; r.accepted = accepted; r.n_meas = n_meas; r.chi2 = new_chi2;
-      for (int k = 0; k < 6; ++k) r.x[k] = s.x[k];
-      pose_to_rt12(s.model, r.T);
+      for (int k = 0; k < 6; ++k) r.x[k] = x[k];
+      pose_to_rt12(out, r.T);
     }
     s.n_trace++;
   }
-  (void)Jres;
 }
 
-template <int FPT, bool EVAL>
-__global__ void __launch_bounds__(512) sia_kernel(const SiaParams P) {
+template <int FPT, bool EVAL, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SiaShared& s = *reinterpret_cast<SiaShared*>(smem_raw);
   const int S = P.slots;
@@ -235,7 +275,7 @@ __global__ void __launch_bounds__(512) sia_kernel(const SiaParams P) {
     s.model = pose_from_rt12(job.T);
     s.old_model = s.model;
     s.chi2_prev = 1e10;  // NLLSSolver::reset() [EXT]
-    s.stop = 0; s.done = 0; s.slow = 0; s.n_in_last = 0;
+    s.stop = 0; s.done = 0; s.slow = 0; s.n_in_last = 0; s.h_is_tot = 0;
     s.n_iters = 0; s.sum_vis = 0; s.sum_in = 0; s.n_trace = 0;
     for (int k = 0; k < 36; ++k) s.Hs[k] = 0.0;
     publish_model(s);
@@ -372,8 +412,7 @@ __global__ void __launch_bounds__(512) sia_kernel(const SiaParams P) {
           s.Htot[r * 6 + c] = v;
           s.Htot[c * 6 + r] = v;
         }
-      for (int k = 0; k < 36; ++k) s.ldl_tot[k] = s.Htot[k];
-      ldlt6_factor(s.ldl_tot, s.tr_tot);
+      solver_factor(s.sol_tot, s.Htot);
       s.sum_vis += (int)s.sums[21];
       s.done = 0;
     }
@@ -461,12 +500,12 @@ __global__ void __launch_bounds__(512) sia_kernel(const SiaParams P) {
         s.slow = (EVAL || (n_out > 0 && n_in > 0)) ? 1 : 0;
         if (!s.slow) {
           if (n_in == 0) {  // H_ == 0 exactly: Eigen's LDLT yields x = 0
-            for (int k = 0; k < 36; ++k) { s.Hs[k] = 0.0; s.ldl[k] = 0.0; }
-            for (int k = 0; k < 6; ++k) s.tr[k] = k;
-            gn_finish(s, P, s.ldl, s.tr, level, iter, s.sums[6], n_in);
+            for (int k = 0; k < 36; ++k) s.Hs[k] = 0.0;
+            s.h_is_tot = 0;
+            gn_finish(s, P, nullptr, level, iter, s.sums[6], n_in);
           } else {
-            for (int k = 0; k < 36; ++k) s.Hs[k] = s.Htot[k];
-            gn_finish(s, P, s.ldl_tot, s.tr_tot, level, iter, s.sums[6], n_in);
+            s.h_is_tot = 1;
+            gn_finish(s, P, &s.sol_tot, level, iter, s.sums[6], n_in);
           }
         }
       }
@@ -498,6 +537,7 @@ __global__ void __launch_bounds__(512) sia_kernel(const SiaParams P) {
         if (tid == 0) {
           const double s2 = jscale * jscale;
           int idx = 0;
+          s.h_is_tot = 0;
           for (int r = 0; r < 6; ++r)
             for (int c = r; c < 6; ++c, ++idx) {
               const double v = s.sums[idx] * s2;
@@ -512,9 +552,8 @@ __global__ void __launch_bounds__(512) sia_kernel(const SiaParams P) {
             s.n_in_last = n_in_keep;
             s.done = 1;
           } else {
-            for (int k = 0; k < 36; ++k) s.ldl[k] = s.Hs[k];
-            ldlt6_factor(s.ldl, s.tr);
-            gn_finish(s, P, s.ldl, s.tr, level, iter, chi2_keep, n_in_keep);
+            solver_factor(s.sol_cur, s.Hs);
+            gn_finish(s, P, &s.sol_cur, level, iter, chi2_keep, n_in_keep);
           }
         }
         __syncthreads();
@@ -547,7 +586,7 @@ __global__ void __launch_bounds__(512) sia_kernel(const SiaParams P) {
   if (tid == 0) {
     if (P.T_out) pose_to_rt12(s.model, P.T_out + 12 * (size_t)blockIdx.x);
     if (P.H_out)
-      for (int k = 0; k < 36; ++k) P.H_out[36 * (size_t)blockIdx.x + k] = s.Hs[k];
+      for (int k = 0; k < 36; ++k) P.H_out[36 * (size_t)blockIdx.x + k] = s.h_is_tot ? s.Htot[k] : s.Hs[k];
     if (P.stats) {
       svo_b200_sia_stats st;
       st.n_iters = s.n_iters; st.sum_visible = s.sum_vis; st.sum_in_image = s.sum_in;
@@ -602,14 +641,22 @@ template <bool EVAL>
 static int launch_sia(svo_b200_ctx* ctx, const SiaParams& P, int B, int threads, int fpt, size_t smem) {
   auto go = [&](auto kern) -> int {
     SVO_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // ask for the full shared-memory carveout so that two CTAs of ~90 KB fit one SM
+    SVO_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             (int)cudaSharedmemCarveoutMaxShared));
     kern<<<B, threads, smem, ctx->stream>>>(P);
     ctx->launches++;
     SVO_CUDA_CHECK(ctx, cudaGetLastError());
     return 0;
   };
-  if (fpt == 1) return go(sia_kernel<1, EVAL>);
-  if (fpt == 2) return go(sia_kernel<2, EVAL>);
-  return go(sia_kernel<4, EVAL>);
+  // <= 384 threads: cap registers so that two CTAs are resident per SM
+  if (fpt == 1) {
+    if (threads <= 320) return go(sia_kernel<1, EVAL, 320, 2>);
+    if (threads <= 384) return go(sia_kernel<1, EVAL, 384, 2>);
+    return go(sia_kernel<1, EVAL, 512, 1>);
+  }
+  if (fpt == 2) return go(sia_kernel<2, EVAL, 512, 1>);
+  return go(sia_kernel<4, EVAL, 512, 1>);
 }
 
 static inline int pad16(int n) { return (n + 15) / 16 * 16; }

@@ -213,6 +213,124 @@ __device__ inline void ldlt6_solve(const double* m, const int* tr, double* x) {
   for (int i = 5; i >= 0; --i) { const int j = tr[i]; double s = x[i]; x[i] = x[j]; x[j] = s; }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Latency-tuned variants used on the serial critical path of the Gauss-Newton loops (one thread
+// works while the CTA waits): explicit FMAs, no divisions, no sincos for small rotations.
+// Results agree with the plain versions to a few ulp.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ Pose se3_exp_fast(const double* u) {
+  const double wx = u[3], wy = u[4], wz = u[5];
+  const double th2 = fma(wx, wx, fma(wy, wy, wz * wz));
+  double imag, real, a, b;
+  if (th2 < 0.25) {
+    // Taylor series in th2 (|th| < 0.5: the 8th term is < 1e-17 of the leading one)
+    // imag = sin(th/2)/th, real = cos(th/2), a = (1-cos th)/th^2, b = (th - sin th)/th^3
+    const double q2 = 0.25 * th2;  // (th/2)^2
+    imag = 0.5 * fma(q2, fma(q2, fma(q2, fma(q2, fma(q2, fma(q2, fma(q2, -1.0 / 1307674368000.0, 1.0 / 6227020800.0),
+                     -1.0 / 39916800.0), 1.0 / 362880.0), -1.0 / 5040.0), 1.0 / 120.0), -1.0 / 6.0), 1.0);
+    real = fma(q2, fma(q2, fma(q2, fma(q2, fma(q2, fma(q2, fma(q2, -1.0 / 87178291200.0, 1.0 / 479001600.0),
+               -1.0 / 3628800.0), 1.0 / 40320.0), -1.0 / 720.0), 1.0 / 24.0), -0.5), 1.0);
+    a = fma(th2, fma(th2, fma(th2, fma(th2, fma(th2, fma(th2, fma(th2, -1.0 / 20922789888000.0, 1.0 / 87178291200.0),
+            -1.0 / 479001600.0), 1.0 / 3628800.0), -1.0 / 40320.0), 1.0 / 720.0), -1.0 / 24.0), 0.5);
+    b = fma(th2, fma(th2, fma(th2, fma(th2, fma(th2, fma(th2, fma(th2, -1.0 / 355687428096000.0, 1.0 / 1307674368000.0),
+            -1.0 / 6227020800.0), 1.0 / 39916800.0), -1.0 / 362880.0), 1.0 / 5040.0), -1.0 / 120.0), 1.0 / 6.0);
+  } else {
+    const double th = sqrt(th2);
+    double sh, ch, s, c;
+    sincos(0.5 * th, &sh, &ch);
+    sincos(th, &s, &c);
+    real = ch;
+    imag = sh / th;
+    a = (1.0 - c) / th2;
+    b = (th - s) / (th2 * th);
+  }
+  Pose P;
+  P.q.w = real; P.q.x = imag * wx; P.q.y = imag * wy; P.q.z = imag * wz;
+  const double cx = fma(wy, u[2], -(wz * u[1])), cy = fma(wz, u[0], -(wx * u[2])), cz = fma(wx, u[1], -(wy * u[0]));
+  const double ccx = fma(wy, cz, -(wz * cy)), ccy = fma(wz, cx, -(wx * cz)), ccz = fma(wx, cy, -(wy * cx));
+  P.t[0] = fma(b, ccx, fma(a, cx, u[0]));
+  P.t[1] = fma(b, ccy, fma(a, cy, u[1]));
+  P.t[2] = fma(b, ccz, fma(a, cz, u[2]));
+  return P;
+}
+
+// C = A * B with the product quaternion re-normalised by one Newton step of 1/sqrt at 1
+// (both inputs are unit to ~1e-16, so the step is exact to double precision).
+__device__ __forceinline__ Pose pose_mul_fast(const Pose& A, const Pose& B) {
+  Pose C;
+  const Quat &a = A.q, &b = B.q;
+  Quat r;
+  r.w = fma(a.w, b.w, -fma(a.x, b.x, fma(a.y, b.y, a.z * b.z)));
+  r.x = fma(a.w, b.x, fma(a.x, b.w, fma(a.y, b.z, -(a.z * b.y))));
+  r.y = fma(a.w, b.y, fma(a.y, b.w, fma(a.z, b.x, -(a.x * b.z))));
+  r.z = fma(a.w, b.z, fma(a.z, b.w, fma(a.x, b.y, -(a.y * b.x))));
+  const double n2 = fma(r.w, r.w, fma(r.x, r.x, fma(r.y, r.y, r.z * r.z)));
+  const double sc = fma(-0.5, n2, 1.5);
+  C.q.w = r.w * sc; C.q.x = r.x * sc; C.q.y = r.y * sc; C.q.z = r.z * sc;
+  // t = A.t + rotate(A.q, B.t)
+  const double* v = B.t;
+  double ux = fma(a.y, v[2], -(a.z * v[1])), uy = fma(a.z, v[0], -(a.x * v[2])), uz = fma(a.x, v[1], -(a.y * v[0]));
+  ux += ux; uy += uy; uz += uz;
+  C.t[0] = A.t[0] + fma(a.w, ux, v[0]) + fma(a.y, uz, -(a.z * uy));
+  C.t[1] = A.t[1] + fma(a.w, uy, v[1]) + fma(a.z, ux, -(a.x * uz));
+  C.t[2] = A.t[2] + fma(a.w, uz, v[2]) + fma(a.x, uy, -(a.y * ux));
+  return C;
+}
+
+// Unpivoted LDL^T of a symmetric positive definite 6x6, fully unrolled in registers.
+// L: strict lower triangle row-major (15), dinv: 1/d.  Returns false when a pivot is not safely
+// positive (caller falls back to the pivoted Eigen-like routine above).
+struct Fact6 {
+  double L[15];
+  double dinv[6];
+};
+__device__ __forceinline__ int tri(int i, int j) { return i * (i - 1) / 2 + j; }  // i > j
+__device__ __forceinline__ bool fact6_compute(const double* H /*36 row-major*/, Fact6& F) {
+  double d[6];
+  double maxdiag = 0.0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) maxdiag = fmax(maxdiag, fabs(H[j * 6 + j]));
+  bool ok = maxdiag > 0.0 && maxdiag < 1e300;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double dj = H[j * 6 + j];
+#pragma unroll
+    for (int k = 0; k < j; ++k) dj = fma(-(F.L[tri(j, k)] * F.L[tri(j, k)]), d[k], dj);
+    d[j] = dj;
+    ok = ok && (dj > 1e-13 * maxdiag);
+    const double inv = 1.0 / dj;
+    F.dinv[j] = inv;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double v = H[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v = fma(-(F.L[tri(i, k)] * F.L[tri(j, k)]), d[k], v);
+      F.L[tri(i, j)] = v * inv;
+    }
+  }
+  return ok;
+}
+__device__ __forceinline__ void fact6_solve(const Fact6& F, const double* b, double* x) {
+  double y[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double s = b[i];
+#pragma unroll
+    for (int j = 0; j < i; ++j) s = fma(-F.L[tri(i, j)], y[j], s);
+    y[i] = s;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) y[i] *= F.dinv[i];
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double s = y[i];
+#pragma unroll
+    for (int j = i + 1; j < 6; ++j) s = fma(-F.L[tri(j, i)], x[j], s);
+    x[i] = s;
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // Reductions: each warp folds its K doubles with __shfl_down, lane 0 parks them in shared memory.
 // ------------------------------------------------------------------------------------------

@@ -273,3 +273,65 @@ def make_stream(seed: int, n_frames: int, width: int = 640, height: int = 480, n
         drift += xi
         T = se3_mul(se3_exp(xi), T)
     return dict(cam=cam, frames=frames, poses=poses, feats=feats, n_levels=n_levels, seed=seed)
+
+
+# --------------------------------------------------------------------------- bulk stream (bench)
+def render_torch(cam: Camera, poses: list, plane: Plane, tex: np.ndarray, device: str = "cpu"):
+    """Same plane render as `render`, batched over poses with torch (data manufacture only, not
+    part of any measured path).  Returns a uint8 tensor [len(poses), H, W] on `device`."""
+    import torch
+
+    dev = torch.device(device)
+    t_tex = torch.from_numpy(tex).to(dev)
+    u, v = torch.meshgrid(torch.arange(cam.width, dtype=torch.float64, device=dev),
+                          torch.arange(cam.height, dtype=torch.float64, device=dev), indexing="xy")
+    rays = torch.stack([(u.reshape(-1) - cam.cx) / cam.fx, (v.reshape(-1) - cam.cy) / cam.fy,
+                        torch.ones(u.numel(), dtype=torch.float64, device=dev)], dim=1)
+    n = torch.tensor(plane.n, device=dev)
+    e1 = torch.tensor(plane.e1, device=dev)
+    e2 = torch.tensor(plane.e2, device=dev)
+    out = torch.empty((len(poses), cam.height, cam.width), dtype=torch.uint8, device=dev)
+    for k, T in enumerate(poses):
+        R = torch.tensor(T[:, :3], device=dev)
+        t = torch.tensor(T[:, 3], device=dev)
+        o = -(R.T @ t)
+        d = rays @ R
+        lam = (plane.d - n @ o) / (d @ n)
+        X = o[None, :] + lam[:, None] * d
+        s = ((X @ e1) * TEXELS_PER_M + TEX_SIZE / 2).clamp(0, TEX_SIZE - 1.001)
+        tt = ((X @ e2) * TEXELS_PER_M + TEX_SIZE / 2).clamp(0, TEX_SIZE - 1.001)
+        s0, t0 = s.floor().long(), tt.floor().long()
+        fs, ft = (s - s0).float(), (tt - t0).float()
+        a, b = t_tex[t0, s0], t_tex[t0, s0 + 1]
+        c, dd = t_tex[t0 + 1, s0], t_tex[t0 + 1, s0 + 1]
+        val = (a * (1 - fs) + b * fs) * (1 - ft) + (c * (1 - fs) + dd * fs) * ft
+        out[k] = val.round().clamp(0, 255).to(torch.uint8).reshape(cam.height, cam.width)
+    return out
+
+
+def stream_poses(seed: int, n_frames: int, trans: float = 0.02, rot_deg: float = 0.35) -> list:
+    """Bounded random walk of camera poses T_f_w (the trajectory of `make_stream`)."""
+    rng = np.random.default_rng(seed)
+    T = base_pose()
+    poses, drift = [], np.zeros(6)
+    for _ in range(n_frames):
+        poses.append(T)
+        xi = np.concatenate([rng.uniform(-trans, trans, 3), np.deg2rad(rng.uniform(-rot_deg, rot_deg, 3))])
+        xi -= 0.2 * drift
+        drift += xi
+        T = se3_mul(se3_exp(xi), T)
+    return poses
+
+
+def make_stream_fast(seed: int, n_frames: int, width: int = 640, height: int = 480, n_feat: int = 300,
+                     n_levels: int = 5, device: str = "cpu", tex_seed: int = 7) -> dict:
+    """A camera stream for the benchmark: level-0 images as one uint8 torch tensor (rendered with
+    torch on `device`, returned on the CPU), per-frame features as numpy arrays."""
+    cam = camera_for(width, height)
+    plane = Plane.tilted()
+    tex = make_texture(tex_seed)
+    poses = stream_poses(seed, n_frames)
+    imgs = render_torch(cam, poses, plane, tex, device).cpu()
+    rng = np.random.default_rng(seed + 77)
+    feats = [features_for(rng, cam, T, plane, n_feat, n_levels - 1) for T in poses]
+    return dict(cam=cam, level0=imgs, poses=poses, feats=feats, n_levels=n_levels, seed=seed)
