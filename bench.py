@@ -139,31 +139,26 @@ def run_reference(args, rank: int, world: int):
     """CPU arm: the oracle port on all host cores (rank 0 only)."""
     if rank != 0:
         return
-    from concurrent.futures import ThreadPoolExecutor
-
     from oracle import binding as ob
     from rpg_svo_b200 import synth
 
     ob.build()
     cores = os.cpu_count() or 1
-    sample = min(args.pairs_per_gpu, max(cores, 128))
+    sample = args.pairs_per_gpu  # the whole window of the step (bounded: ~1 s of CPU work on 1 core per 500 pairs)
     inp = make_inputs(0, sample, "cuda" if _has_cuda() else "cpu")
     pyrs = [synth.build_pyramid(inp["level0"][i].numpy(), NLEVELS) for i in range(sample + 1)]
 
-    def one(k):
-        s = slice(k * NFEAT, (k + 1) * NFEAT)
-        r = ob.sparse_img_align(pyrs[k], pyrs[k + 1], inp["cam"], inp["T0"][k], inp["px"][s], inp["f"][s],
-                                inp["pos"][s], inp["hp"][s], inp["ref_pos"][k], MAX_LEVEL, MIN_LEVEL, NITER,
-                                want_trace=False)
-        return r["T"]
+    def step():
+        return ob.sparse_img_align_batch(pyrs[:sample], pyrs[1:sample + 1], inp["cam"], inp["T0"], inp["off"],
+                                         inp["px"], inp["f"], inp["pos"], inp["hp"], inp["ref_pos"], MAX_LEVEL,
+                                         MIN_LEVEL, NITER, n_threads=cores)
 
-    with ThreadPoolExecutor(max_workers=cores) as ex:
-        for _ in range(args.warmup):
-            list(ex.map(one, range(sample)))
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            list(ex.map(one, range(sample)))
-        dt = time.perf_counter() - t0
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
     fps = sample * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
@@ -315,21 +310,20 @@ def main():
         n = min(args.cpu_sample, B)
         pyrs = [synth.build_pyramid(inp["level0"][i].numpy(), NLEVELS) for i in range(n + 1)]
 
-        def one(k):
-            s = slice(k * NFEAT, (k + 1) * NFEAT)
-            ob.sparse_img_align(pyrs[k], pyrs[k + 1], inp["cam"], inp["T0"][k], inp["px"][s], inp["f"][s],
-                                inp["pos"][s], inp["hp"][s], inp["ref_pos"][k], MAX_LEVEL, MIN_LEVEL, NITER,
-                                want_trace=False)
+        sl = slice(0, n * NFEAT)
 
-        for k in range(min(8, n)):
-            one(k)
+        def run_sample():
+            ob.sparse_img_align_batch(pyrs[:n], pyrs[1:n + 1], inp["cam"], inp["T0"][:n], inp["off"][:n + 1],
+                                      inp["px"][sl], inp["f"][sl], inp["pos"][sl], inp["hp"][sl],
+                                      inp["ref_pos"][:n], MAX_LEVEL, MIN_LEVEL, NITER, n_threads=1)
+
+        run_sample()
         reps = 0
         t0 = time.perf_counter()
         while True:
-            for k in range(n):
-                one(k)
+            run_sample()
             reps += 1
-            if time.perf_counter() - t0 > 10.0 or reps >= 20:
+            if time.perf_counter() - t0 > 10.0 or reps >= 40:
                 break
         dt = time.perf_counter() - t0
         cpu = {"value": n * reps / dt, "unit": UNIT, "cores": 1, "kind": "port",

@@ -63,6 +63,7 @@ def lib() -> C.CDLL:
             build()
         _lib = C.CDLL(_LIB_PATH)
         _lib.orc_sparse_img_align_run.restype = C.c_int64
+        _lib.orc_sparse_img_align_batch.restype = None
         _lib.orc_compute_tau.restype = C.c_double
         _lib.orc_compute_tau.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_double]
         _lib.orc_update_seed.argtypes = [C.c_float, C.c_float] + [C.c_void_p] * 5
@@ -121,6 +122,32 @@ def sparse_img_align(ref_pyr, cur_pyr, cam, T_init, px, f, pos, has_point, ref_p
                            chi2=r.chi2, x=np.array(r.x[:]), T=np.array(r.T[:]).reshape(3, 4)))
     return dict(T=T.reshape(3, 4), n_tracked=int(ret), visible=visible[:n], H=H.reshape(6, 6),
                 residuals=res[:n], trace=tr)
+
+
+def sparse_img_align_batch(ref_pyrs, cur_pyrs, cam, T_init, feat_offset, px, f, pos, has_point, ref_pos,
+                           max_level, min_level, n_iter=30, eps=1e-6, n_threads=1):
+    """B independent runs on n_threads host threads (no Python in the loop).  Returns (T [B,3,4], n_tracked [B])."""
+    L = lib()
+    B = len(ref_pyrs)
+    nl = len(ref_pyrs[0])
+    rp = (C.c_void_p * (B * nl))()
+    cp = (C.c_void_p * (B * nl))()
+    for b in range(B):
+        for l in range(nl):
+            rp[b * nl + l] = ref_pyrs[b][l].ctypes.data
+            cp[b * nl + l] = cur_pyrs[b][l].ctypes.data
+    cols = np.array([im.shape[1] for im in ref_pyrs[0]], dtype=np.int32)
+    rows = np.array([im.shape[0] for im in ref_pyrs[0]], dtype=np.int32)
+    T = c64(T_init).copy().reshape(B, 12)
+    fo = np.ascontiguousarray(feat_offset, np.int32)
+    px, f, pos, rpos = c64(px), c64(f), c64(pos), c64(ref_pos)
+    hp = np.ascontiguousarray(has_point, np.uint8)
+    ntr = np.zeros(B, np.int64)
+    cs = cam_struct(cam)
+    L.orc_sparse_img_align_batch(B, rp, cp, _p(cols), _p(rows), nl, C.byref(cs), _p(T), _p(fo), _p(px), _p(f),
+                                 _p(pos), _p(hp), _p(rpos), max_level, min_level, n_iter, C.c_double(eps),
+                                 _p(ntr), int(n_threads))
+    return T.reshape(B, 3, 4), ntr
 
 
 def sparse_residuals(ref_img, cur_img, level, cam, T, px, f, pos, has_point, ref_pos, visible_in=None):

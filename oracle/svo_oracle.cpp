@@ -15,6 +15,8 @@
 #include "svo_oracle.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <cmath>
 #include <cstdio>
 #include <vector>
@@ -388,6 +390,36 @@ int64_t orc_sparse_img_align_run(const uint8_t* const* ref_levels,
     std::memcpy(residuals_out, sia.last_res_.data(), sizeof(float) * size_t(N) * 16);
   if (n_trace) *n_trace = sia.n_trace;
   return int64_t(ret);
+}
+
+void orc_sparse_img_align_batch(int B, const uint8_t* const* ref_levels,
+                                const uint8_t* const* cur_levels, const int* cols, const int* rows,
+                                int n_levels, const orc_camera* cam, double* T_io,
+                                const int* feat_offset, const double* px, const double* f,
+                                const double* point_pos, const uint8_t* has_point,
+                                const double* ref_pos, int max_level, int min_level, int n_iter,
+                                double eps, int64_t* n_tracked_out, int n_threads) {
+  std::atomic<int> next(0);
+  auto worker = [&]() {
+    for (;;) {
+      const int b = next.fetch_add(1);
+      if (b >= B) break;
+      const int o = feat_offset[b], n = feat_offset[b + 1] - o;
+      const int64_t r = orc_sparse_img_align_run(
+          ref_levels + size_t(b) * n_levels, cur_levels + size_t(b) * n_levels, cols, rows, n_levels, cam,
+          T_io + 12 * size_t(b), px + 2 * size_t(o), f + 3 * size_t(o), point_pos + 3 * size_t(o),
+          has_point + o, ref_pos + 3 * size_t(b), n, max_level, min_level, n_iter, eps, nullptr, nullptr,
+          nullptr, nullptr, 0, nullptr);
+      if (n_tracked_out) n_tracked_out[b] = r;
+    }
+  };
+  if (n_threads <= 1) {
+    worker();
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (int t = 0; t < n_threads; ++t) pool.emplace_back(worker);
+  for (auto& th : pool) th.join();
 }
 
 int orc_sparse_residuals(const uint8_t* ref_img, const uint8_t* cur_img, int cols, int rows,

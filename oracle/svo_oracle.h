@@ -51,6 +51,17 @@ int64_t orc_sparse_img_align_run(
     float* residuals_out /*N*16 or NULL: last residual pass, NaN where not evaluated*/,
     orc_sia_iter* trace /*or NULL*/, int trace_cap, int* n_trace /*or NULL*/);
 
+/* B independent runs of orc_sparse_img_align_run on n_threads host threads (std::thread, dynamic
+ * work queue) -- the CPU arm of bench.py.  Level pointer arrays are [B * n_levels]; feat_offset has
+ * B+1 entries; T_io is B*12; ref_pos B*3; n_tracked_out B (or NULL). */
+void orc_sparse_img_align_batch(int B, const uint8_t* const* ref_levels,
+                                const uint8_t* const* cur_levels, const int* cols, const int* rows,
+                                int n_levels, const orc_camera* cam, double* T_io,
+                                const int* feat_offset, const double* px, const double* f,
+                                const double* point_pos, const uint8_t* has_point,
+                                const double* ref_pos, int max_level, int min_level, int n_iter,
+                                double eps, int64_t* n_tracked_out, int n_threads);
+
 /* One computeResiduals(model, linearize=true) pass at a given level and pose, starting from
  * the visibility flags in visible_io (may be all zero).  Exposes every intermediate. */
 int orc_sparse_residuals(

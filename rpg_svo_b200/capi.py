@@ -291,3 +291,109 @@ class Context:
             _p(vis), _p(ref_patch), _p(res), _p(inimg), _p(H), _p(Jres), C.byref(chi2), C.byref(nm)))
         return dict(visible=vis, ref_patch=ref_patch, residuals=res, in_image=inimg, H=H.reshape(6, 6),
                     Jres=Jres, chi2=chi2.value, n_meas=nm.value)
+
+
+# --------------------------------------------------------------------------------------------
+# feature alignment / matcher / pose optimizer / depth filter entry points (methods of Context)
+# --------------------------------------------------------------------------------------------
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _frame_array(frames):
+    return (C.c_void_p * len(frames))(*[f.h.value for f in frames])
+
+
+def _align2d_batch(self, cur: Frame, level, pwb, patch, n_iter, px):
+    """feature_alignment::align2D for M features; returns (converged[M] bool, px[M,2])."""
+    level = _i32(level)
+    M = len(level)
+    px = c64(px).copy().reshape(M, 2)
+    conv = np.zeros(max(M, 1), np.uint8)
+    pwb, patch = _u8(pwb).reshape(M, 100), _u8(patch).reshape(M, 64)
+    self._check(self.lib.svo_b200_align2d_batch(self.h, cur.h, M, _p(level), _p(pwb), _p(patch), int(n_iter),
+                                                _p(px), _p(conv)))
+    return conv[:M].astype(bool), px
+
+
+def _align1d_batch(self, cur: Frame, level, direction, pwb, patch, n_iter, px):
+    level = _i32(level)
+    M = len(level)
+    px = c64(px).copy().reshape(M, 2)
+    conv = np.zeros(max(M, 1), np.uint8)
+    h_inv = np.zeros(max(M, 1))
+    d = np.ascontiguousarray(direction, np.float32).reshape(M, 2)
+    pwb, patch = _u8(pwb).reshape(M, 100), _u8(patch).reshape(M, 64)
+    self._check(self.lib.svo_b200_align1d_batch(self.h, cur.h, M, _p(level), _p(d), _p(pwb), _p(patch), int(n_iter),
+                                                _p(px), _p(conv), _p(h_inv)))
+    return conv[:M].astype(bool), px, h_inv[:M]
+
+
+def _find_match_direct(self, ref_frames, ref_T_f_w, cur: Frame, cur_T_f_w, cam, ref_index, ref_px, ref_f, ref_level,
+                       ftr_type, ref_grad, point_pos, px_cur, max_search_level, align_max_iter=10):
+    M = len(ref_index)
+    ra = _frame_array(ref_frames)
+    refT = c64(np.asarray(ref_T_f_w)).reshape(-1)
+    px = c64(px_cur).copy().reshape(M, 2)
+    succ = np.zeros(max(M, 1), np.uint8)
+    sl = np.zeros(max(M, 1), np.int32)
+    A = np.zeros((max(M, 1), 4))
+    hinv = np.zeros(max(M, 1))
+    cs = cam_struct(cam)
+    opt = MatchOptions(max_search_level, align_max_iter)
+    ri, lv, ty = _i32(ref_index), _i32(ref_level), _i32(ftr_type)
+    rpx, rf, rg, pp, cT = c64(ref_px), c64(ref_f), c64(ref_grad), c64(point_pos), c64(cur_T_f_w).reshape(12)
+    self._check(self.lib.svo_b200_find_match_direct(self.h, ra, _p(refT), len(ref_frames), cur.h, _p(cT), C.byref(cs),
+                                                    C.byref(opt), M, _p(ri), _p(rpx), _p(rf), _p(lv), _p(ty), _p(rg),
+                                                    _p(pp), _p(px), _p(succ), _p(sl), _p(A), _p(hinv)))
+    return dict(success=succ[:M].astype(bool), px_cur=px, search_level=sl[:M], A_cur_ref=A[:M].reshape(M, 2, 2),
+                h_inv=hinv[:M])
+
+
+def _pose_optimize(self, reproj_thresh, n_iter, fx, T_f_w, f, pos, level, has_point):
+    """pose_optimizer::optimizeGaussNewton; returns dict like the oracle's."""
+    T = c64(T_f_w).copy().reshape(12)
+    hp = _u8(has_point).copy()
+    out = PoseOptResult()
+    lv = _i32(level)
+    f, pos = c64(f), c64(pos)
+    self._check(self.lib.svo_b200_pose_optimize(self.h, C.c_double(reproj_thresh), int(n_iter), C.c_double(fx), _p(T),
+                                                _p(f), _p(pos), _p(lv), _p(hp), len(hp), C.byref(out)))
+    return dict(T=T.reshape(3, 4), has_point=hp, estimated_scale=out.estimated_scale, error_init=out.error_init,
+                error_final=out.error_final, num_obs=out.num_obs, n_iter_done=out.n_iter_done,
+                cov=np.array(out.cov[:]).reshape(6, 6))
+
+
+def _depth_filter_update(self, ref_frames, ref_T_f_w, cur: Frame, cur_T_f_w, cam, ref_index, ftr_px, ftr_f, ftr_level,
+                         ftr_type, ftr_grad, batch_id, batch_counter, seeds, max_n_kfs=3, sigma2_thresh=200.0,
+                         max_search_level=2, align_max_iter=10, max_epi_search_steps=1000):
+    """DepthFilter::updateSeeds; `seeds` = dict of float32 arrays a,b,mu,z_range,sigma2 (copies are updated)."""
+    M = len(ref_index)
+    ra = _frame_array(ref_frames)
+    refT = c64(np.asarray(ref_T_f_w)).reshape(-1)
+    out = {k: np.ascontiguousarray(seeds[k], np.float32).copy() for k in ("a", "b", "mu", "z_range", "sigma2")}
+    status = np.zeros(max(M, 1), np.uint8)
+    pxc = np.zeros((max(M, 1), 2))
+    z = np.zeros(max(M, 1))
+    nz = np.zeros(max(M, 1), np.int32)
+    cs = cam_struct(cam)
+    opt = DepthOptions(max_n_kfs, sigma2_thresh, max_search_level, align_max_iter, max_epi_search_steps)
+    ri, fl, ft, bi = _i32(ref_index), _i32(ftr_level), _i32(ftr_type), _i32(batch_id)
+    fpx, ff, fg, cT = c64(ftr_px), c64(ftr_f), c64(ftr_grad), c64(cur_T_f_w).reshape(12)
+    self._check(self.lib.svo_b200_depth_filter_update(
+        self.h, ra, _p(refT), len(ref_frames), cur.h, _p(cT), C.byref(cs), C.byref(opt), M, _p(ri), _p(fpx), _p(ff),
+        _p(fl), _p(ft), _p(fg), _p(bi), int(batch_counter), _p(out["a"]), _p(out["b"]), _p(out["mu"]),
+        _p(out["z_range"]), _p(out["sigma2"]), _p(status), _p(pxc), _p(z), _p(nz)))
+    out.update(status=status[:M], px_cur=pxc[:M], z=z[:M], n_zmssd=nz[:M])
+    return out
+
+
+Context.align2d_batch = _align2d_batch
+Context.align1d_batch = _align1d_batch
+Context.find_match_direct = _find_match_direct
+Context.pose_optimize = _pose_optimize
+Context.depth_filter_update = _depth_filter_update

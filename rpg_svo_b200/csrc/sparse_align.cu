@@ -37,26 +37,6 @@ constexpr int kPatchArea = 16;
 constexpr int kPartK = 22;  // widest block reduction: 21 unique H entries + 1 count
 constexpr int kMaxWarps = 16;  // blockDim <= 512
 
-// LDL^T of the 6x6 normal matrix: the register-resident unpivoted factorisation when H is safely
-// positive definite (always, outside degenerate inputs), else the pivoted Eigen-like routine.
-struct Solver6 {
-  Fact6 F;
-  double ldl[36];
-  int tr[8];
-  int pivoted;
-};
-__device__ inline void solver_factor(Solver6& S, const double* H) {
-  Fact6 F;
-  if (fact6_compute(H, F)) {
-    S.F = F;
-    S.pivoted = 0;
-  } else {
-    for (int k = 0; k < 36; ++k) S.ldl[k] = H[k];
-    ldlt6_factor(S.ldl, S.tr);
-    S.pivoted = 1;
-  }
-}
-
 struct SiaJob {  // one frame pair; array lives in device memory
   const uint8_t* ref_lvl[SVO_B200_MAX_LEVELS];
   const uint8_t* cur_lvl[SVO_B200_MAX_LEVELS];

@@ -331,6 +331,27 @@ __device__ __forceinline__ void fact6_solve(const Fact6& F, const double* b, dou
   }
 }
 
+// LDL^T of the 6x6 normal matrix: the register-resident unpivoted factorisation when H is safely
+// positive definite (always, outside degenerate inputs), else the pivoted Eigen-like routine.
+struct Solver6 {
+  Fact6 F;
+  double ldl[36];
+  int tr[8];
+  int pivoted;
+};
+__device__ inline void solver_factor(Solver6& S, const double* H) {
+  Fact6 F;
+  if (fact6_compute(H, F)) {
+    S.F = F;
+    S.pivoted = 0;
+  } else {
+    for (int k = 0; k < 36; ++k) S.ldl[k] = H[k];
+    ldlt6_factor(S.ldl, S.tr);
+    S.pivoted = 1;
+  }
+}
+
+
 // ------------------------------------------------------------------------------------------
 // Reductions: each warp folds its K doubles with __shfl_down, lane 0 parks them in shared memory.
 // ------------------------------------------------------------------------------------------

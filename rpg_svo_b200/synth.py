@@ -335,3 +335,125 @@ def make_stream_fast(seed: int, n_frames: int, width: int = 640, height: int = 4
     rng = np.random.default_rng(seed + 77)
     feats = [features_for(rng, cam, T, plane, n_feat, n_levels - 1) for T in poses]
     return dict(cam=cam, level0=imgs, poses=poses, feats=feats, n_levels=n_levels, seed=seed)
+
+
+# ------------------------------------------------------------ cases for align / matcher / pose-opt / depth filter
+def patch_with_border(img: np.ndarray, px: np.ndarray) -> np.ndarray:
+    """10x10 bilinear patch around sub-pixel px, truncated to u8 -- the procedure of
+    svo/test/test_feature_alignment.cpp:29-52 (generateRefPatchNoWarpInterpolate)."""
+    u_r, v_r = int(np.floor(px[0])), int(np.floor(px[1]))
+    su, sv = np.float32(px[0] - u_r), np.float32(px[1] - v_r)
+    wTL = np.float32((1.0 - su) * (1.0 - sv)); wTR = np.float32(su * (1.0 - sv))
+    wBL = np.float32((1.0 - su) * sv); wBR = np.float32(su * sv)
+    blk = img[v_r - 5: v_r + 6, u_r - 5: u_r + 6].astype(np.float32)
+    val = wTL * blk[:-1, :-1] + wTR * blk[:-1, 1:] + wBL * blk[1:, :-1] + wBR * blk[1:, 1:]
+    return val.astype(np.uint8)  # truncation, as the C assignment to uint8_t
+
+
+def make_align_case(seed: int, m: int, width: int = 640, height: int = 480, n_levels: int = 3) -> dict:
+    """m independent align2D/align1D problems on the levels of one rendered frame."""
+    rng = np.random.default_rng(seed)
+    cam = camera_for(width, height)
+    pyr = build_pyramid(render(cam, base_pose(), Plane.tilted(), make_texture(7)), n_levels)
+    level = rng.integers(0, n_levels, m).astype(np.int32)
+    px_true = np.zeros((m, 2)); px_start = np.zeros((m, 2))
+    pwb = np.zeros((m, 100), np.uint8); patch = np.zeros((m, 64), np.uint8)
+    direction = np.zeros((m, 2), np.float32)
+    for i in range(m):
+        im = pyr[level[i]]
+        h, w = im.shape
+        margin = 12 if i % 10 else 5  # every 10th problem starts close to the border
+        px_true[i] = [rng.uniform(margin, w - margin), rng.uniform(margin, h - margin)]
+        p = patch_with_border(im, px_true[i])
+        pwb[i] = p.ravel()
+        patch[i] = p[1:9, 1:9].ravel()
+        off = rng.uniform(-1.5, 1.5, 2)
+        px_start[i] = px_true[i] - off
+        d = off / (np.linalg.norm(off) + 1e-12)
+        direction[i] = d.astype(np.float32)
+    return dict(cam=cam, pyr=pyr, level=level, px_true=px_true, px_start=px_start, pwb=pwb, patch=patch,
+                dir=direction)
+
+
+def make_two_view(seed: int, width: int = 752, height: int = 480, n_levels: int = 5, baseline: float = 0.3,
+                  rot_deg: float = 2.0) -> dict:
+    """Reference keyframe + current frame with a real baseline (geometry of svo/test/test_matcher.cpp:52-57)."""
+    rng = np.random.default_rng(seed)
+    cam = camera_for(width, height)
+    plane, tex = Plane.tilted(), make_texture(7)
+    T_ref_w = base_pose()
+    d = rng.normal(size=3); d[2] *= 0.2; d *= baseline / np.linalg.norm(d)
+    xi = np.concatenate([d, np.deg2rad(rng.uniform(-rot_deg, rot_deg, 3))])
+    T_cur_w = se3_mul(se3_exp(xi), T_ref_w)
+    ref_pyr = build_pyramid(render(cam, T_ref_w, plane, tex), n_levels)
+    cur_pyr = build_pyramid(render(cam, T_cur_w, plane, tex), n_levels)
+    return dict(cam=cam, plane=plane, T_ref_w=T_ref_w, T_cur_w=T_cur_w, ref_pyr=ref_pyr, cur_pyr=cur_pyr,
+                n_levels=n_levels, rng=rng)
+
+
+def make_match_case(seed: int, m: int, **kw) -> dict:
+    """m Matcher::findMatchDirect candidates: reference features with 3D points and a current-frame
+    guess within ~1.5 px of the true reprojection."""
+    tv = make_two_view(seed, baseline=kw.pop("baseline", 0.12), **kw)
+    rng, cam = tv["rng"], tv["cam"]
+    level = rng.integers(0, 3, m).astype(np.int32)
+    px = np.stack([rng.uniform(40, cam.width - 40, m), rng.uniform(40, cam.height - 40, m)], axis=1)
+    px = np.round(px / (1 << level)[:, None]) * (1 << level)[:, None]  # detected at integer level pixels
+    f = cam.cam2world(px)
+    pos = intersect(tv["plane"], tv["T_ref_w"], f)
+    Tc = tv["T_cur_w"]
+    pc = pos @ Tc[:, :3].T + Tc[:, 3]
+    px_cur_true = cam.world2cam(pc)
+    px_cur = px_cur_true + rng.uniform(-1.5, 1.5, (m, 2))
+    ftr_type = (rng.uniform(size=m) < 0.15).astype(np.int32)
+    ang = rng.uniform(0, 2 * np.pi, m)
+    grad = np.stack([np.cos(ang), np.sin(ang)], axis=1)
+    tv.update(M=m, ref_px=px, ref_f=f, ref_level=level, ftr_type=ftr_type, ref_grad=grad, point_pos=pos,
+              px_cur=px_cur, px_cur_true=px_cur_true)
+    return tv
+
+
+def make_depth_case(seed: int, n_seeds: int = 2000, **kw) -> dict:
+    """BASELINE config C2: seeds `Seed(ftr, 2.0, 0.5)` (svo/test/test_depth_filter.cpp:128) on a jittered
+    grid of integer pixels of a 752x480 keyframe, one current frame with a baseline."""
+    tv = make_two_view(seed, **kw)
+    rng, cam = tv["rng"], tv["cam"]
+    px = np.floor(jittered_features(rng, cam, n_seeds, margin=6.0))
+    level = rng.integers(0, 3, n_seeds).astype(np.int32)
+    px = np.floor(px / (1 << level)[:, None]) * (1 << level)[:, None]
+    f = cam.cam2world(px)
+    ftr_type = (rng.uniform(size=n_seeds) < 0.1).astype(np.int32)
+    ang = rng.uniform(0, 2 * np.pi, n_seeds)
+    grad = np.stack([np.cos(ang), np.sin(ang)], axis=1)
+    depth_mean, depth_min = np.float32(2.0), np.float32(0.5)
+    z_range = np.float32(1.0) / depth_min  # depth_filter.cpp:37-46
+    seeds = dict(a=np.full(n_seeds, 10, np.float32), b=np.full(n_seeds, 10, np.float32),
+                 mu=np.full(n_seeds, np.float32(1.0) / depth_mean, np.float32),
+                 z_range=np.full(n_seeds, z_range, np.float32),
+                 sigma2=np.full(n_seeds, z_range * z_range / np.float32(36), np.float32))
+    batch_id = np.where(rng.uniform(size=n_seeds) < 0.03, 0, 5).astype(np.int32)  # a few too-old seeds
+    depth_gt = np.linalg.norm(intersect(tv["plane"], tv["T_ref_w"], f) - se3_inv(tv["T_ref_w"])[:, 3], axis=1)
+    tv.update(M=n_seeds, ftr_px=px, ftr_f=f, ftr_level=level, ftr_type=ftr_type, ftr_grad=grad, seeds=seeds,
+              batch_id=batch_id, batch_counter=6, ref_index=np.zeros(n_seeds, np.int32), depth_gt=depth_gt)
+    return tv
+
+
+def make_pose_opt_case(seed: int, n: int = 1000, width: int = 1920, height: int = 1080, px_noise: float = 1.0,
+                       outlier_frac: float = 0.03) -> dict:
+    """BASELINE config C3 (pose optimizer part): n observations with N(0, px_noise) pixel noise
+    (svo/test/test_pose_optimizer.cpp:92), a few gross outliers, perturbed initial pose."""
+    rng = np.random.default_rng(seed)
+    cam = camera_for(width, height)
+    plane = Plane.tilted()
+    T_true = base_pose()
+    px = np.stack([rng.uniform(20, width - 20, n), rng.uniform(20, height - 20, n)], axis=1)
+    pos = intersect(plane, T_true, cam.cam2world(px))
+    noisy = px + rng.normal(0, px_noise, (n, 2))
+    k = int(outlier_frac * n)
+    if k:
+        noisy[rng.choice(n, k, replace=False)] += rng.uniform(-25, 25, (k, 2))
+    f = cam.cam2world(noisy)
+    level = rng.integers(0, 3, n).astype(np.int32)
+    has_point = (rng.uniform(size=n) > 0.02).astype(np.uint8)
+    T_init = se3_mul(se3_exp(np.concatenate([rng.uniform(-0.05, 0.05, 3), rng.uniform(-0.01, 0.01, 3)])), T_true)
+    return dict(cam=cam, f=f, pos=pos, level=level, has_point=has_point, T_init=T_init, T_true=T_true)
