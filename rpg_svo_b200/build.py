@@ -44,7 +44,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for cmd, p in procs:
         if p.wait() != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    cmd = [_nvcc(), "-shared", "-cudart", "static", "-o", OUT] + objs
+    cmd = [_nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs
     subprocess.check_call(cmd)
     return OUT
 

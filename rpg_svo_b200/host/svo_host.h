@@ -1,0 +1,374 @@
+// rpg_svo_b200/host/svo_host.h -- C++ host classes that keep the reference's call surface for the
+// hot path and forward to the C ABI (include/svo_b200.h).  Header-only, depends on nothing but the
+// C++17 standard library and libsvo_b200.so.
+//
+// What is mirrored (names, argument meaning, error behaviour):
+//   svo::SparseImgAlign(max_level, min_level, n_iter, method, display, verbose)::run(ref, cur)
+//       + getFisherInformation()                      svo/include/svo/sparse_img_align.h:43-57
+//   svo::pose_optimizer::optimizeGaussNewton(...)     svo/include/svo/pose_optimizer.h:37-45
+//   svo::feature_alignment::align2D / align1D         svo/include/svo/feature_alignment.h:29-44
+//   svo::DepthFilter::{addFrame, addKeyframe(seeds), removeKeyframe, reset, getSeeds, updateSeeds}
+//       + static updateSeed/computeTau stay host-side in the reference and are not re-exported
+//                                                     svo/include/svo/depth_filter.h:101-158
+//   svo::Frame / Feature / Point / Seed               svo/include/svo/{frame,feature,point,depth_filter}.h
+// The data model is the reference's pointer graph (std::list<Feature*>, Point*); the wrappers gather it
+// into the flat arrays the C ABI takes -- that gather is the cost SURVEY.md row a18 says must be
+// counted end to end.  Differences from the reference, all forced by the missing third-party types:
+//   * Eigen/Sophus/cv::Mat are replaced by the minimal Vector2d/Vector3d/SE3/Image below;
+//   * FramePtr is std::shared_ptr (reference: boost::shared_ptr);
+//   * the camera is the pinhole-without-distortion model only;
+//   * DepthFilter has no detector: addKeyframe takes the new features explicitly, and the mapper
+//     thread / halt flag are the caller's (updateSeeds is synchronous, as in the reference when
+//     thread_ == NULL, depth_filter.cpp:95-96).
+#pragma once
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <list>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/svo_b200.h"
+
+namespace svo {
+
+using Vector2d = std::array<double, 2>;
+using Vector3d = std::array<double, 3>;
+using Matrix6d = std::array<double, 36>;  // row-major
+
+// Minimal rigid transform, row-major [R|t]; only what the wrappers need on the host.
+struct SE3 {
+  double m[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  SE3 operator*(const SE3& o) const {
+    SE3 r;
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j)
+        r.m[i * 4 + j] = m[i * 4] * o.m[j] + m[i * 4 + 1] * o.m[4 + j] + m[i * 4 + 2] * o.m[8 + j];
+      r.m[i * 4 + 3] = m[i * 4] * o.m[3] + m[i * 4 + 1] * o.m[7] + m[i * 4 + 2] * o.m[11] + m[i * 4 + 3];
+    }
+    return r;
+  }
+  SE3 inverse() const {
+    SE3 r;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) r.m[i * 4 + j] = m[j * 4 + i];
+    for (int i = 0; i < 3; ++i) r.m[i * 4 + 3] = -(r.m[i * 4] * m[3] + r.m[i * 4 + 1] * m[7] + r.m[i * 4 + 2] * m[11]);
+    return r;
+  }
+  Vector3d translation() const { return {m[3], m[7], m[11]}; }
+};
+
+struct PinholeCamera {  // [EXT] vk::PinholeCamera without distortion
+  int width_, height_;
+  double fx_, fy_, cx_, cy_;
+  PinholeCamera(int w, int h, double fx, double fy, double cx, double cy) : width_(w), height_(h), fx_(fx), fy_(fy), cx_(cx), cy_(cy) {}
+  Vector3d cam2world(const Vector2d& px) const {
+    double x = (px[0] - cx_) / fx_, y = (px[1] - cy_) / fy_, n = std::sqrt(x * x + y * y + 1.0);
+    return {x / n, y / n, 1.0 / n};
+  }
+  double errorMultiplier2() const { return std::fabs(fx_); }
+  svo_b200_camera c_abi() const { return svo_b200_camera{fx_, fy_, cx_, cy_, width_, height_}; }
+};
+
+// One CUDA context per calling thread, as include/svo_b200.h asks.
+class Context {
+ public:
+  explicit Context(int device = 0) {
+    if (svo_b200_create(&ctx_, device) != 0)
+      throw std::runtime_error("svo_b200_create failed: no usable CUDA device (there is no CPU fallback)");
+  }
+  ~Context() { svo_b200_destroy(ctx_); }
+  Context(const Context&) = delete;
+  Context& operator=(const Context&) = delete;
+  svo_b200_ctx* get() const { return ctx_; }
+  void check(int rc) const {
+    if (rc != 0) throw std::runtime_error(std::string("svo_b200: ") + svo_b200_last_error(ctx_));
+  }
+
+ private:
+  svo_b200_ctx* ctx_ = nullptr;
+};
+
+class Frame;
+struct Point {  // svo/include/svo/point.h:35-106 (the fields the hot path reads)
+  Vector3d pos_;
+  explicit Point(const Vector3d& pos) : pos_(pos) {}
+};
+
+struct Feature {  // svo/include/svo/feature.h:25-71
+  enum FeatureType { CORNER, EDGELET };
+  FeatureType type = CORNER;
+  Frame* frame;
+  Vector2d px;
+  Vector3d f;
+  int level;
+  Point* point = nullptr;
+  Vector2d grad{1.0, 0.0};
+  Feature(Frame* _frame, const Vector2d& _px, int _level);
+  Feature(Frame* _frame, Point* _point, const Vector2d& _px, const Vector3d& _f, int _level)
+      : frame(_frame), px(_px), f(_f), level(_level), point(_point) {}
+};
+typedef std::list<Feature*> Features;
+
+// svo/include/svo/frame.h:40-139.  The image pyramid lives in HBM (level 0 uploaded once, the other
+// levels built on the device with the scalar vk::halfSample rule).
+class Frame {
+ public:
+  PinholeCamera* cam_;
+  SE3 T_f_w_;
+  Matrix6d Cov_{};
+  Features fts_;
+  bool is_keyframe_ = false;
+  Frame(Context& ctx, PinholeCamera* cam, const uint8_t* img, int n_levels, double /*timestamp*/) : cam_(cam), ctx_(ctx) {
+    if (!img) throw std::runtime_error("Frame: provided image is empty");  // frame.cpp:51-52
+    ctx_.check(svo_b200_frame_create(ctx_.get(), cam->width_, cam->height_, n_levels, &dev_));
+    const uint8_t* lv[1] = {img};
+    ctx_.check(svo_b200_frame_upload(ctx_.get(), dev_, lv, 1));
+    ctx_.check(svo_b200_synchronize(ctx_.get()));
+  }
+  ~Frame() {
+    for (Feature* f : fts_) delete f;  // frame.cpp:43-46
+    svo_b200_frame_destroy(ctx_.get(), dev_);
+  }
+  Frame(const Frame&) = delete;
+  void addFeature(Feature* ftr) { fts_.push_back(ftr); }
+  void setKeyframe() { is_keyframe_ = true; }
+  bool isKeyframe() const { return is_keyframe_; }
+  Vector3d pos() const { return T_f_w_.inverse().translation(); }  // frame.h:112
+  size_t nObs() const { return fts_.size(); }
+  svo_b200_frame* device() const { return dev_; }
+  Context& context() const { return ctx_; }
+
+ private:
+  Context& ctx_;
+  svo_b200_frame* dev_ = nullptr;
+};
+typedef std::shared_ptr<Frame> FramePtr;
+
+inline Feature::Feature(Frame* _frame, const Vector2d& _px, int _level)
+    : frame(_frame), px(_px), f(_frame->cam_->cam2world(_px)), level(_level) {}
+
+// ------------------------------------------------------------------------------------------------
+// svo::SparseImgAlign (svo/include/svo/sparse_img_align.h:33-81)
+// ------------------------------------------------------------------------------------------------
+class SparseImgAlign {
+ public:
+  enum Method { GaussNewton, LevenbergMarquardt };  // [EXT] vk::NLLSSolver::Method; only GaussNewton is used
+  SparseImgAlign(int max_level, int min_level, int n_iter, Method method, bool /*display*/, bool /*verbose*/)
+      : max_level_(max_level), min_level_(min_level), n_iter_(n_iter) {
+    if (method != GaussNewton) throw std::invalid_argument("SparseImgAlign: only GaussNewton is implemented");
+    H_.fill(0.0);
+  }
+  // sparse_img_align.cpp:43-75
+  size_t run(FramePtr ref_frame, FramePtr cur_frame) {
+    if (ref_frame->fts_.empty()) return 0;  // "SparseImgAlign: no features to track!"
+    const size_t n = ref_frame->fts_.size();
+    std::vector<double> px(2 * n), f(3 * n), pos(3 * n, 0.0);
+    std::vector<uint8_t> has_point(n);
+    size_t i = 0;
+    for (Feature* ft : ref_frame->fts_) {
+      px[2 * i] = ft->px[0]; px[2 * i + 1] = ft->px[1];
+      for (int k = 0; k < 3; ++k) f[3 * i + k] = ft->f[k];
+      has_point[i] = ft->point != nullptr;
+      if (ft->point) for (int k = 0; k < 3; ++k) pos[3 * i + k] = ft->point->pos_[k];
+      ++i;
+    }
+    SE3 T_cur_from_ref = cur_frame->T_f_w_ * ref_frame->T_f_w_.inverse();  // :59
+    const Vector3d ref_pos = ref_frame->pos();
+    const svo_b200_camera cam = ref_frame->cam_->c_abi();
+    const svo_b200_sia_options opt = {max_level_, min_level_, n_iter_, 0.000001};  // eps_ (:40)
+    svo_b200_sia_stats st;
+    visible_fts_.assign(n, 0);
+    Context& c = ref_frame->context();
+    c.check(svo_b200_sparse_img_align(c.get(), ref_frame->device(), cur_frame->device(), &cam, &opt, T_cur_from_ref.m,
+                                      px.data(), f.data(), pos.data(), has_point.data(), ref_pos.data(), (int)n,
+                                      visible_fts_.data(), H_.data(), &st, nullptr, 0, nullptr));
+    cur_frame->T_f_w_ = T_cur_from_ref * ref_frame->T_f_w_;  // :70
+    return (size_t)st.n_tracked;                              // n_meas_/patch_area_ (:74)
+  }
+  // sparse_img_align.cpp:77-82
+  Matrix6d getFisherInformation() const {
+    const double sigma_i_sq = 5e-4 * 255 * 255;
+    Matrix6d I;
+    for (int k = 0; k < 36; ++k) I[k] = H_[k] / sigma_i_sq;
+    return I;
+  }
+  const std::vector<uint8_t>& visibleFeatures() const { return visible_fts_; }
+
+ private:
+  int max_level_, min_level_, n_iter_;
+  Matrix6d H_;
+  std::vector<uint8_t> visible_fts_;
+};
+
+// ------------------------------------------------------------------------------------------------
+// svo::pose_optimizer (svo/include/svo/pose_optimizer.h:37-45)
+// ------------------------------------------------------------------------------------------------
+namespace pose_optimizer {
+inline void optimizeGaussNewton(const double reproj_thresh, const size_t n_iter, const bool /*verbose*/, FramePtr& frame,
+                                double& estimated_scale, double& error_init, double& error_final, size_t& num_obs) {
+  const size_t n = frame->fts_.size();
+  std::vector<double> f(3 * n), pos(3 * n, 0.0);
+  std::vector<int> level(n);
+  std::vector<uint8_t> has_point(n);
+  size_t i = 0;
+  for (Feature* ft : frame->fts_) {
+    for (int k = 0; k < 3; ++k) f[3 * i + k] = ft->f[k];
+    level[i] = ft->level;
+    has_point[i] = ft->point != nullptr;
+    if (ft->point) for (int k = 0; k < 3; ++k) pos[3 * i + k] = ft->point->pos_[k];
+    ++i;
+  }
+  size_t n_with_point = 0;
+  for (uint8_t h : has_point) n_with_point += h;
+  if (n_with_point == 0) return;  // errors.empty(): outputs untouched (pose_optimizer.cpp:57-58)
+  svo_b200_pose_opt_result out;
+  Context& c = frame->context();
+  c.check(svo_b200_pose_optimize(c.get(), reproj_thresh, (int)n_iter, frame->cam_->errorMultiplier2(), frame->T_f_w_.m,
+                                 f.data(), pos.data(), level.data(), has_point.data(), (int)n, &out));
+  i = 0;
+  for (Feature* ft : frame->fts_) {  // culled observations lose their point (:139-143)
+    if (ft->point && !has_point[i]) ft->point = nullptr;
+    ++i;
+  }
+  for (int k = 0; k < 36; ++k) frame->Cov_[k] = out.cov[k];
+  estimated_scale = out.estimated_scale;
+  error_init = out.error_init;
+  error_final = out.error_final;
+  num_obs = (size_t)out.num_obs;
+}
+}  // namespace pose_optimizer
+
+// ------------------------------------------------------------------------------------------------
+// svo::feature_alignment (svo/include/svo/feature_alignment.h:29-44).  `cur_img` of the reference is
+// (frame, level) here because the pyramid lives on the device.
+// ------------------------------------------------------------------------------------------------
+namespace feature_alignment {
+inline bool align2D(const Frame& cur_frame, int level, uint8_t* ref_patch_with_border, uint8_t* ref_patch, const int n_iter,
+                    Vector2d& cur_px_estimate, bool /*no_simd*/ = false) {
+  uint8_t conv = 0;
+  Context& c = cur_frame.context();
+  c.check(svo_b200_align2d_batch(c.get(), cur_frame.device(), 1, &level, ref_patch_with_border, ref_patch, n_iter,
+                                 cur_px_estimate.data(), &conv));
+  return conv != 0;
+}
+inline bool align1D(const Frame& cur_frame, int level, const std::array<float, 2>& dir, uint8_t* ref_patch_with_border,
+                    uint8_t* ref_patch, const int n_iter, Vector2d& cur_px_estimate, double& h_inv) {
+  uint8_t conv = 0;
+  Context& c = cur_frame.context();
+  c.check(svo_b200_align1d_batch(c.get(), cur_frame.device(), 1, &level, dir.data(), ref_patch_with_border, ref_patch,
+                                 n_iter, cur_px_estimate.data(), &conv, &h_inv));
+  return conv != 0;
+}
+}  // namespace feature_alignment
+
+// ------------------------------------------------------------------------------------------------
+// svo::DepthFilter (svo/include/svo/depth_filter.h:35-51,53-158)
+// ------------------------------------------------------------------------------------------------
+struct Seed {
+  static int& batch_counter() { static int c = 0; return c; }
+  static int& seed_counter() { static int c = 0; return c; }
+  int batch_id, id;
+  Feature* ftr;
+  float a, b, mu, z_range, sigma2;
+  Seed(Feature* _ftr, float depth_mean, float depth_min)  // depth_filter.cpp:37-46
+      : batch_id(batch_counter()), id(seed_counter()++), ftr(_ftr), a(10), b(10), mu(1.0 / depth_mean),
+        z_range(1.0 / depth_min), sigma2(z_range * z_range / 36) {}
+};
+
+class DepthFilter {
+ public:
+  typedef std::function<void(Point*, double)> callback_t;
+  struct Options {
+    int max_n_kfs = 3;
+    double seed_convergence_sigma2_thresh = 200.0;
+    int max_search_level = 2;  // Config::nPyrLevels()-1 with the non-ROS default n_pyr_levels = 3
+  } options_;
+  explicit DepthFilter(callback_t seed_converged_cb) : seed_converged_cb_(seed_converged_cb) {}
+  // addKeyframe + initializeSeeds (depth_filter.cpp:101-132) with the detector's output passed in
+  void addKeyframe(FramePtr frame, const std::vector<Feature*>& new_features, double depth_mean, double depth_min) {
+    keyframes_.push_back(frame);
+    ++Seed::batch_counter();
+    for (Feature* ftr : new_features) seeds_.push_back(Seed(ftr, (float)depth_mean, (float)depth_min));
+  }
+  void addFrame(FramePtr frame) { updateSeeds(frame); }  // synchronous branch (:95-96)
+  void removeKeyframe(FramePtr frame) {                  // :134-151
+    seeds_.remove_if([&](const Seed& s) { return s.ftr->frame == frame.get(); });
+    keyframes_.remove(frame);
+  }
+  void reset() { seeds_.clear(); keyframes_.clear(); }
+  std::list<Seed>& getSeeds() { return seeds_; }
+  size_t n_failed_matches_ = 0, n_updates_ = 0;
+
+  // depth_filter.cpp:197-291: one launch for all seeds, then the list side effects in list order
+  virtual void updateSeeds(FramePtr frame) {
+    const size_t M = seeds_.size();
+    if (M == 0) return;
+    std::vector<FramePtr> refs(keyframes_.begin(), keyframes_.end());
+    std::vector<const svo_b200_frame*> ref_dev(refs.size());
+    std::vector<double> ref_T(12 * refs.size());
+    for (size_t r = 0; r < refs.size(); ++r) { ref_dev[r] = refs[r]->device(); std::memcpy(&ref_T[12 * r], refs[r]->T_f_w_.m, sizeof(double) * 12); }
+    std::vector<int> ref_index(M), level(M), type(M), batch(M);
+    std::vector<double> px(2 * M), f(3 * M), grad(2 * M), px_cur(2 * M), z(M);
+    std::vector<float> a(M), b(M), mu(M), zr(M), s2(M);
+    std::vector<uint8_t> status(M);
+    size_t i = 0;
+    for (const Seed& s : seeds_) {
+      size_t r = 0;
+      while (r < refs.size() && refs[r].get() != s.ftr->frame) ++r;
+      if (r == refs.size()) throw std::runtime_error("DepthFilter: seed references a frame that is not a keyframe");
+      ref_index[i] = (int)r; level[i] = s.ftr->level; type[i] = s.ftr->type; batch[i] = s.batch_id;
+      px[2 * i] = s.ftr->px[0]; px[2 * i + 1] = s.ftr->px[1];
+      grad[2 * i] = s.ftr->grad[0]; grad[2 * i + 1] = s.ftr->grad[1];
+      for (int k = 0; k < 3; ++k) f[3 * i + k] = s.ftr->f[k];
+      a[i] = s.a; b[i] = s.b; mu[i] = s.mu; zr[i] = s.z_range; s2[i] = s.sigma2;
+      ++i;
+    }
+    const svo_b200_camera cam = frame->cam_->c_abi();
+    const svo_b200_depth_options opt = {options_.max_n_kfs, options_.seed_convergence_sigma2_thresh,
+                                        options_.max_search_level, 10, 1000};
+    Context& c = frame->context();
+    c.check(svo_b200_depth_filter_update(c.get(), ref_dev.data(), ref_T.data(), (int)refs.size(), frame->device(),
+                                         frame->T_f_w_.m, &cam, &opt, (int)M, ref_index.data(), px.data(), f.data(),
+                                         level.data(), type.data(), grad.data(), batch.data(), Seed::batch_counter(),
+                                         a.data(), b.data(), mu.data(), zr.data(), s2.data(), status.data(),
+                                         px_cur.data(), z.data(), nullptr));
+    i = 0;
+    for (auto it = seeds_.begin(); it != seeds_.end(); ++i) {
+      it->a = a[i]; it->b = b[i]; it->mu = mu[i]; it->sigma2 = s2[i];
+      switch (status[i]) {
+        case SVO_B200_SEED_TOO_OLD: it = seeds_.erase(it); continue;                       // :216-219
+        case SVO_B200_SEED_NO_MATCH: ++n_failed_matches_; break;                           // :240-244
+        case SVO_B200_SEED_CONVERGED: {                                                    // :261-282
+          ++n_updates_;
+          const SE3 T_w_f = it->ftr->frame->T_f_w_.inverse();
+          const double d = 1.0 / it->mu;
+          const Vector3d p{it->ftr->f[0] * d, it->ftr->f[1] * d, it->ftr->f[2] * d};
+          Vector3d xyz_world;
+          for (int r = 0; r < 3; ++r) xyz_world[r] = T_w_f.m[r * 4] * p[0] + T_w_f.m[r * 4 + 1] * p[1] + T_w_f.m[r * 4 + 2] * p[2] + T_w_f.m[r * 4 + 3];
+          Point* point = new Point(xyz_world);
+          it->ftr->point = point;
+          seed_converged_cb_(point, it->sigma2);
+          it = seeds_.erase(it);
+          continue;
+        }
+        case SVO_B200_SEED_NAN: ++n_updates_; it = seeds_.erase(it); continue;             // :283-287
+        case SVO_B200_SEED_UPDATED: ++n_updates_; break;
+        default: break;  // behind the camera / not in frame: untouched
+      }
+      ++it;
+    }
+  }
+  virtual ~DepthFilter() = default;
+
+ protected:
+  callback_t seed_converged_cb_;
+  std::list<Seed> seeds_;
+  std::list<FramePtr> keyframes_;
+};
+
+}  // namespace svo
