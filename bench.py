@@ -42,13 +42,14 @@ W, H, NFEAT, NLEVELS, MAX_LEVEL, MIN_LEVEL, NITER = 640, 480, 300, 5, 4, 0, 30
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs-per-gpu", type=int, default=592)
     ap.add_argument("--cpu-sample", type=int, default=256, help="pairs timed by the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the C2/C3 side measurements")
     return ap.parse_args()
 
 
@@ -182,6 +183,72 @@ def _has_cuda() -> bool:
         return False
 
 
+
+def measure_other_paths(ctx, rank: int) -> dict:
+    """BASELINE configs C2 (DepthFilter, 2000 seeds, 752x480) and C3 (HD 1920x1080, 1000 features: align2D +
+    pose_optimizer) through the C ABI with host buffers (each call = H2D + one kernel + D2H + sync), next to
+    the single-thread CPU oracle on the same inputs.  Reported as extra keys; not the headline metric."""
+    import time as _t
+
+    from oracle import binding as ob  # checker / CPU baseline only
+    from rpg_svo_b200 import synth
+
+    out = {}
+
+    def timeit(fn, reps):
+        fn()
+        t0 = _t.perf_counter()
+        for _ in range(reps):
+            fn()
+        return (_t.perf_counter() - t0) / reps
+
+    # ---- C2: DepthFilter::updateSeeds --------------------------------------------------------
+    c = synth.make_depth_case(2031, 2000, baseline=0.3)
+    ref, cur = ctx.frame(c["ref_pyr"]), ctx.frame(c["cur_pyr"])
+    args = ([ref], [c["T_ref_w"]], cur, c["T_cur_w"], c["cam"], c["ref_index"], c["ftr_px"], c["ftr_f"], c["ftr_level"],
+            c["ftr_type"], c["ftr_grad"], c["batch_id"], c["batch_counter"], c["seeds"])
+    g = ctx.depth_filter_update(*args)
+    t_gpu = timeit(lambda: ctx.depth_filter_update(*args), 20)
+    oargs = ([c["ref_pyr"]], [c["T_ref_w"]], c["cur_pyr"], c["T_cur_w"], c["cam"], c["ref_index"], c["ftr_px"], c["ftr_f"],
+             c["ftr_level"], c["ftr_type"], c["ftr_grad"], c["batch_id"], c["batch_counter"], c["seeds"])
+    o = ob.depth_filter_update(*oargs)
+    t_cpu = timeit(lambda: ob.depth_filter_update(*oargs), 5)
+    evals = int(g["n_zmssd"].sum())
+    alg = 2000 * (48 + 64 + 400) + 64 * evals + 81 * 10 * int((g["status"] >= 4).sum())
+    out["depth_filter_C2"] = {"seeds": 2000, "gpu_seeds_per_s_e2e": 2000 / t_gpu, "cpu_port_seeds_per_s_1thread": 2000 / t_cpu,
+                              "ms_per_call_e2e": 1e3 * t_gpu, "zmssd_evals": evals, "algorithmic_bytes": alg,
+                              "status_bit_exact_vs_oracle": bool(np.array_equal(g["status"], o["status"])),
+                              "updated": int((g["status"] >= 5).sum())}
+    ref.destroy(); cur.destroy()
+
+    # ---- C3: HD align2D (1000 features, 10 iterations) + pose_optimizer (1000 observations) -----
+    a = synth.make_align_case(3001, 1000, 1920, 1080, n_levels=6)
+    fr = ctx.frame(a["pyr"])
+    conv, px = ctx.align2d_batch(fr, a["level"], a["pwb"], a["patch"], 10, a["px_start"])
+    t_gpu = timeit(lambda: ctx.align2d_batch(fr, a["level"], a["pwb"], a["patch"], 10, a["px_start"]), 20)
+
+    def cpu_align():
+        for i in range(1000):
+            ob.align2d(a["pyr"][a["level"][i]], a["pwb"][i], a["patch"][i], 10, a["px_start"][i])
+
+    t_cpu = timeit(cpu_align, 2)
+    out["align2d_C3"] = {"features": 1000, "gpu_features_per_s_e2e": 1000 / t_gpu, "cpu_port_features_per_s_1thread": 1000 / t_cpu,
+                         "ms_per_call_e2e": 1e3 * t_gpu, "converged": int(conv.sum()),
+                         "note": "CPU figure includes ~1 us/feature of ctypes call overhead"}
+    fr.destroy()
+    pcase = synth.make_pose_opt_case(1005, 1000, 1920, 1080)
+    pargs = (2.0, 10, pcase["cam"].fx, pcase["T_init"], pcase["f"], pcase["pos"], pcase["level"], pcase["has_point"])
+    gp = ctx.pose_optimize(*pargs)
+    t_gpu = timeit(lambda: ctx.pose_optimize(*pargs), 20)
+    op = ob.pose_optimize(*pargs)
+    t_cpu = timeit(lambda: ob.pose_optimize(*pargs), 10)
+    out["pose_optimizer_C3"] = {"observations": 1000, "gpu_frames_per_s_e2e": 1 / t_gpu, "cpu_port_frames_per_s_1thread": 1 / t_cpu,
+                                "ms_per_call_e2e": 1e3 * t_gpu, "iterations": int(gp["n_iter_done"]),
+                                "pose_diff_vs_oracle_m": float(synth.pose_error(gp["T"], op["T"])[0]),
+                                "algorithmic_bytes": 52 * 1000 * (int(gp["n_iter_done"]) + 2)}
+    return out
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -232,13 +299,14 @@ def main():
         return float(t.item())
 
     # ---------------- leg 1: device-resident (value) ----------------
+    # clocks / throttle reasons are sampled from here to the end of the e2e leg (both timed regions)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     upload_all()
     stage()
     for _ in range(max(Wm, 3)):
         ctx.sia_batch_run()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -248,7 +316,6 @@ def main():
     barrier()
     launches = ctx.launch_count() - l0
     ms_dev = max_over_ranks(e0.elapsed_time(e1))
-    clocks = sampler.stop()
     res = ctx.sia_batch_fetch()
     stats = res["stats"]
     alg_bytes = sum(algorithmic_bytes(stats[b], NFEAT) for b in range(B))
@@ -300,6 +367,11 @@ def main():
         d2h = B * (96 + 288 + 16) + B * NFEAT
         e2e = {"value": world * B * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / K}
+
+    clocks = sampler.stop()
+    other = None
+    if rank == 0 and world == 1 and not args.no_extras:
+        other = measure_other_paths(ctx, rank)
 
     # ---------------- CPU baseline (rank 0, N == 1 only) ----------------
     cpu = None
@@ -354,7 +426,8 @@ def main():
                              "traffic": traffic, "peak_source": peak_src, "kernel": "svo::sia_kernel<1,false>",
                              "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
                              "mean_gn_iterations_per_pair": float(np.mean(stats["n_iters"]))},
-                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+                "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+                "other_paths": other}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

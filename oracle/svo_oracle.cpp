@@ -401,16 +401,33 @@ void orc_sparse_img_align_batch(int B, const uint8_t* const* ref_levels,
                                 double eps, int64_t* n_tracked_out, int n_threads) {
   std::atomic<int> next(0);
   auto worker = [&]() {
+    // one solver object per worker: its caches are allocated once and reused for every pair this
+    // thread processes (a fresh 230 KB Jacobian cache per pair would go through mmap/munmap and
+    // serialise the threads in the kernel).
+    SparseImgAlign sia(max_level, min_level, n_iter, eps);
+    sia.cam = make_cam(cam);
+    Img rp[ORC_MAX_LEVELS], cp[ORC_MAX_LEVELS];
     for (;;) {
       const int b = next.fetch_add(1);
       if (b >= B) break;
       const int o = feat_offset[b], n = feat_offset[b + 1] - o;
-      const int64_t r = orc_sparse_img_align_run(
-          ref_levels + size_t(b) * n_levels, cur_levels + size_t(b) * n_levels, cols, rows, n_levels, cam,
-          T_io + 12 * size_t(b), px + 2 * size_t(o), f + 3 * size_t(o), point_pos + 3 * size_t(o),
-          has_point + o, ref_pos + 3 * size_t(b), n, max_level, min_level, n_iter, eps, nullptr, nullptr,
-          nullptr, nullptr, 0, nullptr);
-      if (n_tracked_out) n_tracked_out[b] = r;
+      for (int l = 0; l < n_levels && l < ORC_MAX_LEVELS; ++l) {
+        rp[l] = Img{ref_levels[size_t(b) * n_levels + l], cols[l], rows[l], cols[l]};
+        cp[l] = Img{cur_levels[size_t(b) * n_levels + l], cols[l], rows[l], cols[l]};
+      }
+      sia.ref_pyr = rp;
+      sia.cur_pyr = cp;
+      sia.N = n;
+      sia.px = px + 2 * size_t(o);
+      sia.f = f + 3 * size_t(o);
+      sia.pos = point_pos + 3 * size_t(o);
+      sia.has_point = has_point + o;
+      sia.ref_pos = V3{ref_pos[3 * size_t(b)], ref_pos[3 * size_t(b) + 1], ref_pos[3 * size_t(b) + 2]};
+      sia.n_trace = 0;
+      SE3 T = se3_from_rt12(T_io + 12 * size_t(b));
+      const size_t r = sia.run(T);
+      se3_to_rt12(T, T_io + 12 * size_t(b));
+      if (n_tracked_out) n_tracked_out[b] = int64_t(r);
     }
   };
   if (n_threads <= 1) {

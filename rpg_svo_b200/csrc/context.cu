@@ -87,17 +87,17 @@ __global__ void half_sample_kernel(const uint8_t* __restrict__ in, int in_w, int
 // (level l+1 = (a+b+c+d)/4 of level l), so the result is identical to the level-by-level build.
 struct PyrGeom {
   int w[SVO_B200_MAX_LEVELS], h[SVO_B200_MAX_LEVELS];
-  unsigned long long off[SVO_B200_MAX_LEVELS];
+  uint8_t* slab[SVO_B200_MAX_LEVELS];            // level l of frame i at slab[l] + i*stride[l]
+  unsigned long long stride[SVO_B200_MAX_LEVELS];
   int n_levels;
   int tiles_x;
 };
-__global__ void __launch_bounds__(128) pyramid_fused_kernel(uint8_t* __restrict__ slab, size_t stride, int first,
-                                                            PyrGeom g) {
+__global__ void __launch_bounds__(128) pyramid_fused_kernel(int first, PyrGeom g) {
   __shared__ __align__(16) uint8_t t0[16][128];
   __shared__ __align__(16) uint8_t t1[8][64];
   __shared__ __align__(16) uint8_t t2[4][32];
   __shared__ __align__(16) uint8_t t3[2][16];
-  uint8_t* fr = slab + (size_t)(first + blockIdx.y) * stride;
+  const size_t fi = (size_t)(first + blockIdx.y);
   const int tx = blockIdx.x % g.tiles_x, ty = blockIdx.x / g.tiles_x;
   const int t = threadIdx.x;
   const int W0 = g.w[0], H0 = g.h[0];
@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128) pyramid_fused_kernel(uint8_t* __restrict_
     const int y = ty * 16 + r, x = tx * 128 + c;
     uint4 v = make_uint4(0, 0, 0, 0);
     if (y < H0) {
-      const uint8_t* src = fr + g.off[0] + (size_t)y * W0 + x;
+      const uint8_t* src = g.slab[0] + fi * g.stride[0] + (size_t)y * W0 + x;
       if (x + 16 <= W0 && ((W0 & 15) == 0)) {
         v = *reinterpret_cast<const uint4*>(src);
       } else {
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(128) pyramid_fused_kernel(uint8_t* __restrict_
     *reinterpret_cast<uint32_t*>(&t1[r][c]) = o;
     const int y = ty * 8 + r, x = tx * 64 + c, W1 = g.w[1];
     if (y < g.h[1]) {
-      uint8_t* dst = fr + g.off[1] + (size_t)y * W1 + x;
+      uint8_t* dst = g.slab[1] + fi * g.stride[1] + (size_t)y * W1 + x;
       if (x + 4 <= W1 && ((W1 & 3) == 0)) *reinterpret_cast<uint32_t*>(dst) = o;
       else
         for (int k = 0; k < 4; ++k)
@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(128) pyramid_fused_kernel(uint8_t* __restrict_
     const uint8_t o = (uint8_t)(sum >> 2);
     t2[r][c] = o;
     const int y = ty * 4 + r, x = tx * 32 + c;
-    if (y < g.h[2] && x < g.w[2]) fr[g.off[2] + (size_t)y * g.w[2] + x] = o;
+    if (y < g.h[2] && x < g.w[2]) g.slab[2][fi * g.stride[2] + (size_t)y * g.w[2] + x] = o;
   }
   __syncthreads();
   if (g.n_levels > 3 && t < 32) {  // level 3: 2 x 16
@@ -156,13 +156,13 @@ __global__ void __launch_bounds__(128) pyramid_fused_kernel(uint8_t* __restrict_
     const uint8_t o = (uint8_t)(sum >> 2);
     t3[r][c] = o;
     const int y = ty * 2 + r, x = tx * 16 + c;
-    if (y < g.h[3] && x < g.w[3]) fr[g.off[3] + (size_t)y * g.w[3] + x] = o;
+    if (y < g.h[3] && x < g.w[3]) g.slab[3][fi * g.stride[3] + (size_t)y * g.w[3] + x] = o;
   }
   __syncthreads();
   if (g.n_levels > 4 && t < 8) {  // level 4: 1 x 8
     const uint32_t sum = (uint32_t)t3[0][2 * t] + t3[0][2 * t + 1] + t3[1][2 * t] + t3[1][2 * t + 1];
     const int y = ty, x = tx * 8 + t;
-    if (y < g.h[4] && x < g.w[4]) fr[g.off[4] + (size_t)y * g.w[4] + x] = (uint8_t)(sum >> 2);
+    if (y < g.h[4] && x < g.w[4]) g.slab[4][fi * g.stride[4] + (size_t)y * g.w[4] + x] = (uint8_t)(sum >> 2);
   }
 }
 
@@ -264,6 +264,7 @@ int svo_b200_frame_create(svo_b200_ctx* ctx, int width, int height, int n_levels
     delete fr;
     return set_err(ctx, SVO_B200_ENOMEM, "frame_create: cudaMalloc(%zu): %s", off, cudaGetErrorString(e));
   }
+  for (int l = 0; l < n_levels; ++l) fr->lv[l] = fr->base + fr->off[l];
   cudaMemsetAsync(fr->base, 0, fr->bytes, ctx->stream);
   *frame_out = fr;
   return 0;
@@ -318,26 +319,31 @@ int svo_b200_frame_pool_create(svo_b200_ctx* ctx, int width, int height, int n_l
   cudaSetDevice(ctx->device);
   svo_b200_frame proto;
   proto.width = width; proto.height = height; proto.n_levels = n_levels; proto.pooled = true;
-  size_t off = 0;
+  svo_b200_frame_pool* pool = new svo_b200_frame_pool();
+  pool->count = count;
+  pool->n_levels = n_levels;
+  size_t total = 0, slab_off[SVO_B200_MAX_LEVELS];
   for (int l = 0; l < n_levels; ++l) {
     proto.w[l] = l ? proto.w[l - 1] / 2 : width;
     proto.h[l] = l ? proto.h[l - 1] / 2 : height;
-    if (proto.w[l] <= 0 || proto.h[l] <= 0) return set_err(ctx, SVO_B200_EINVAL, "frame_pool_create: level %d is empty", l);
-    proto.off[l] = off;
-    off += ((size_t)proto.w[l] * proto.h[l] + 255 + 16) / 256 * 256;
+    if (proto.w[l] <= 0 || proto.h[l] <= 0) {
+      delete pool;
+      return set_err(ctx, SVO_B200_EINVAL, "frame_pool_create: level %d is empty", l);
+    }
+    pool->stride[l] = ((size_t)proto.w[l] * proto.h[l] + 255) / 256 * 256;
+    slab_off[l] = total;
+    total += pool->stride[l] * (size_t)count + 256;  // slack: kernels fetch aligned words around footprints
   }
-  proto.bytes = off;
-  svo_b200_frame_pool* pool = new svo_b200_frame_pool();
-  pool->count = count;
-  pool->stride = off;
-  cudaError_t e = cudaMalloc((void**)&pool->slab, off * (size_t)count);
+  cudaError_t e = cudaMalloc((void**)&pool->mem, total);
   if (e != cudaSuccess) {
     delete pool;
-    return set_err(ctx, SVO_B200_ENOMEM, "frame_pool_create: cudaMalloc(%zu): %s", off * (size_t)count, cudaGetErrorString(e));
+    return set_err(ctx, SVO_B200_ENOMEM, "frame_pool_create: cudaMalloc(%zu): %s", total, cudaGetErrorString(e));
   }
-  cudaMemsetAsync(pool->slab, 0, off * (size_t)count, ctx->stream);
+  cudaMemsetAsync(pool->mem, 0, total, ctx->stream);
+  for (int l = 0; l < n_levels; ++l) pool->slab[l] = pool->mem + slab_off[l];
   pool->frames.assign(count, proto);
-  for (int i = 0; i < count; ++i) pool->frames[i].base = pool->slab + (size_t)i * off;
+  for (int i = 0; i < count; ++i)
+    for (int l = 0; l < n_levels; ++l) pool->frames[i].lv[l] = pool->slab[l] + (size_t)i * pool->stride[l];
   *pool_out = pool;
   return 0;
 }
@@ -355,20 +361,24 @@ int svo_b200_frame_pool_upload(svo_b200_ctx* ctx, svo_b200_frame_pool* pool, int
   const svo_b200_frame& f0 = pool->frames[0];
   const size_t img = (size_t)f0.w[0] * f0.h[0];
   if (host_stride_bytes < img) return set_err(ctx, SVO_B200_EINVAL, "frame_pool_upload: host stride < image size");
-  // ONE strided copy: row i = level 0 of frame first+i
-  SVO_CUDA_CHECK(ctx, cudaMemcpy2DAsync(pool->slab + (size_t)first * pool->stride, pool->stride, level0_host,
-                                        host_stride_bytes, img, (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+  uint8_t* dst = pool->slab[0] + (size_t)first * pool->stride[0];
+  if (host_stride_bytes == img && pool->stride[0] == img) {  // fully contiguous on both sides: one flat copy
+    SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(dst, level0_host, img * (size_t)count, cudaMemcpyHostToDevice, ctx->stream));
+  } else {  // ONE strided copy: row i = level 0 of frame first+i
+    SVO_CUDA_CHECK(ctx, cudaMemcpy2DAsync(dst, pool->stride[0], level0_host, host_stride_bytes, img, (size_t)count,
+                                          cudaMemcpyHostToDevice, ctx->stream));
+  }
   if (f0.n_levels > 1) {
     PyrGeom g;
     memset(&g, 0, sizeof(g));
     g.n_levels = f0.n_levels < 5 ? f0.n_levels : 5;
-    for (int l = 0; l < f0.n_levels; ++l) { g.w[l] = f0.w[l]; g.h[l] = f0.h[l]; g.off[l] = f0.off[l]; }
+    for (int l = 0; l < f0.n_levels; ++l) { g.w[l] = f0.w[l]; g.h[l] = f0.h[l]; g.slab[l] = pool->slab[l]; g.stride[l] = pool->stride[l]; }
     g.tiles_x = (f0.w[0] + 127) / 128;
     const int tiles_y = (f0.h[0] + 15) / 16;
     for (int done = 0; done < count; done += 32768) {  // gridDim.y limit 65535
       const int n = count - done < 32768 ? count - done : 32768;
       dim3 grid(g.tiles_x * tiles_y, n);
-      pyramid_fused_kernel<<<grid, 128, 0, ctx->stream>>>(pool->slab, pool->stride, first + done, g);
+      pyramid_fused_kernel<<<grid, 128, 0, ctx->stream>>>(first + done, g);
       ctx->launches++;
     }
     SVO_CUDA_CHECK(ctx, cudaGetLastError());
@@ -386,7 +396,7 @@ void svo_b200_frame_pool_destroy(svo_b200_ctx* ctx, svo_b200_frame_pool* pool) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
   }
-  if (pool->slab) cudaFree(pool->slab);
+  if (pool->mem) cudaFree(pool->mem);
   delete pool;
 }
 

@@ -15,13 +15,19 @@ struct svo_b200_frame {
   size_t off[SVO_B200_MAX_LEVELS] = {0};
   size_t bytes = 0;
   bool pooled = false;  // memory belongs to a svo_b200_frame_pool
-  uint8_t* lvl(int l) const { return base + off[l]; }
+  uint8_t* lv[SVO_B200_MAX_LEVELS] = {nullptr};  // level pointers (base + off[l], or into a pool's per-level slabs)
+  uint8_t* lvl(int l) const { return lv[l]; }
 };
 
 struct svo_b200_frame_pool {
   int count = 0;
-  size_t stride = 0;  // bytes between consecutive frames in the slab
-  uint8_t* slab = nullptr;
+  int n_levels = 0;
+  // one slab per pyramid level: level l of frame i at slab[l] + i*stride[l].  Level 0 of consecutive
+  // frames is contiguous up to the 256-byte rounding, so a window uploads as ONE strided copy whose
+  // rows are whole images.
+  uint8_t* slab[SVO_B200_MAX_LEVELS] = {nullptr};
+  size_t stride[SVO_B200_MAX_LEVELS] = {0};
+  uint8_t* mem = nullptr;  // the single allocation behind all slabs
   std::vector<svo_b200_frame> frames;
 };
 

@@ -6,8 +6,8 @@
 // round trip): threads stride over the features, every iteration ends in a 28-value block reduction
 // (21 unique A entries, 6 b entries, chi2), thread 0 factorises the 6x6 system, applies
 // T <- exp(dT) * T and the accept / rollback rule, and broadcasts the pose.  The three medians
-// ([EXT] vk::getMedian = nth_element at floor(n/2)) are exact order statistics obtained by rank
-// counting in shared memory.  All arithmetic is f64 except the f32 error vector / Tukey weight, as
+// ([EXT] vk::getMedian = nth_element at floor(n/2)) are exact order statistics obtained by an
+// 8-pass radix select on order-preserving keys in shared memory.  All arithmetic is f64 except the f32 error vector / Tukey weight, as
 // in the reference.
 #include <cstring>
 
@@ -16,7 +16,7 @@
 
 namespace svo {
 
-constexpr int kPoThreads = 256;
+constexpr int kPoThreads = 512;
 constexpr int kPoWarps = kPoThreads / 32;
 constexpr int kPoK = 28;
 
@@ -43,6 +43,8 @@ struct PoseOptShared {
   Solver6 sol;
   double chi2, scale;
   int done, num_obs, iters, n_deleted;
+  unsigned hist[256];
+  int sel_bin, sel_k;
 };
 
 // [EXT] vk::robust_cost::TukeyWeightFunction::value, b = 4.6851f
@@ -58,11 +60,30 @@ __device__ __forceinline__ float tukey_weight(float x) {
 
 template <int K>
 __device__ __forceinline__ void po_block_sum(double (&v)[K], PoseOptShared& s) {
-  warp_sum<K>(v);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) {
+  if (K == kPoK) {  // 28 = 16 + 8 (transposed reductions) + 4 (tree)
+    double a16[16], a8[8], a4[4];
 #pragma unroll
-    for (int k = 0; k < K; ++k) s.part[warp * kPoK + k] = v[k];
+    for (int k = 0; k < 16; ++k) a16[k] = v[k];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a8[k] = v[16 + k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a4[k] = v[24 + k];
+    warp_reduce_t<16>(a16);
+    warp_reduce_t<8>(a8);
+    warp_sum<4>(a4);
+    if ((lane & 1) == 0) s.part[warp * kPoK + (lane >> 1)] = a16[0];
+    if ((lane & 3) == 0) s.part[warp * kPoK + 16 + (lane >> 2)] = a8[0];
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s.part[warp * kPoK + 24 + k] = a4[k];
+    }
+  } else {
+    warp_sum<K>(v);
+    if (lane == 0) {
+#pragma unroll
+      for (int k = 0; k < K; ++k) s.part[warp * kPoK + k] = v[k];
+    }
   }
   __syncthreads();
   if (warp == 0) {
@@ -76,21 +97,67 @@ __device__ __forceinline__ void po_block_sum(double (&v)[K], PoseOptShared& s) {
   __syncthreads();
 }
 
-// k-th smallest (0-based) of the entries of v[0..N) whose valid flag is set; ties broken by index so
-// exactly one element has rank k.  Result in s.med (NaN if k is out of range).  O(N^2 / threads).
+// k-th smallest (0-based) of the entries of v[0..N) whose valid flag is set: exact order statistic by
+// MSB-first radix select on order-preserving 64-bit keys (8 passes of 8 bits; shared-memory histogram,
+// warp-parallel bin scan).  Result in s.med (NaN if there are no more than k valid entries).
+__device__ __forceinline__ unsigned long long order_key(double d) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(d);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
+}
 __device__ void block_kth(const double* v, const uint8_t* valid, int N, int k, PoseOptShared& s) {
-  if (threadIdx.x == 0) s.med = __longlong_as_double(0x7ff8000000000000LL);
-  __syncthreads();
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
-    if (!valid[i]) continue;
-    const double vi = v[i];
-    int rank = 0;
-    for (int j = 0; j < N; ++j) {
-      if (!valid[j]) continue;
-      const double vj = v[j];
-      rank += (vj < vi || (vj == vi && j < i)) ? 1 : 0;
+  unsigned long long prefix = 0, mask = 0;
+  int kk = k;
+  for (int pass = 7; pass >= 0; --pass) {
+    const int shift = pass * 8;
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) s.hist[b] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x) {
+      if (!valid[i]) continue;
+      const unsigned long long key = order_key(v[i]);
+      if ((key & mask) == prefix) atomicAdd(&s.hist[(unsigned)(key >> shift) & 255u], 1u);
     }
-    if (rank == k) s.med = vi;
+    __syncthreads();
+    if (threadIdx.x < 32) {  // warp 0: lane l owns bins [8l, 8l+8)
+      const int lane = threadIdx.x;
+      unsigned loc[8], sum = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { loc[j] = s.hist[8 * lane + j]; sum += loc[j]; }
+      unsigned inc = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+      }
+      const unsigned exc = inc - sum;
+      const unsigned hit = __ballot_sync(0xffffffffu, inc > (unsigned)kk);
+      if (hit == 0) {
+        if (lane == 0) { s.sel_bin = -1; }
+      } else if (lane == __ffs(hit) - 1) {
+        unsigned cum = exc;
+        int bin = 8 * lane;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          if (cum + loc[j] > (unsigned)kk) { bin = 8 * lane + j; break; }
+          cum += loc[j];
+        }
+        s.sel_bin = bin;
+        s.sel_k = kk - (int)cum;
+      }
+    }
+    __syncthreads();
+    if (s.sel_bin < 0) {  // fewer than k+1 valid entries
+      if (threadIdx.x == 0) s.med = __longlong_as_double(0x7ff8000000000000LL);
+      __syncthreads();
+      return;
+    }
+    prefix |= (unsigned long long)s.sel_bin << shift;
+    mask |= 0xffULL << shift;
+    kk = s.sel_k;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const unsigned long long u = (prefix >> 63) ? (prefix & 0x7fffffffffffffffULL) : ~prefix;
+    s.med = __longlong_as_double((long long)u);
   }
   __syncthreads();
 }
@@ -209,7 +276,7 @@ __global__ void __launch_bounds__(kPoThreads) pose_opt_kernel(PoseOptParams P) {
         s.T = s.T_old;  // roll-back (:100-107)
         s.done = 1;
       } else {
-        const Pose Tn = pose_mul(se3_exp(dT), s.T);  // exp(dT) * T  (:110)
+        const Pose Tn = pose_mul_fast(se3_exp_fast(dT), s.T);  // exp(dT) * T  (:110)
         s.T_old = s.T;
         s.T = Tn;
         s.chi2 = new_chi2;

@@ -25,6 +25,7 @@
 // Precision follows the reference per quantity: f32 interpolation/residual/chi2, f64 geometry and
 // normal equations.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -33,8 +34,11 @@
 
 namespace svo {
 
+#ifndef SVO_SIA_DEBUG
+#define SVO_SIA_DEBUG 0  // 1: thread 0 accumulates clock64 section timings and a few CTAs print them
+#endif
 constexpr int kPatchArea = 16;
-constexpr int kPartK = 22;  // widest block reduction: 21 unique H entries + 1 count
+constexpr int kPartK = 24;  // widest block reduction: 21 unique H entries + 1 count, padded to 16 + 8
 constexpr int kMaxWarps = 16;  // blockDim <= 512
 
 struct SiaJob {  // one frame pair; array lives in device memory
@@ -63,6 +67,7 @@ struct SiaParams {
   svo_b200_sia_iter* trace;
   int trace_cap;
   int* n_trace;
+  int debug;  // env SVO_B200_SIA_DEBUG=1: thread 0 of a few CTAs prints clock64 section timings
   // EVAL mode (svo_b200_sparse_residuals)
   int eval_level;
   const uint8_t* visible_in;
@@ -90,11 +95,16 @@ struct SiaShared {
   int stop, done, slow, n_in_last, h_is_tot;
   int n_iters, sum_vis, sum_in, n_trace;
   unsigned mbar_phase;
+  int cnt[kMaxWarps][2];
+  double keep_chi2;
+  int keep_n_in;
+  long long tkx[2];
+  long long tk[8];  // debug: cycles in [pre-parallel, pre-serial, pass, pass-reduce, serial, total]
 };
 
 // ---------------------------------------------------------------------------------------------
-// Unaligned byte-row fetch: `n` <= 8 consecutive bytes starting at byte offset `off` from a
-// 4-byte aligned base, as two (or three) aligned 32-bit loads + funnel shifts.
+// Unaligned byte-row fetch: consecutive bytes starting at byte offset `off` from a 4-byte aligned
+// base, as two (or three) aligned 32-bit loads + funnel shifts.
 // ---------------------------------------------------------------------------------------------
 template <bool SMEM>
 __device__ __forceinline__ uint32_t ld_word(const uint8_t* base, int word_off) {
@@ -107,7 +117,7 @@ __device__ __forceinline__ void fetch8(const uint8_t* base, int off, uint32_t& l
   const unsigned sh = (unsigned)(off & 3) * 8u;
   const uint32_t w0 = ld_word<SMEM>(base, a), w1 = ld_word<SMEM>(base, a + 4);
   lo = __funnelshift_r(w0, w1, sh);
-  hi = w1 >> sh;  // valid bytes: 4 - (off&3); callers needing more use fetch12
+  hi = w1 >> sh;  // byte 4 of the row in its low byte
 }
 template <bool SMEM>
 __device__ __forceinline__ void fetch12(const uint8_t* base, int off, uint32_t& lo, uint32_t& hi) {
@@ -118,7 +128,6 @@ __device__ __forceinline__ void fetch12(const uint8_t* base, int off, uint32_t& 
   lo = __funnelshift_r(w0, w1, sh);
   hi = __funnelshift_r(w1, w2, sh);
 }
-__device__ __forceinline__ float byte_f(uint32_t w, int k) { return (float)((w >> (8 * k)) & 0xffu); }
 
 // per-feature unscaled Jacobian rows: a = row0 of jacobian_xyz2uv, b = row1 (frame.h:116-138)
 __device__ __forceinline__ void jac_rows(double x, double y, double zi, double (&a)[6], double (&b)[6]) {
@@ -136,26 +145,54 @@ __device__ __forceinline__ void add_h(double x, double y, double zi, double sxx,
   for (int r = 0; r < 6; ++r)
 #pragma unroll
     for (int c = r; c < 6; ++c, ++idx)
-      h[idx] += sxx * (a[r] * a[c]) + sxy * (a[r] * b[c] + b[r] * a[c]) + syy * (b[r] * b[c]);
+      h[idx] = fma(sxx, a[r] * a[c], fma(sxy, fma(a[r], b[c], b[r] * a[c]), fma(syy, b[r] * b[c], h[idx])));
 }
 
-// Sum `K` doubles over the block: on return thread 0..K-1 of warp 0 ... the totals are in s.sums
-// (valid for warp 0 after its __syncwarp).  Contains ONE __syncthreads.
-template <int K>
-__device__ __forceinline__ void block_sum_to_warp0(double (&v)[K], SiaShared& s, int nwarps) {
-  warp_sum<K>(v);
+// Block sum of 24 doubles (21 H entries + counts), once per level: transposed warp reductions of
+// 16 + 8 values, one shared-memory hop, warp 0 adds the per-warp partials.  ONE __syncthreads.
+__device__ __forceinline__ void block_sum24_to_warp0(double (&v)[kPartK], SiaShared& s, int nwarps) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (lane == 0) {
+  double a16[16], a8[8];
 #pragma unroll
-    for (int k = 0; k < K; ++k) s.part[warp * kPartK + k] = v[k];
-  }
+  for (int k = 0; k < 16; ++k) a16[k] = v[k];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a8[k] = v[16 + k];
+  warp_reduce_t<16>(a16);
+  warp_reduce_t<8>(a8);
+  if ((lane & 1) == 0) s.part[warp * kPartK + (lane >> 1)] = a16[0];
+  if ((lane & 3) == 0) s.part[warp * kPartK + 16 + (lane >> 2)] = a8[0];
   __syncthreads();
   if (warp == 0) {
-    if (lane < K) {
+    if (lane < kPartK) {
       double acc = 0.0;
       for (int wv = 0; wv < nwarps; ++wv) acc += s.part[wv * kPartK + lane];
       s.sums[lane] = acc;
     }
+    __syncwarp();
+  }
+}
+
+// Block sum of the 7 per-iteration doubles (6 Jres + chi2; slot 7 unused) and the two patch counts.
+// ONE __syncthreads; on return (warp 0 only) s.sums[0..6] hold the totals, the counts are returned.
+__device__ __forceinline__ void block_sum8_to_warp0(double (&v)[8], int n_in, int n_out, SiaShared& s, int nwarps,
+                                                    int& tot_in, int& tot_out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  warp_reduce_t<8>(v);
+  const int w_in = __reduce_add_sync(0xffffffffu, n_in), w_out = __reduce_add_sync(0xffffffffu, n_out);
+  if ((lane & 3) == 0) s.part[warp * kPartK + (lane >> 2)] = v[0];
+  if (lane == 0) { s.cnt[warp][0] = w_in; s.cnt[warp][1] = w_out; }
+  __syncthreads();
+  tot_in = tot_out = 0;
+  if (warp == 0) {
+    const int k = lane & 7;
+    double acc = 0.0;
+    for (int wv = lane >> 3; wv < nwarps; wv += 4) acc += s.part[wv * kPartK + k];
+    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+    if (lane < 8) s.sums[lane] = acc;
+    const int ci = lane < nwarps ? s.cnt[lane][0] : 0, co = lane < nwarps ? s.cnt[lane][1] : 0;
+    tot_in = __reduce_add_sync(0xffffffffu, ci);
+    tot_out = __reduce_add_sync(0xffffffffu, co);
     __syncwarp();
   }
 }
@@ -169,7 +206,7 @@ __device__ inline void publish_model(SiaShared& s) {
 // when H_ is exactly zero), run the tail of one NLLSSolver::optimizeGaussNewton iteration [EXT]:
 // solve, accept/rollback, update.  Everything is pulled into registers first (independent loads),
 // the dependent chain is FMAs only.
-__device__ __forceinline__ void gn_finish(SiaShared& s, const SiaParams& P, const Solver6* S, int level,
+static __device__ __noinline__ void gn_finish(SiaShared& s, const SiaParams& P, const Solver6* S, int level,
                                           int iter, double chi2sum, int n_in) {
   const int n_meas = n_in * kPatchArea;
   const float chi2f = (float)chi2sum;
@@ -206,9 +243,7 @@ __device__ __forceinline__ void gn_finish(SiaShared& s, const SiaParams& P, cons
     s.old_model = model;
     s.chi2_prev = new_chi2;
     accepted = 1;
-    double m = 0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) m = fmax(m, fabs(x[k]));
+    const double m = fmax(fmax(fmax(fabs(x[0]), fabs(x[1])), fmax(fabs(x[2]), fabs(x[3]))), fmax(fabs(x[4]), fabs(x[5])));
     if (m <= P.eps) done = 1;
   }
   s.model = out;
@@ -234,44 +269,39 @@ template <int FPT, bool EVAL, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SiaShared& s = *reinterpret_cast<SiaShared*>(smem_raw);
-  const int S = P.slots;
+  constexpr int S = MAXT * FPT;  // feature slots (== P.slots, checked on the host)
   float* pat_ref = reinterpret_cast<float*>(smem_raw + ((sizeof(SiaShared) + 15) & ~size_t(15)));
-  float* pat_dx = pat_ref + kPatchArea * S;
-  float* pat_dy = pat_dx + kPatchArea * S;
-  uint8_t* stage = reinterpret_cast<uint8_t*>(pat_dy + kPatchArea * S);  // 16-byte aligned
+  float2* pat_dxy = reinterpret_cast<float2*>(pat_ref + kPatchArea * S);
+  uint8_t* stage = reinterpret_cast<uint8_t*>(pat_dxy + kPatchArea * S);  // 16-byte aligned
 
   const SiaJob& job = P.jobs[blockIdx.x];
   const int tid = threadIdx.x, T = blockDim.x, nwarps = (T + 31) >> 5;
   const int N = job.n_feat;
-
   const int np = job.n_pad;
-  const uint32_t blob_bytes = (uint32_t)np * 65u;
-  const bool blob_staged = blob_bytes <= (uint32_t)P.stage_cap;
+  const uint32_t blob_bytes = (uint32_t)np * 65u;  // <= 192*S: the patch arrays are free until the first level
+
   if (tid == 0) {
     mbar_init(&s.mbar, 1);
     fence_mbar_init();
-    // use k of the barrier completes phase parity k&1; the blob copy (if any) is use 0
-    s.mbar_phase = blob_staged ? 0u : 1u;
+    s.mbar_phase = 0;  // use k of the barrier completes phase parity k&1; the blob copy is use 0
     s.model = pose_from_rt12(job.T);
     s.old_model = s.model;
     s.chi2_prev = 1e10;  // NLLSSolver::reset() [EXT]
     s.stop = 0; s.done = 0; s.slow = 0; s.n_in_last = 0; s.h_is_tot = 0;
     s.n_iters = 0; s.sum_vis = 0; s.sum_in = 0; s.n_trace = 0;
+    for (int k = 0; k < 8; ++k) s.tk[k] = 0;
+    s.tkx[0] = s.tkx[1] = 0;
+    s.tk[5] = clock64();
     for (int k = 0; k < 36; ++k) s.Hs[k] = 0.0;
     publish_model(s);
+    // ---- TMA: the packed feature records of this pair, one bulk copy into the (idle) patch arrays
+    fence_proxy_async();
+    mbar_expect_tx(&s.mbar, blob_bytes);
+    tma_bulk_g2s(pat_ref, job.blob, blob_bytes, &s.mbar);
   }
   __syncthreads();
-
-  // ---- stage the packed feature records of this pair with one TMA bulk copy -----------------
-  if (blob_staged) {
-    if (tid == 0) {
-      fence_proxy_async();
-      mbar_expect_tx(&s.mbar, blob_bytes);
-      tma_bulk_g2s(stage, job.blob, blob_bytes, &s.mbar);
-    }
-    mbar_wait(&s.mbar, 0);
-  }
-  const uint8_t* blob = blob_staged ? stage : job.blob;
+  mbar_wait(&s.mbar, 0);
+  const uint8_t* blob = reinterpret_cast<const uint8_t*>(pat_ref);
   const double* b_px = reinterpret_cast<const double*>(blob);
   const double* b_f = b_px + 2 * np;
   const double* b_pos = b_f + 3 * np;
@@ -298,7 +328,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       if (EVAL && P.visible_in[i]) vis_mask |= 1u << k;
     }
   }
-  __syncthreads();  // everyone is done with the staged blob; the stage region may be reused
+  __syncthreads();  // everyone is done with the staged blob; the patch arrays may be written
 
   const int lvl_hi = EVAL ? P.eval_level : P.max_level;
   const int lvl_lo = EVAL ? P.eval_level : P.min_level;
@@ -319,6 +349,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       tma_bulk_g2s(stage, cur_img, img_bytes, &s.mbar);
     }
 
+    long long tq0 = 0;
+    if ((SVO_SIA_DEBUG && P.debug) && tid == 0) tq0 = clock64();
     // ---- precomputeReferencePatches (:84-145), one feature per thread -----------------------
     double hsum[kPartK];
 #pragma unroll
@@ -328,49 +360,52 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       const int slot = tid + k * T;
       const float u_ref = (float)(fpx_[k] * (double)scale);
       const float v_ref = (float)(fpy_[k] * (double)scale);
-      const int ui = (int)floorf(u_ref), vi = (int)floorf(v_ref);
+      const bool rng = u_ref >= 0.f && v_ref >= 0.f && u_ref < 1e6f && v_ref < 1e6f;  // else: outside, floor not needed
+      float ufl = 0.f, vfl = 0.f;
+      const int ui = rng ? floor_pos(u_ref, ufl) : -1, vi = rng ? floor_pos(v_ref, vfl) : -1;
       const bool ok = ((hp_mask >> k) & 1u) && ui - 3 >= 0 && vi - 3 >= 0 && ui + 3 < W && vi + 3 < Hh;
       if (ok) {
         vis_mask |= 1u << k;
         float wtl, wtr, wbl, wbr;
-        bilin_weights(u_ref - (float)ui, v_ref - (float)vi, wtl, wtr, wbl, wbr);
-        // 7x7 footprint rows vi-3..vi+3, cols ui-3..ui+3 -> floats
-        float Pf[7][7];
-#pragma unroll
-        for (int r = 0; r < 7; ++r) {
+        bilin_weights(__fsub_rn(u_ref, ufl), __fsub_rn(v_ref, vfl), wtl, wtr, wbl, wbr);
+        // 7x7 footprint rows vi-3..vi+3, cols ui-3..ui+3, streamed row by row to keep the register
+        // footprint small: Bq row r (bilinear blends with top-left tap P[r][c]) needs footprint rows
+        // r, r+1; patch row y needs Bq rows y, y+1, y+2.
+        float pr0[7], pr1[7], b0[6], b1[6], b2[6];
+        double sxx = 0, sxy = 0, syy = 0;
+        auto load_row = [&](int r, float (&dst)[7]) {
           uint32_t lo, hi;
           fetch12<false>(ref_img, (vi - 3 + r) * W + (ui - 3), lo, hi);
+          dst[0] = byte_to_float<0>(lo); dst[1] = byte_to_float<1>(lo); dst[2] = byte_to_float<2>(lo);
+          dst[3] = byte_to_float<3>(lo); dst[4] = byte_to_float<0>(hi); dst[5] = byte_to_float<1>(hi);
+          dst[6] = byte_to_float<2>(hi);
+        };
+        load_row(0, pr0);
 #pragma unroll
-          for (int c = 0; c < 4; ++c) Pf[r][c] = byte_f(lo, c);
+        for (int r = 0; r < 6; ++r) {
+          load_row(r + 1, pr1);
 #pragma unroll
-          for (int c = 4; c < 7; ++c) Pf[r][c] = byte_f(hi, c - 4);
+          for (int c = 0; c < 6; ++c) b2[c] = bilin(wtl, wtr, wbl, wbr, pr0[c], pr0[c + 1], pr1[c], pr1[c + 1]);
+          if (r >= 2) {  // rows b0 (= Bq[y]), b1 (= Bq[y+1]), b2 (= Bq[y+2]) with y = r-2 are complete
+            const int y = r - 2;
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              const int p = y * 4 + x;
+              const float val = b1[x + 1];
+              const float dx = __fmul_rn(0.5f, __fsub_rn(b1[x + 2], b1[x]));
+              const float dy = __fmul_rn(0.5f, __fsub_rn(b2[x + 1], b0[x + 1]));
+              pat_ref[p * S + slot] = val;
+              pat_dxy[p * S + slot] = make_float2(dx, dy);
+              sxx = fma((double)dx, (double)dx, sxx);
+              sxy = fma((double)dx, (double)dy, sxy);
+              syy = fma((double)dy, (double)dy, syy);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 6; ++c) { b0[c] = b1[c]; b1[c] = b2[c]; }
+#pragma unroll
+          for (int c = 0; c < 7; ++c) pr0[c] = pr1[c];
         }
-        // Bq[r][c] = bilinear blend with top-left tap P[r][c]; only the 32 needed ones are formed
-        float Bq[6][6];
-#pragma unroll
-        for (int r = 0; r < 6; ++r)
-#pragma unroll
-          for (int c = 0; c < 6; ++c) {
-            const bool corner = (r == 0 || r == 5) && (c == 0 || c == 5);
-            Bq[r][c] = corner ? 0.f
-                              : bilin(wtl, wtr, wbl, wbr, Pf[r][c], Pf[r][c + 1], Pf[r + 1][c], Pf[r + 1][c + 1]);
-          }
-        double sxx = 0, sxy = 0, syy = 0;
-#pragma unroll
-        for (int y = 0; y < 4; ++y)
-#pragma unroll
-          for (int x = 0; x < 4; ++x) {
-            const int p = y * 4 + x;
-            const float val = Bq[y + 1][x + 1];
-            const float dx = __fmul_rn(0.5f, __fsub_rn(Bq[y + 1][x + 2], Bq[y + 1][x]));
-            const float dy = __fmul_rn(0.5f, __fsub_rn(Bq[y + 2][x + 1], Bq[y][x + 1]));
-            pat_ref[p * S + slot] = val;
-            pat_dx[p * S + slot] = dx;
-            pat_dy[p * S + slot] = dy;
-            sxx = fma((double)dx, (double)dx, sxx);
-            sxy = fma((double)dx, (double)dy, sxy);
-            syy = fma((double)dy, (double)dy, syy);
-          }
         add_h(fx_[k], fy_[k], fzi_[k], sxx, sxy, syy, hsum);
         hsum[21] += 1.0;
       } else if ((vis_mask >> k) & 1u) {
@@ -378,12 +413,14 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         // and a zeroed Jacobian (jacobian_cache_.setZero() per level, :64).  Unreachable for
         // dyadic pyramids but kept bit-faithful.
 #pragma unroll
-        for (int p = 0; p < kPatchArea; ++p) { pat_dx[p * S + slot] = 0.f; pat_dy[p * S + slot] = 0.f; }
+        for (int p = 0; p < kPatchArea; ++p) pat_dxy[p * S + slot] = make_float2(0.f, 0.f);
         hsum[21] += 1.0;
       }
     }
-    block_sum_to_warp0<kPartK>(hsum, s, nwarps);
+    block_sum24_to_warp0(hsum, s, nwarps);
     if (tid == 0) {
+      long long tq1 = 0;
+      if (SVO_SIA_DEBUG && P.debug) { tq1 = clock64(); s.tk[0] += tq1 - tq0; }
       const double s2 = jscale * jscale;
       int idx = 0;
       for (int r = 0; r < 6; ++r)
@@ -395,6 +432,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       solver_factor(s.sol_tot, s.Htot);
       s.sum_vis += (int)s.sums[21];
       s.done = 0;
+      if (SVO_SIA_DEBUG && P.debug) s.tk[1] += clock64() - tq1;
     }
     if (staged) mbar_wait(&s.mbar, s.mbar_phase);
     __syncthreads();
@@ -402,33 +440,35 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
     // ---- Gauss-Newton iterations at this level ---------------------------------------------
     const int n_iter = EVAL ? 1 : P.n_iter;
     for (int iter = 0; iter < n_iter; ++iter) {
-      double R[9], tt[3];
+      long long ti0 = 0;
+      if ((SVO_SIA_DEBUG && P.debug) && tid == 0) ti0 = clock64();
+      double acc[8];
 #pragma unroll
-      for (int k = 0; k < 9; ++k) R[k] = s.R[k];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) tt[k] = s.t[k];
-
-      double acc[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) acc[k] = 0.0;
+      for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+      int n_in_t = 0, n_out_t = 0;
       in_mask = 0;
 #pragma unroll
       for (int k = 0; k < FPT; ++k) {
         if (!((vis_mask >> k) & 1u)) continue;
         const int slot = tid + k * T;
+        long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0;
+        if ((SVO_SIA_DEBUG && P.debug) && tid == 0) tp0 = clock64();
         const double x = fx_[k], y = fy_[k], z = fz_[k];
-        const double xc = fma(R[0], x, fma(R[1], y, fma(R[2], z, tt[0])));
-        const double yc = fma(R[3], x, fma(R[4], y, fma(R[5], z, tt[1])));
-        const double zc = fma(R[6], x, fma(R[7], y, fma(R[8], z, tt[2])));
-        const double ud = fma(P.fx, xc / zc, P.cx);  // [EXT] world2cam: fx * (x/z) + cx
-        const double vd = fma(P.fy, yc / zc, P.cy);
+        const double xc = fma(s.R[0], x, fma(s.R[1], y, fma(s.R[2], z, s.t[0])));
+        const double yc = fma(s.R[3], x, fma(s.R[4], y, fma(s.R[5], z, s.t[1])));
+        const double zc = fma(s.R[6], x, fma(s.R[7], y, fma(s.R[8], z, s.t[2])));
+        const double rz = fast_rcp(zc);
+        const double ud = fma(P.fx, xc * rz, P.cx);  // [EXT] world2cam: fx * (x/z) + cx
+        const double vd = fma(P.fy, yc * rz, P.cy);
         const float u_cur = __fmul_rn((float)ud, scale);  // .cast<float>() * scale (:183)
         const float v_cur = __fmul_rn((float)vd, scale);
-        const bool finite = fabsf(u_cur) < 1e8f && fabsf(v_cur) < 1e8f;
-        const int ui = finite ? (int)floorf(u_cur) : -1, vi = finite ? (int)floorf(v_cur) : -1;
+        // negative / non-finite / huge coordinates can never pass the border test (:190)
+        const bool rng = u_cur >= 0.f && v_cur >= 0.f && u_cur < 1e6f && v_cur < 1e6f;
+        float ufl = 0.f, vfl = 0.f;
+        const int ui = rng ? floor_pos(u_cur, ufl) : -1, vi = rng ? floor_pos(v_cur, vfl) : -1;
         const bool in = ui >= 0 && vi >= 0 && ui - 3 >= 0 && vi - 3 >= 0 && ui + 3 < W && vi + 3 < Hh;  // :190
         if (!in) {
-          acc[8] += 1.0;
+          ++n_out_t;
           if (EVAL) {
             for (int p = 0; p < kPatchArea; ++p)
               P.residuals_out[(size_t)slot * kPatchArea + p] = __int_as_float(0x7fc00000);
@@ -436,32 +476,41 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           continue;
         }
         in_mask |= 1u << k;
+        ++n_in_t;
+        if ((SVO_SIA_DEBUG && P.debug) && tid == 0) tp1 = clock64();
         float wtl, wtr, wbl, wbr;
-        bilin_weights(u_cur - (float)ui, v_cur - (float)vi, wtl, wtr, wbl, wbr);
-        float Q[5][5];
+        bilin_weights(__fsub_rn(u_cur, ufl), __fsub_rn(v_cur, vfl), wtl, wtr, wbl, wbr);
+        uint32_t lo[5], hi[5];
 #pragma unroll
         for (int r = 0; r < 5; ++r) {
-          uint32_t lo, hi;
           const int off = (vi - 2 + r) * W + (ui - 2);
-          if (staged) fetch8<true>(stage, off, lo, hi);
-          else fetch8<false>(cur_img, off, lo, hi);
-#pragma unroll
-          for (int c = 0; c < 4; ++c) Q[r][c] = byte_f(lo, c);
-          Q[r][4] = byte_f(hi, 0);
+          if (staged) fetch8<true>(stage, off, lo[r], hi[r]);
+          else fetch8<false>(cur_img, off, lo[r], hi[r]);
         }
         float c2 = 0.f, gx = 0.f, gy = 0.f;
+        float q0[5], q1[5];
+        if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { tp2 = clock64() + (long long)(lo[4] & 0u); }
+        q0[0] = byte_to_float<0>(lo[0]); q0[1] = byte_to_float<1>(lo[0]); q0[2] = byte_to_float<2>(lo[0]);
+        q0[3] = byte_to_float<3>(lo[0]); q0[4] = byte_to_float<0>(hi[0]);
 #pragma unroll
-        for (int yy = 0; yy < 4; ++yy)
+        for (int yy = 0; yy < 4; ++yy) {
+          q1[0] = byte_to_float<0>(lo[yy + 1]); q1[1] = byte_to_float<1>(lo[yy + 1]); q1[2] = byte_to_float<2>(lo[yy + 1]);
+          q1[3] = byte_to_float<3>(lo[yy + 1]); q1[4] = byte_to_float<0>(hi[yy + 1]);
 #pragma unroll
           for (int xx = 0; xx < 4; ++xx) {
             const int p = yy * 4 + xx;
-            const float I = bilin(wtl, wtr, wbl, wbr, Q[yy][xx], Q[yy][xx + 1], Q[yy + 1][xx], Q[yy + 1][xx + 1]);
+            const float I = bilin(wtl, wtr, wbl, wbr, q0[xx], q0[xx + 1], q1[xx], q1[xx + 1]);
             const float res = __fsub_rn(I, pat_ref[p * S + slot]);
-            c2 = __fadd_rn(c2, __fmul_rn(res, res));  // chi2 += res*res*weight, weight == 1 (:222)
-            gx = fmaf(pat_dx[p * S + slot], res, gx);
-            gy = fmaf(pat_dy[p * S + slot], res, gy);
+            const float2 g = pat_dxy[p * S + slot];
+            c2 = fmaf(res, res, c2);  // chi2 += res*res*weight, weight == 1 (:222); order differs from the serial sum anyway
+            gx = fmaf(g.x, res, gx);
+            gy = fmaf(g.y, res, gy);
             if (EVAL) P.residuals_out[(size_t)slot * kPatchArea + p] = res;
           }
+#pragma unroll
+          for (int c = 0; c < 5; ++c) q0[c] = q1[c];
+        }
+        if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { tp3 = clock64() + (long long)(__float_as_int(gx) & 0); s.tk[6] += tp1 - tp0; s.tk[7] += tp2 - tp1; s.tk[0] += 0; }
         const double zi = fzi_[k], X = x * zi, Y = y * zi, dgx = (double)gx, dgy = (double)gy;
         acc[0] = fma(-zi, dgx, acc[0]);
         acc[1] = fma(-zi, dgy, acc[1]);
@@ -470,13 +519,18 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         acc[4] = fma(-fma(X, X, 1.0), dgx, fma(-(X * Y), dgy, acc[4]));
         acc[5] = fma(Y, dgx, fma(-X, dgy, acc[5]));
         acc[6] += (double)c2;
-        acc[7] += 1.0;
+        if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { s.tkx[0] += tp3 - tp2; s.tkx[1] += clock64() - tp3 + (long long)(acc[5] != acc[5]); }
       }
-      block_sum_to_warp0<9>(acc, s, nwarps);  // contains the first __syncthreads of the iteration
+      int n_in, n_out;
+      long long ti1 = 0;
+      if ((SVO_SIA_DEBUG && P.debug) && tid == 0) ti1 = clock64();
+      block_sum8_to_warp0(acc, n_in_t, n_out_t, s, nwarps, n_in, n_out);  // first __syncthreads of the iteration
       if (tid == 0) {
-        const int n_in = (int)s.sums[7], n_out = (int)s.sums[8];
+        long long ti2 = 0;
+        if (SVO_SIA_DEBUG && P.debug) { ti2 = clock64(); s.tk[2] += ti1 - ti0; s.tk[3] += ti2 - ti1; }
         for (int k = 0; k < 6; ++k) s.x[k] = -(s.sums[k] * jscale);  // Jres_ = -sum J r
-        s.sums[9] = s.sums[6];                                       // chi2 parked across the slow path
+        s.keep_chi2 = s.sums[6];
+        s.keep_n_in = n_in;
         s.slow = (EVAL || (n_out > 0 && n_in > 0)) ? 1 : 0;
         if (!s.slow) {
           if (n_in == 0) {  // H_ == 0 exactly: Eigen's LDLT yields x = 0
@@ -488,6 +542,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
             gn_finish(s, P, &s.sol_tot, level, iter, s.sums[6], n_in);
           }
         }
+        if (SVO_SIA_DEBUG && P.debug) s.tk[4] += clock64() - ti2;
       }
       __syncthreads();
       if (s.slow) {
@@ -503,17 +558,15 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           double sxx = 0, sxy = 0, syy = 0;
 #pragma unroll
           for (int p = 0; p < kPatchArea; ++p) {
-            const double dx = (double)pat_dx[p * S + slot], dy = (double)pat_dy[p * S + slot];
+            const float2 g = pat_dxy[p * S + slot];
+            const double dx = (double)g.x, dy = (double)g.y;
             sxx = fma(dx, dx, sxx);
             sxy = fma(dx, dy, sxy);
             syy = fma(dy, dy, syy);
           }
           add_h(fx_[k], fy_[k], fzi_[k], sxx, sxy, syy, hs2);
         }
-        const double chi2_keep = s.sums[9];
-        const int n_in_keep = (int)s.sums[7];
-        __syncthreads();
-        block_sum_to_warp0<kPartK>(hs2, s, nwarps);
+        block_sum24_to_warp0(hs2, s, nwarps);
         if (tid == 0) {
           const double s2 = jscale * jscale;
           int idx = 0;
@@ -524,6 +577,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
               s.Hs[r * 6 + c] = v;
               s.Hs[c * 6 + r] = v;
             }
+          const double chi2_keep = s.keep_chi2;
+          const int n_in_keep = s.keep_n_in;
           if (EVAL) {
             for (int k = 0; k < 6; ++k) P.Jres_out[k] = s.x[k];
             const float chi2f = (float)chi2_keep;
@@ -574,6 +629,9 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       P.stats[blockIdx.x] = st;
     }
     if (P.n_trace) *P.n_trace = s.n_trace;
+    if (SVO_SIA_DEBUG && P.debug && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2 || blockIdx.x == gridDim.x - 1))
+      printf("[sia dbg] cta %d iters %d cycles: pre_par %lld pre_ser %lld pass %lld reduce %lld serial %lld total %lld | t0: geom %lld wts+ld %lld pix %lld acc %lld\n", blockIdx.x,
+             s.n_iters, s.tk[0], s.tk[1], s.tk[2], s.tk[3], s.tk[4], (long long)clock64() - s.tk[5], s.tk[6], s.tk[7], s.tkx[0], s.tkx[1]);
   }
 }
 
@@ -598,19 +656,30 @@ void sia_batch_free(svo_b200_ctx* ctx) {
   ctx->sia = nullptr;
 }
 
+static int g_sia_minb = 2;      // tuning knobs (env SVO_B200_SIA_MINB / SVO_B200_SIA_STAGE_KB), read once
+static int g_sia_stage_kb = 20;
+
 static int pick_launch(svo_b200_ctx* ctx, int max_feat, int& threads, int& fpt, int& stage_cap, size_t& smem) {
   if (max_feat <= 512) fpt = 1;
   else if (max_feat <= 1024) fpt = 2;
   else if (max_feat <= 2048) fpt = 4;
   else return set_err(ctx, SVO_B200_ELIMIT, "sparse_img_align: %d features per pair > 2048", max_feat);
   threads = ((max_feat + fpt - 1) / fpt + 31) / 32 * 32;
-  if (threads < 32) threads = 32;
+  // the kernels are instantiated for MAXT in {320, 384, 512}; launching exactly MAXT threads makes the
+  // slot count S = MAXT*FPT a compile-time constant (immediate shared-memory offsets)
+  threads = fpt == 1 ? (threads <= 320 ? 320 : threads <= 384 ? 384 : 512) : 512;
   const size_t base = ((sizeof(SiaShared) + 15) & ~size_t(15)) + (size_t)3 * kPatchArea * threads * fpt * sizeof(float);
   const size_t budget = (size_t)ctx->max_smem_optin;
   if (base + 1024 > budget)
     return set_err(ctx, SVO_B200_ELIMIT, "sparse_img_align: %d features need %zu B of shared memory", max_feat, base);
-  // staging region: feature blob (65 B / feature) and coarse level images; default 20 KB
-  size_t cap = 20480;
+  static bool env_read = false;
+  if (!env_read) {
+    env_read = true;
+    if (const char* e = getenv("SVO_B200_SIA_MINB")) g_sia_minb = atoi(e) == 3 ? 3 : 2;
+    if (const char* e = getenv("SVO_B200_SIA_STAGE_KB")) g_sia_stage_kb = atoi(e) > 0 ? atoi(e) : 20;
+  }
+  // staging region for the coarse current-level images (TMA); default 20 KB holds level >= 2 of 640x480
+  size_t cap = (size_t)g_sia_stage_kb * 1024;
   if (base + cap > budget) cap = (budget - base) & ~size_t(15);
   stage_cap = (int)cap;
   smem = base + cap;
@@ -631,6 +700,7 @@ static int launch_sia(svo_b200_ctx* ctx, const SiaParams& P, int B, int threads,
   };
   // <= 384 threads: cap registers so that two CTAs are resident per SM
   if (fpt == 1) {
+    if (threads <= 320 && g_sia_minb == 3) return go(sia_kernel<1, EVAL, 320, 3>);
     if (threads <= 320) return go(sia_kernel<1, EVAL, 320, 2>);
     if (threads <= 384) return go(sia_kernel<1, EVAL, 384, 2>);
     return go(sia_kernel<1, EVAL, 512, 1>);
@@ -661,6 +731,7 @@ static int fill_common(svo_b200_ctx* ctx, SiaParams& P, const svo_b200_frame* fr
   for (int l = 0; l < fr->n_levels; ++l) { P.w[l] = fr->w[l]; P.h[l] = fr->h[l]; }
   P.fx = cam->fx; P.fy = cam->fy; P.cx = cam->cx; P.cy = cam->cy;
   P.max_level = opt->max_level; P.min_level = opt->min_level; P.n_iter = opt->n_iter; P.eps = opt->eps;
+  P.debug = getenv("SVO_B200_SIA_DEBUG") ? 1 : 0;
   return 0;
 }
 

@@ -339,7 +339,7 @@ struct Solver6 {
   int tr[8];
   int pivoted;
 };
-__device__ inline void solver_factor(Solver6& S, const double* H) {
+static __device__ __noinline__ void solver_factor(Solver6& S, const double* H) {
   Fact6 F;
   if (fact6_compute(H, F)) {
     S.F = F;
@@ -364,6 +364,43 @@ __device__ __forceinline__ void warp_sum(double (&v)[K]) {
   }
 }
 
+
+// Transposed ("reduce-scatter") warp sum of K = 8 or 16 doubles: each butterfly step halves the number
+// of values a lane carries, so the whole reduction costs K-1+... f64 exchanges instead of 5*K.
+// On return v[0] of lane (32/K)*e holds the warp total of element e.
+template <int K>
+__device__ __forceinline__ void warp_reduce_t(double (&v)[K]) {
+  const unsigned lane = threadIdx.x & 31u;
+  int bit = 16;
+#pragma unroll
+  for (int n = K; n > 1; n >>= 1, bit >>= 1) {
+    const bool hi = (lane & (unsigned)bit) != 0;
+#pragma unroll
+    for (int i = 0; i < n / 2; ++i) {
+      const double keep = hi ? v[n / 2 + i] : v[i];
+      const double send = hi ? v[i] : v[n / 2 + i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+#pragma unroll
+  for (; bit > 0; bit >>= 1) v[0] += __shfl_xor_sync(0xffffffffu, v[0], bit);
+}
+
+// 1/z to ~1 ulp without the IEEE-division slow path: f32 reciprocal seed + two f64 Newton steps.
+__device__ __forceinline__ double fast_rcp(double z) {
+  double r = (double)__frcp_rn((float)z);
+  double e = fma(-z, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-z, r, 1.0);
+  return fma(r, e, r);
+}
+
+// byte k of w -> float, exactly: PRMT builds the float 2^23 + byte, one FADD removes the 2^23.
+template <int KB>
+__device__ __forceinline__ float byte_to_float(uint32_t w) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | (unsigned)KB)) - 8388608.0f;
+}
+
 // Canonical bilinear blend shared with the oracle (oracle/svo_oracle.cpp `bilin`):
 // fma(wbr,d, fma(wbl,c, fma(wtl,a, wtr*b))).
 __device__ __forceinline__ float bilin(float wtl, float wtr, float wbl, float wbr, float a, float b,
@@ -372,14 +409,30 @@ __device__ __forceinline__ float bilin(float wtl, float wtr, float wbl, float wb
 }
 
 // Bilinear weights exactly as the reference forms them: (1.0 - su) promotes to double, the
-// product is rounded once to float (svo/src/sparse_img_align.cpp:115-120,194-199).
+// product is rounded once to float (svo/src/sparse_img_align.cpp:115-120,194-199).  Pure-f32
+// evaluation is bit-identical whenever the coordinate is >= 2 (always true inside the +-3 / +-4 pixel
+// borders every caller enforces): su = u - floor(u) is then a multiple of 2^-22, so 1 - su is exact
+// in f32, and the product of two exact f32 operands rounded once to f32 equals the double product
+// rounded to f32.  This keeps the conversion (XU) pipe out of the inner loops.
 __device__ __forceinline__ void bilin_weights(float su, float sv, float& wtl, float& wtr, float& wbl,
                                               float& wbr) {
-  const double omu = 1.0 - (double)su, omv = 1.0 - (double)sv;
-  wtl = (float)(omu * omv);
-  wtr = (float)((double)su * omv);
-  wbl = (float)(omu * (double)sv);
+  const float omu = __fsub_rn(1.0f, su), omv = __fsub_rn(1.0f, sv);
+  wtl = __fmul_rn(omu, omv);
+  wtr = __fmul_rn(su, omv);
+  wbl = __fmul_rn(omu, sv);
   wbr = __fmul_rn(su, sv);
+}
+
+// floor() of a float known to lie in [0, 2^22) without the conversion pipe: adding 2^23 rounds to the
+// nearest integer (result integer in the low mantissa bits), one compare fixes round-up cases.
+// Returns the integer; `fl` receives floor(u) as a float.
+__device__ __forceinline__ int floor_pos(float u, float& fl) {
+  const float t = __fadd_rn(u, 8388608.0f);
+  float r = __fsub_rn(t, 8388608.0f);
+  int i = __float_as_int(t) - 0x4B000000;
+  if (r > u) { r = __fsub_rn(r, 1.0f); i -= 1; }
+  fl = r;
+  return i;
 }
 
 // ------------------------------------------------------------------------------------------
