@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--pairs-per-gpu", type=int, default=592)
     ap.add_argument("--cpu-sample", type=int, default=256, help="pairs timed by the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks of the window in the e2e leg (copy/compute overlap)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the C2/C3 side measurements")
     return ap.parse_args()
@@ -262,6 +263,7 @@ def main():
     import torch.distributed as dist
 
     from rpg_svo_b200 import capi
+    from rpg_svo_b200.shard import shard_range
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the CUDA path is the only path (no CPU fallback)")
@@ -346,24 +348,56 @@ def main():
     # ---------------- leg 2: end to end through the C ABI with host buffers ----------------
     e2e = None
     if not args.no_e2e:
-        def e2e_step():
-            upload_all()
-            stage()
-            ctx.sia_batch_run()
-            return ctx.sia_batch_fetch()
+        # The window is cut into chunks that alternate between two contexts (= two CUDA streams): while
+        # one stream runs the alignment kernel of chunk c, the other copies the images of chunk c+1 over
+        # PCIe.  Each chunk owns a private frame pool (pairs k..k+n-1 need frames k..k+n), so nothing
+        # is shared between the streams; the boundary frame of a chunk is simply uploaded twice.
+        n_chunks = max(1, min(args.e2e_chunks, B))
+        ctx2 = capi.Context(local_rank)
+        ctxs = [ctx, ctx2]
+        bounds = [shard_range(B, c, n_chunks) for c in range(n_chunks)]
+        pools = [capi.FramePool(ctxs[c % 2], W, H, NLEVELS, e - b + 1) for c, (b, e) in enumerate(bounds)]
+        base = host_l0.data_ptr()
 
+        def e2e_step():
+            for c, (b, e) in enumerate(bounds):
+                cx, pl, n = ctxs[c % 2], pools[c], e - b
+                fo = inp["off"][b:e + 1] - inp["off"][b]  # offsets index the (sliced) arrays passed below
+                sl = slice(b * NFEAT, e * NFEAT)
+                if c >= 2:  # the context's staging buffers are about to be reused: drain its previous chunk
+                    results[c - 2] = cx.sia_batch_fetch()
+                # features first (host packing + small H2D), then the images: the packing of the NEXT chunk
+                # (other context) overlaps this chunk's image copy; the kernel is ordered after both
+                cx.sia_batch_stage(pl.frames[:n], pl.frames[1:n + 1], inp["cam"], inp["T0"][b:e], fo, inp["px"][sl],
+                                   inp["f"][sl], inp["pos"][sl], inp["hp"][sl], inp["ref_pos"][b:e], MAX_LEVEL,
+                                   MIN_LEVEL, NITER)
+                pl.upload(0, n + 1, base + b * frame_bytes, frame_bytes)
+                cx.sia_batch_run()
+            for c in range(max(0, n_chunks - 2), n_chunks):
+                results[c] = ctxs[c % 2].sia_batch_fetch()
+            return results
+
+        results = [None] * n_chunks
         for _ in range(max(Wm, 3)):
             e2e_step()
+        # the chunked path must give the same poses as the one-launch path
+        T_chunks = np.concatenate([r["T"] for r in results])
+        assert np.array_equal(T_chunks, res["T"]), "chunked e2e path disagrees with the device-resident run"
         barrier()
+        ctx2.synchronize()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record(stream)
         for _ in range(K):
-            out = e2e_step()
+            out = e2e_step()  # every fetch synchronises its stream, so all work of the step is complete here
         s1.record(stream)
         barrier()
+        ctx2.synchronize()
         ms_e2e = max_over_ranks(s0.elapsed_time(s1))
+        for pl in pools:
+            pl.destroy()
+        ctx2.close()
         # level-0 images + per-pair job descriptor (272 B) + packed feature blob (65 B x padded N)
-        h2d = (B + 1) * frame_bytes + B * (272 + ((NFEAT + 15) // 16 * 16) * 65)
+        h2d = (B + n_chunks) * frame_bytes + B * (272 + ((NFEAT + 15) // 16 * 16) * 65)
         d2h = B * (96 + 288 + 16) + B * NFEAT
         e2e = {"value": world * B * K / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / K}

@@ -8,6 +8,7 @@
  *   svo_b200_align2d_batch/_1d      <- feature_alignment::align2D / align1D   svo/include/svo/feature_alignment.h:29-44
  *   svo_b200_find_match_direct      <- Matcher::findMatchDirect               svo/include/svo/matcher.h:109-112
  *   svo_b200_pose_optimize          <- pose_optimizer::optimizeGaussNewton    svo/include/svo/pose_optimizer.h:37-45
+ *   svo_b200_point_optimize_batch   <- Point::optimize                        svo/include/svo/point.h:86, svo/src/point.cpp:119-177
  *   svo_b200_depth_filter_update    <- DepthFilter::updateSeeds               svo/include/svo/depth_filter.h:155
  *                                      (Matcher::findEpipolarMatchDirect, updateSeed, computeTau inside)
  *   svo_b200_frame_*                <- svo::Frame image pyramid               svo/include/svo/frame.h:52, svo/src/frame.cpp:156-165
@@ -190,6 +191,14 @@ int svo_b200_pose_optimize(svo_b200_ctx* ctx, double reproj_thresh, int n_iter,
                            double fx /*cam->errorMultiplier2()*/, double* T_f_w_io, const double* f,
                            const double* point_pos, const int* level, uint8_t* has_point_io, int N,
                            svo_b200_pose_opt_result* out);
+
+/* Point::optimize (svo/src/point.cpp:119-177) for P independent points ("next" row f3: structure
+ * refinement after the pose optimizer, frame_handler_base.cpp:178-196).  Point p owns observations
+ * [obs_offset[p], obs_offset[p+1]); observation o is seen from frame obs_frame[o] (pose frame_T_f_w) with
+ * unit bearing obs_f[o].  pos_io: P*3 world positions, updated in place. */
+int svo_b200_point_optimize_batch(svo_b200_ctx* ctx, int P, int n_iter, const int* obs_offset,
+                                  const int* obs_frame, const double* obs_f, const double* frame_T_f_w,
+                                  int n_frames, double* pos_io);
 
 /* ------------------------------------------------------------------ depth filter -------- */
 #define SVO_B200_SEED_TOO_OLD 1

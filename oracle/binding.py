@@ -336,3 +336,11 @@ def pose_optimize(reproj_thresh, n_iter, fx, T_f_w, f, pos, level, has_point):
     return dict(T=T.reshape(3, 4), has_point=hp, estimated_scale=out.estimated_scale,
                 error_init=out.error_init, error_final=out.error_final, num_obs=out.num_obs,
                 n_iter_done=out.n_iter_done, cov=np.array(out.cov[:]).reshape(6, 6))
+
+
+def point_optimize(n_iter, pos, obs_T_f_w, obs_f):
+    p = c64(pos).copy()
+    T = c64(np.asarray(obs_T_f_w)).reshape(-1)
+    f = c64(obs_f)
+    lib().orc_point_optimize(int(n_iter), _p(p), len(f), _p(T), _p(f))
+    return p

@@ -176,6 +176,10 @@ void orc_pose_optimize(double reproj_thresh, int n_iter, double fx /*errorMultip
                        const int* level /*N*/, uint8_t* has_point_io /*N*/, int N,
                        orc_pose_opt_result* out);
 
+/* svo::Point::optimize (svo/src/point.cpp:119-177): one point, n_obs observing frames. */
+void orc_point_optimize(int n_iter, double* pos_io /*3*/, int n_obs, const double* obs_T_f_w /*n_obs*12*/,
+                        const double* obs_f /*n_obs*3*/);
+
 #ifdef __cplusplus
 }
 #endif

@@ -397,3 +397,16 @@ Context.align1d_batch = _align1d_batch
 Context.find_match_direct = _find_match_direct
 Context.pose_optimize = _pose_optimize
 Context.depth_filter_update = _depth_filter_update
+
+
+def _point_optimize_batch(self, n_iter, pos, obs_offset, obs_frame, obs_f, frame_T_f_w):
+    """Point::optimize for P points; returns the refined positions [P,3]."""
+    p = c64(pos).copy().reshape(-1, 3)
+    off, fr = _i32(obs_offset), _i32(obs_frame)
+    f, T = c64(obs_f), c64(np.asarray(frame_T_f_w)).reshape(-1)
+    self._check(self.lib.svo_b200_point_optimize_batch(self.h, len(p), int(n_iter), _p(off), _p(fr), _p(f), _p(T),
+                                                       len(T) // 12, _p(p)))
+    return p
+
+
+Context.point_optimize_batch = _point_optimize_batch

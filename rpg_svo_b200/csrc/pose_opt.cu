@@ -406,3 +406,140 @@ extern "C" int svo_b200_pose_optimize(svo_b200_ctx* ctx, double reproj_thresh, i
   memcpy(out, h + o_out, sizeof(*out));
   return 0;
 }
+
+// ================================================================================================
+// Point::optimize (svo/src/point.cpp:119-177): 3-DoF Gauss-Newton on a point's world position over
+// the frames observing it.  Points are independent: one thread per point, observations streamed from
+// global memory; the 3x3 system is solved with the same pivoted LDL^T as Eigen's (tiny, in registers).
+// ================================================================================================
+namespace svo {
+
+__device__ inline void ldlt3_solve(double (&A)[3][3], const double (&b)[3], double (&x)[3]) {
+  int tr[3];
+  for (int k = 0; k < 3; ++k) {
+    int big = k;
+    double bigv = fabs(A[k][k]);
+    for (int i = k + 1; i < 3; ++i)
+      if (fabs(A[i][i]) > bigv) { bigv = fabs(A[i][i]); big = i; }
+    tr[k] = big;
+    if (big != k) {
+      for (int j = 0; j < k; ++j) { const double s = A[k][j]; A[k][j] = A[big][j]; A[big][j] = s; }
+      for (int i = big + 1; i < 3; ++i) { const double s = A[i][k]; A[i][k] = A[i][big]; A[i][big] = s; }
+      { const double s = A[k][k]; A[k][k] = A[big][big]; A[big][big] = s; }
+      for (int i = k + 1; i < big; ++i) { const double s = A[i][k]; A[i][k] = A[big][i]; A[big][i] = s; }
+    }
+    if (k > 0) {
+      double temp[3], acc = 0;
+      for (int j = 0; j < k; ++j) { temp[j] = A[j][j] * A[k][j]; acc += A[k][j] * temp[j]; }
+      A[k][k] -= acc;
+      for (int i = k + 1; i < 3; ++i) {
+        double a2 = 0;
+        for (int j = 0; j < k; ++j) a2 += A[i][j] * temp[j];
+        A[i][k] -= a2;
+      }
+    }
+    const double akk = A[k][k];
+    const bool ok = fabs(akk) > 0.0;
+    if (k == 0 && !ok) { tr[0] = 0; tr[1] = 1; tr[2] = 2; break; }
+    if (ok)
+      for (int i = k + 1; i < 3; ++i) A[i][k] /= akk;
+  }
+  for (int i = 0; i < 3; ++i) x[i] = b[i];
+  for (int i = 0; i < 3; ++i) { const int j = tr[i]; const double s = x[i]; x[i] = x[j]; x[j] = s; }
+  for (int i = 1; i < 3; ++i)
+    for (int j = 0; j < i; ++j) x[i] -= A[i][j] * x[j];
+  for (int i = 0; i < 3; ++i) x[i] = (fabs(A[i][i]) > 5.562684646268003e-309) ? x[i] / A[i][i] : 0.0;
+  for (int i = 1; i >= 0; --i)
+    for (int j = i + 1; j < 3; ++j) x[i] -= A[j][i] * x[j];
+  for (int i = 2; i >= 0; --i) { const int j = tr[i]; const double s = x[i]; x[i] = x[j]; x[j] = s; }
+}
+
+__global__ void point_optimize_kernel(int P, int n_iter, const int* __restrict__ obs_offset,
+                                      const int* __restrict__ obs_frame, const double* __restrict__ obs_f,
+                                      const double* __restrict__ frame_T, double* __restrict__ pos_io) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  double pos[3] = {pos_io[3 * p], pos_io[3 * p + 1], pos_io[3 * p + 2]};
+  double old_point[3] = {pos[0], pos[1], pos[2]};
+  double chi2 = 0.0;
+  const int o0 = obs_offset[p], o1 = obs_offset[p + 1];
+  for (int it = 0; it < n_iter; ++it) {
+    double A[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}}, b[3] = {0, 0, 0}, new_chi2 = 0.0;
+    for (int o = o0; o < o1; ++o) {
+      const double* T = frame_T + 12 * (size_t)obs_frame[o];
+      const double px = T[0] * pos[0] + T[1] * pos[1] + T[2] * pos[2] + T[3];
+      const double py = T[4] * pos[0] + T[5] * pos[1] + T[6] * pos[2] + T[7];
+      const double pz = T[8] * pos[0] + T[9] * pos[1] + T[10] * pos[2] + T[11];
+      const double z_inv = 1.0 / pz, z_inv_sq = z_inv * z_inv;
+      const double pj[2][3] = {{z_inv, 0.0, -px * z_inv_sq}, {0.0, z_inv, -py * z_inv_sq}};
+      double J[2][3];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) J[r][c] = -(pj[r][0] * T[c] + pj[r][1] * T[4 + c] + pj[r][2] * T[8 + c]);
+      const double ex = obs_f[3 * o] / obs_f[3 * o + 2] - px / pz, ey = obs_f[3 * o + 1] / obs_f[3 * o + 2] - py / pz;
+      new_chi2 += ex * ex + ey * ey;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) A[r][c] += J[0][r] * J[0][c] + J[1][r] * J[1][c];
+        b[r] -= J[0][r] * ex + J[1][r] * ey;
+      }
+    }
+    double dp[3];
+    ldlt3_solve(A, b, dp);
+    if ((it > 0 && new_chi2 > chi2) || isnan(dp[0])) {
+      pos[0] = old_point[0]; pos[1] = old_point[1]; pos[2] = old_point[2];  // roll-back
+      break;
+    }
+    for (int k = 0; k < 3; ++k) { old_point[k] = pos[k]; pos[k] += dp[k]; }
+    chi2 = new_chi2;
+    if (fmax(fabs(dp[0]), fmax(fabs(dp[1]), fabs(dp[2]))) <= 0.0000000001) break;
+  }
+  pos_io[3 * p] = pos[0]; pos_io[3 * p + 1] = pos[1]; pos_io[3 * p + 2] = pos[2];
+}
+
+}  // namespace svo
+
+extern "C" int svo_b200_point_optimize_batch(svo_b200_ctx* ctx, int P, int n_iter, const int* obs_offset,
+                                             const int* obs_frame, const double* obs_f, const double* frame_T_f_w,
+                                             int n_frames, double* pos_io) {
+  if (!ctx || P < 0 || n_iter < 0 || n_frames <= 0 || (P > 0 && (!obs_offset || !obs_frame || !obs_f || !frame_T_f_w || !pos_io)))
+    return set_err(ctx, SVO_B200_EINVAL, "point_optimize_batch: bad arguments");
+  if (P == 0) return 0;
+  const int n_obs = obs_offset[P] - obs_offset[0];
+  for (int o = 0; o < n_obs; ++o)
+    if (obs_frame[obs_offset[0] + o] < 0 || obs_frame[obs_offset[0] + o] >= n_frames)
+      return set_err(ctx, SVO_B200_EINVAL, "point_optimize_batch: obs_frame[%d] out of range", o);
+  cudaSetDevice(ctx->device);
+  Carver c;
+  const size_t o_pos = c.take(sizeof(double) * 3 * P);
+  const size_t io_end = c.off;
+  const size_t o_off = c.take(sizeof(int) * (P + 1)), o_fr = c.take(sizeof(int) * (n_obs + 1)),
+               o_f = c.take(sizeof(double) * 3 * (n_obs + 1)), o_T = c.take(sizeof(double) * 12 * n_frames);
+  int rc;
+  if ((rc = ensure_host(ctx, ctx->h_in, c.off))) return rc;
+  if ((rc = ensure_dev(ctx, ctx->d_in, c.off))) return rc;
+  SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  uint8_t* h = static_cast<uint8_t*>(ctx->h_in.p);
+  uint8_t* d = static_cast<uint8_t*>(ctx->d_in.p);
+  memcpy(h + o_pos, pos_io, sizeof(double) * 3 * P);
+  int* off = reinterpret_cast<int*>(h + o_off);
+  for (int p = 0; p <= P; ++p) off[p] = obs_offset[p] - obs_offset[0];
+  memcpy(h + o_fr, obs_frame + obs_offset[0], sizeof(int) * n_obs);
+  memcpy(h + o_f, obs_f + 3 * (size_t)obs_offset[0], sizeof(double) * 3 * n_obs);
+  memcpy(h + o_T, frame_T_f_w, sizeof(double) * 12 * n_frames);
+  SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(d, h, c.off, cudaMemcpyHostToDevice, ctx->stream));
+  const int threads = 128, blocks = (P + threads - 1) / threads;
+  point_optimize_kernel<<<blocks, threads, 0, ctx->stream>>>(P, n_iter, reinterpret_cast<const int*>(d + o_off),
+                                                             reinterpret_cast<const int*>(d + o_fr),
+                                                             reinterpret_cast<const double*>(d + o_f),
+                                                             reinterpret_cast<const double*>(d + o_T),
+                                                             reinterpret_cast<double*>(d + o_pos));
+  ctx->launches++;
+  SVO_CUDA_CHECK(ctx, cudaGetLastError());
+  SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(h + o_pos, d + o_pos, io_end - o_pos, cudaMemcpyDeviceToHost, ctx->stream));
+  SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(pos_io, h + o_pos, sizeof(double) * 3 * P);
+  return 0;
+}

@@ -51,3 +51,33 @@ def test_depth_filter_update_matches_oracle(ctx, oracle, n_seeds, baseline):
     # the measurements are real: triangulated depth close to the plane depth
     assert np.median(np.abs(g["z"][upd] - c["depth_gt"][upd])) < 0.05
     ref.destroy(); cur.destroy()
+
+
+def test_point_optimize_batch_matches_oracle(ctx, oracle):
+    """Point::optimize ("next" row f3): 200 points seen from 2..6 keyframes with noisy bearings."""
+    rng = np.random.default_rng(17)
+    cam = synth.camera_for(752, 480)
+    n_frames, P = 6, 200
+    poses = [synth.se3_mul(synth.se3_exp(np.concatenate([rng.uniform(-0.3, 0.3, 3), rng.uniform(-0.05, 0.05, 3)])),
+                           synth.base_pose()) for _ in range(n_frames)]
+    plane = synth.Plane.tilted()
+    px = np.stack([rng.uniform(150, 600, P), rng.uniform(100, 380, P)], axis=1)
+    truth = synth.intersect(plane, poses[0], cam.cam2world(px))
+    pos0 = truth + rng.normal(0, 0.02, (P, 3))
+    offs, frs, fs = [0], [], []
+    for p in range(P):
+        k = int(rng.integers(2, n_frames + 1))
+        for fr in rng.choice(n_frames, k, replace=False):
+            T = poses[fr]
+            pc = T[:, :3] @ truth[p] + T[:, 3]
+            pxo = cam.world2cam(pc) + rng.normal(0, 0.3, 2)
+            frs.append(fr); fs.append(cam.cam2world(pxo))
+        offs.append(len(frs))
+    frs, fs = np.array(frs, np.int32), np.array(fs)
+    g = ctx.point_optimize_batch(5, pos0, offs, frs, fs, poses)
+    for p in range(P):
+        o = oracle.point_optimize(5, pos0[p], [poses[i] for i in frs[offs[p]:offs[p + 1]]], fs[offs[p]:offs[p + 1]])
+        # two-view points are ill-conditioned along the ray (cond ~1e6): f64 rounding differences between the
+        # quaternion path of the oracle and the matrix path of the kernel show up at the 1e-8 m level
+        assert np.allclose(g[p], o, rtol=0, atol=1e-6), p
+    assert np.median(np.linalg.norm(g - truth, axis=1)) < np.median(np.linalg.norm(pos0 - truth, axis=1))
