@@ -27,6 +27,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 #include <vector>
 
 #include "ctx.h"
@@ -135,32 +136,56 @@ __device__ __forceinline__ void jac_rows(double x, double y, double zi, double (
   a[0] = -zi; a[1] = 0.0; a[2] = X * zi; a[3] = X * Y; a[4] = -(1.0 + X * X); a[5] = Y;
   b[0] = 0.0; b[1] = -zi; b[2] = Y * zi; b[3] = 1.0 + Y * Y; b[4] = -(X * Y); b[5] = -X;
 }
-// h[21] (upper triangle, row-major) += Sxx aa^T + Sxy (ab^T + ba^T) + Syy bb^T
-__device__ __forceinline__ void add_h(double x, double y, double zi, double sxx, double sxy, double syy,
-                                      double* h) {
-  double a[6], b[6];
-  jac_rows(x, y, zi, a, b);
-  int idx = 0;
-#pragma unroll
-  for (int r = 0; r < 6; ++r)
-#pragma unroll
-    for (int c = r; c < 6; ++c, ++idx)
-      h[idx] = fma(sxx, a[r] * a[c], fma(sxy, fma(a[r], b[c], b[r] * a[c]), fma(syy, b[r] * b[c], h[idx])));
+// Entry `idx` (0..20, upper triangle row-major) of Sxx aa^T + Sxy (ab^T + ba^T) + Syy bb^T.
+template <int IDX>
+__device__ __forceinline__ double h_entry(const double (&a)[6], const double (&b)[6], double sxx, double sxy, double syy) {
+  constexpr int R = IDX < 6 ? 0 : IDX < 11 ? 1 : IDX < 15 ? 2 : IDX < 18 ? 3 : IDX < 20 ? 4 : 5;
+  constexpr int BASE = R == 0 ? 0 : R == 1 ? 6 : R == 2 ? 11 : R == 3 ? 15 : R == 4 ? 18 : 20;
+  constexpr int C = R + (IDX - BASE);
+  return fma(sxx, a[R] * a[C], fma(sxy, fma(a[R], b[C], b[R] * a[C]), syy * (b[R] * b[C])));
+}
+template <int CHUNK, int J>
+__device__ __forceinline__ double h_chunk_value(const double (&a)[6], const double (&b)[6], double sxx, double sxy,
+                                                double syy, double cnt) {
+  constexpr int IDX = CHUNK * 8 + J;
+  if constexpr (IDX < 21) return h_entry<IDX>(a, b, sxx, sxy, syy);
+  else if constexpr (IDX == 21) return cnt;
+  else return 0.0;
 }
 
-// Block sum of 24 doubles (21 H entries + counts), once per level: transposed warp reductions of
-// 16 + 8 values, one shared-memory hop, warp 0 adds the per-warp partials.  ONE __syncthreads.
-__device__ __forceinline__ void block_sum24_to_warp0(double (&v)[kPartK], SiaShared& s, int nwarps) {
+// Block sum of the 21 unique H entries + one count over per-feature moments, once per level (and in the
+// rare "slow path"): three transposed 8-value warp reductions computed chunk by chunk so that only ~8
+// accumulators are live at a time (no register spills), one shared-memory hop, warp 0 adds the
+// per-warp partials.  ONE __syncthreads.  `get(k, x, y, zi, sxx, sxy, syy, cnt)` yields feature k's data.
+template <int FPT, class Get>
+__device__ __forceinline__ void block_sum_h_to_warp0(Get get, SiaShared& s, int nwarps) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  double a16[16], a8[8];
+  auto do_chunk = [&](auto chunk_tag) {
+    constexpr int CH = decltype(chunk_tag)::value;
+    double v[8];
 #pragma unroll
-  for (int k = 0; k < 16; ++k) a16[k] = v[k];
+    for (int j = 0; j < 8; ++j) v[j] = 0.0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) a8[k] = v[16 + k];
-  warp_reduce_t<16>(a16);
-  warp_reduce_t<8>(a8);
-  if ((lane & 1) == 0) s.part[warp * kPartK + (lane >> 1)] = a16[0];
-  if ((lane & 3) == 0) s.part[warp * kPartK + 16 + (lane >> 2)] = a8[0];
+    for (int k = 0; k < FPT; ++k) {
+      double x, y, zi, sxx, sxy, syy, cnt;
+      get(k, x, y, zi, sxx, sxy, syy, cnt);
+      double a[6], b[6];
+      jac_rows(x, y, zi, a, b);
+      v[0] += h_chunk_value<CH, 0>(a, b, sxx, sxy, syy, cnt);
+      v[1] += h_chunk_value<CH, 1>(a, b, sxx, sxy, syy, cnt);
+      v[2] += h_chunk_value<CH, 2>(a, b, sxx, sxy, syy, cnt);
+      v[3] += h_chunk_value<CH, 3>(a, b, sxx, sxy, syy, cnt);
+      v[4] += h_chunk_value<CH, 4>(a, b, sxx, sxy, syy, cnt);
+      v[5] += h_chunk_value<CH, 5>(a, b, sxx, sxy, syy, cnt);
+      v[6] += h_chunk_value<CH, 6>(a, b, sxx, sxy, syy, cnt);
+      v[7] += h_chunk_value<CH, 7>(a, b, sxx, sxy, syy, cnt);
+    }
+    warp_reduce_t<8>(v);
+    if ((lane & 3) == 0) s.part[warp * kPartK + CH * 8 + (lane >> 2)] = v[0];
+  };
+  do_chunk(std::integral_constant<int, 0>{});
+  do_chunk(std::integral_constant<int, 1>{});
+  do_chunk(std::integral_constant<int, 2>{});
   __syncthreads();
   if (warp == 0) {
     if (lane < kPartK) {
@@ -352,11 +377,10 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
     long long tq0 = 0;
     if ((SVO_SIA_DEBUG && P.debug) && tid == 0) tq0 = clock64();
     // ---- precomputeReferencePatches (:84-145), one feature per thread -----------------------
-    double hsum[kPartK];
-#pragma unroll
-    for (int k = 0; k < kPartK; ++k) hsum[k] = 0.0;
+    double m_sxx[FPT], m_sxy[FPT], m_syy[FPT], m_cnt[FPT];
 #pragma unroll
     for (int k = 0; k < FPT; ++k) {
+      m_sxx[k] = m_sxy[k] = m_syy[k] = m_cnt[k] = 0.0;
       const int slot = tid + k * T;
       const float u_ref = (float)(fpx_[k] * (double)scale);
       const float v_ref = (float)(fpy_[k] * (double)scale);
@@ -406,18 +430,21 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
 #pragma unroll
           for (int c = 0; c < 7; ++c) pr0[c] = pr1[c];
         }
-        add_h(fx_[k], fy_[k], fzi_[k], sxx, sxy, syy, hsum);
-        hsum[21] += 1.0;
+        m_sxx[k] = sxx; m_sxy[k] = sxy; m_syy[k] = syy; m_cnt[k] = 1.0;
       } else if ((vis_mask >> k) & 1u) {
         // visible from a coarser level but failing here: the reference would keep the stale patch
         // and a zeroed Jacobian (jacobian_cache_.setZero() per level, :64).  Unreachable for
         // dyadic pyramids but kept bit-faithful.
 #pragma unroll
         for (int p = 0; p < kPatchArea; ++p) pat_dxy[p * S + slot] = make_float2(0.f, 0.f);
-        hsum[21] += 1.0;
+        m_cnt[k] = 1.0;
       }
     }
-    block_sum24_to_warp0(hsum, s, nwarps);
+    block_sum_h_to_warp0<FPT>(
+        [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
+          x = fx_[k]; y = fy_[k]; zi = fzi_[k]; sxx = m_sxx[k]; sxy = m_sxy[k]; syy = m_syy[k]; cnt = m_cnt[k];
+        },
+        s, nwarps);
     if (tid == 0) {
       long long tq1 = 0;
       if (SVO_SIA_DEBUG && P.debug) { tq1 = clock64(); s.tk[0] += tq1 - tq0; }
@@ -548,25 +575,26 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       if (s.slow) {
         // some visible patches fell outside the current image (or EVAL wants H): H_ = sum over the
         // patches that contributed in this pass.
-        double hs2[kPartK];
-#pragma unroll
-        for (int k = 0; k < kPartK; ++k) hs2[k] = 0.0;
+        double q_sxx[FPT], q_sxy[FPT], q_syy[FPT];
 #pragma unroll
         for (int k = 0; k < FPT; ++k) {
+          q_sxx[k] = q_sxy[k] = q_syy[k] = 0.0;
           if (!((in_mask >> k) & 1u)) continue;
           const int slot = tid + k * T;
-          double sxx = 0, sxy = 0, syy = 0;
 #pragma unroll
           for (int p = 0; p < kPatchArea; ++p) {
             const float2 g = pat_dxy[p * S + slot];
             const double dx = (double)g.x, dy = (double)g.y;
-            sxx = fma(dx, dx, sxx);
-            sxy = fma(dx, dy, sxy);
-            syy = fma(dy, dy, syy);
+            q_sxx[k] = fma(dx, dx, q_sxx[k]);
+            q_sxy[k] = fma(dx, dy, q_sxy[k]);
+            q_syy[k] = fma(dy, dy, q_syy[k]);
           }
-          add_h(fx_[k], fy_[k], fzi_[k], sxx, sxy, syy, hs2);
         }
-        block_sum24_to_warp0(hs2, s, nwarps);
+        block_sum_h_to_warp0<FPT>(
+            [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
+              x = fx_[k]; y = fy_[k]; zi = fzi_[k]; sxx = q_sxx[k]; sxy = q_sxy[k]; syy = q_syy[k]; cnt = 0.0;
+            },
+            s, nwarps);
         if (tid == 0) {
           const double s2 = jscale * jscale;
           int idx = 0;
