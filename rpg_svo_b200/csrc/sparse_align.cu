@@ -333,15 +333,13 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
   const uint8_t* b_hp = reinterpret_cast<const uint8_t*>(b_pos + 3 * np);
 
   // per-feature register state
-  double fx_[FPT], fy_[FPT], fz_[FPT], fzi_[FPT], fpx_[FPT], fpy_[FPT];
+  double fx_[FPT], fy_[FPT], fz_[FPT], fzi_[FPT];
   unsigned hp_mask = 0, vis_mask = 0, in_mask = 0;
 #pragma unroll
   for (int k = 0; k < FPT; ++k) {
     const int i = tid + k * T;
-    fx_[k] = fy_[k] = 0.0; fz_[k] = fzi_[k] = 1.0; fpx_[k] = fpy_[k] = -1e6;
+    fx_[k] = fy_[k] = 0.0; fz_[k] = fzi_[k] = 1.0;
     if (i < N) {
-      fpx_[k] = b_px[2 * i];
-      fpy_[k] = b_px[2 * i + 1];
       const double dxp = b_pos[3 * i] - job.ref_pos[0], dyp = b_pos[3 * i + 1] - job.ref_pos[1],
                    dzp = b_pos[3 * i + 2] - job.ref_pos[2];
       const double depth = sqrt(dxp * dxp + dyp * dyp + dzp * dzp);  // :107  |pos - ref_pos|
@@ -382,8 +380,10 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
     for (int k = 0; k < FPT; ++k) {
       m_sxx[k] = m_sxy[k] = m_syy[k] = m_cnt[k] = 0.0;
       const int slot = tid + k * T;
-      const float u_ref = (float)(fpx_[k] * (double)scale);
-      const float v_ref = (float)(fpy_[k] * (double)scale);
+      // px is re-read from the pair's blob in global memory (L2) once per level instead of living in registers
+      const double2 pxy = slot < N ? __ldg(reinterpret_cast<const double2*>(job.blob) + slot) : make_double2(-1e6, -1e6);
+      const float u_ref = (float)(pxy.x * (double)scale);
+      const float v_ref = (float)(pxy.y * (double)scale);
       const bool rng = u_ref >= 0.f && v_ref >= 0.f && u_ref < 1e6f && v_ref < 1e6f;  // else: outside, floor not needed
       float ufl = 0.f, vfl = 0.f;
       const int ui = rng ? floor_pos(u_ref, ufl) : -1, vi = rng ? floor_pos(v_ref, vfl) : -1;
