@@ -166,6 +166,37 @@ __global__ void __launch_bounds__(128) pyramid_fused_kernel(int first, PyrGeom g
   }
 }
 
+
+// Level 0 -> level 1 for a batch of frames as a pure streaming kernel: 94 % of the pyramid's bytes move
+// here, so it is written against the HBM roofline -- a persistent grid (a few CTAs per SM), each work
+// item = 16 level-0 pixels of two consecutive rows (2 x 128-bit loads) -> 8 level-1 pixels (one 64-bit
+// store); the 2x2 sums are formed SIMD-in-register (two 16-bit lanes per word).  Requires W0 % 16 == 0.
+__global__ void __launch_bounds__(256) pyramid_l0_l1_stream_kernel(const uint8_t* __restrict__ l0, size_t stride0,
+                                                                   uint8_t* __restrict__ l1, size_t stride1, int first,
+                                                                   int count, int W0, int H1) {
+  const int items_x = W0 >> 4, W1 = W0 >> 1;
+  const long long per_frame = (long long)items_x * H1, total = per_frame * count;
+  for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (long long)gridDim.x * blockDim.x) {
+    const int fr = (int)(it / per_frame);
+    const int rem = (int)(it - (long long)fr * per_frame);
+    const int y = rem / items_x, ix = rem - y * items_x;
+    const uint8_t* src = l0 + (size_t)(first + fr) * stride0 + (size_t)(2 * y) * W0 + 16 * ix;
+    const uint4 a = __ldg(reinterpret_cast<const uint4*>(src));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(src + W0));
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[2] = {0u, 0u};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // horizontal pair sums of both rows in two 16-bit lanes, then the vertical add and the /4
+      const uint32_t s = (aw[k] & 0x00ff00ffu) + ((aw[k] >> 8) & 0x00ff00ffu) + (bw[k] & 0x00ff00ffu) + ((bw[k] >> 8) & 0x00ff00ffu);
+      const uint32_t q = (s >> 2) & 0x00ff00ffu;             // two results, bytes 0 and 2
+      const uint32_t two = (q & 0xffu) | ((q >> 8) & 0xff00u);  // packed into the low 16 bits
+      o[k >> 1] |= two << (16 * (k & 1));
+    }
+    *reinterpret_cast<uint2*>(l1 + (size_t)(first + fr) * stride1 + (size_t)y * W1 + 8 * ix) = make_uint2(o[0], o[1]);
+  }
+}
+
 static int build_levels(svo_b200_ctx* ctx, svo_b200_frame* fr, int from_level) {
   for (int l = from_level; l < fr->n_levels; ++l) {
     const int total = ((fr->w[l] + 3) / 4) * fr->h[l];
@@ -369,21 +400,36 @@ int svo_b200_frame_pool_upload(svo_b200_ctx* ctx, svo_b200_frame_pool* pool, int
                                           cudaMemcpyHostToDevice, ctx->stream));
   }
   if (f0.n_levels > 1) {
-    PyrGeom g;
-    memset(&g, 0, sizeof(g));
-    g.n_levels = f0.n_levels < 5 ? f0.n_levels : 5;
-    for (int l = 0; l < f0.n_levels; ++l) { g.w[l] = f0.w[l]; g.h[l] = f0.h[l]; g.slab[l] = pool->slab[l]; g.stride[l] = pool->stride[l]; }
-    g.tiles_x = (f0.w[0] + 127) / 128;
-    const int tiles_y = (f0.h[0] + 15) / 16;
-    for (int done = 0; done < count; done += 32768) {  // gridDim.y limit 65535
-      const int n = count - done < 32768 ? count - done : 32768;
-      dim3 grid(g.tiles_x * tiles_y, n);
-      pyramid_fused_kernel<<<grid, 128, 0, ctx->stream>>>(first + done, g);
+    // level 0 -> 1 with the streaming kernel when the width allows 128-bit rows, then levels 2.. from
+    // level 1 with the fused tile kernel (base level shifted by one); otherwise everything from level 0.
+    const bool stream01 = (f0.w[0] % 16) == 0;
+    const int base = stream01 ? 1 : 0;
+    if (stream01) {
+      const int blocks = ctx->sm_count * 8;
+      pyramid_l0_l1_stream_kernel<<<blocks, 256, 0, ctx->stream>>>(pool->slab[0], pool->stride[0], pool->slab[1],
+                                                                   pool->stride[1], first, count, f0.w[0], f0.h[1]);
       ctx->launches++;
     }
+    const int n_sub = f0.n_levels - base;  // levels seen by the fused kernel, its level 0 = our level `base`
+    if (n_sub > 1) {
+      PyrGeom g;
+      memset(&g, 0, sizeof(g));
+      g.n_levels = n_sub < 5 ? n_sub : 5;
+      for (int l = 0; l < n_sub; ++l) {
+        g.w[l] = f0.w[base + l]; g.h[l] = f0.h[base + l]; g.slab[l] = pool->slab[base + l]; g.stride[l] = pool->stride[base + l];
+      }
+      g.tiles_x = (g.w[0] + 127) / 128;
+      const int tiles_y = (g.h[0] + 15) / 16;
+      for (int done = 0; done < count; done += 32768) {  // gridDim.y limit 65535
+        const int n = count - done < 32768 ? count - done : 32768;
+        dim3 grid(g.tiles_x * tiles_y, n);
+        pyramid_fused_kernel<<<grid, 128, 0, ctx->stream>>>(first + done, g);
+        ctx->launches++;
+      }
+    }
     SVO_CUDA_CHECK(ctx, cudaGetLastError());
-    for (int i = 0; i < count && f0.n_levels > 5; ++i) {  // levels 5.. : plain per-level kernel
-      int rc = build_levels(ctx, &pool->frames[first + i], 5);
+    for (int i = 0; i < count && f0.n_levels > base + 5; ++i) {  // deeper levels: plain per-level kernel
+      int rc = build_levels(ctx, &pool->frames[first + i], base + 5);
       if (rc) return rc;
     }
   }
