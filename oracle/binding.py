@@ -16,6 +16,15 @@ _LIB_PATH = os.path.join(_HERE, "libsvo_oracle.so")
 MAX_LEVELS = 8
 
 
+def build_ref() -> str | None:
+    """oracle/_ref: the reference's own feature_alignment.cpp compiled against oracle/shim (only where
+    /root/reference exists; the GPU box uses the prebuilt .so that travels with the snapshot)."""
+    out = os.path.join(_HERE, "_ref", "libsvo_ref_align.so")
+    if os.path.isdir("/root/reference/svo/src"):
+        subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
+    return out if os.path.exists(out) else None
+
+
 def build(force: bool = False) -> str:
     srcs = ["svo_oracle.cpp", "svo_oracle_align.inc", "svo_oracle_depth.inc", "svo_oracle_pose.inc",
             "oracle_math.h", "svo_oracle.h", "Makefile"]
@@ -344,3 +353,37 @@ def point_optimize(n_iter, pos, obs_T_f_w, obs_f):
     f = c64(obs_f)
     lib().orc_point_optimize(int(n_iter), _p(p), len(f), _p(T), _p(f))
     return p
+
+
+# ---- oracle/_ref: the reference's own align1D/align2D (compiled from /root/reference with stand-in headers) ----
+_ref_lib = None
+
+
+def ref_lib():
+    """CDLL of oracle/_ref/libsvo_ref_align.so or None when it has not been built."""
+    global _ref_lib
+    if _ref_lib is None:
+        path = os.path.join(_HERE, "_ref", "libsvo_ref_align.so")
+        if not os.path.exists(path):
+            build_ref()
+        if os.path.exists(path):
+            _ref_lib = C.CDLL(path)
+    return _ref_lib
+
+
+def ref_align2d(cur_img, pwb, ref_patch, n_iter, px):
+    px = c64(px).copy()
+    pwb, ref_patch = np.ascontiguousarray(pwb, np.uint8).copy(), np.ascontiguousarray(ref_patch, np.uint8).copy()
+    ok = ref_lib().ref_align2d(_p(cur_img), cur_img.shape[1], cur_img.shape[0], cur_img.strides[0], _p(pwb), _p(ref_patch),
+                               n_iter, _p(px))
+    return bool(ok), px
+
+
+def ref_align1d(cur_img, direction, pwb, ref_patch, n_iter, px):
+    px = c64(px).copy()
+    d = np.ascontiguousarray(direction, np.float32)
+    pwb, ref_patch = np.ascontiguousarray(pwb, np.uint8).copy(), np.ascontiguousarray(ref_patch, np.uint8).copy()
+    h = C.c_double(0)
+    ok = ref_lib().ref_align1d(_p(cur_img), cur_img.shape[1], cur_img.shape[0], cur_img.strides[0], _p(d), _p(pwb),
+                               _p(ref_patch), n_iter, _p(px), C.byref(h))
+    return bool(ok), px, h.value

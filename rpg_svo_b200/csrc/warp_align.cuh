@@ -211,8 +211,8 @@ __device__ inline bool warp_align1d(const ImgView& img, WarpAlignScratch& S, flo
       break;
     }
     chi2 = new_chi2;
-    up0 = fmaf(Hinv[0][0], J0, __fmul_rn(Hinv[0][1], J1));
-    up1 = fmaf(Hinv[1][0], J0, __fmul_rn(Hinv[1][1], J1));
+    up0 = fmaf(Hinv[0][1], J1, __fmul_rn(Hinv[0][0], J0));  // fusion order as the compiled reference (oracle/_ref)
+    up1 = fmaf(Hinv[1][1], J1, __fmul_rn(Hinv[1][0], J0));
     u = fmaf(up0, dir0, u);
     v = fmaf(up0, dir1, v);
     mean_diff = __fadd_rn(mean_diff, up1);

@@ -73,3 +73,21 @@ def test_find_match_direct(ctx, oracle):
     ok = g["success"]
     assert np.median(np.linalg.norm(g["px_cur"][ok] - c["px_cur_true"][ok], axis=1)) < 0.3
     ref.destroy(); cur.destroy()
+
+
+def test_align_kernels_equal_reference_source_compiled(ctx, oracle, case):
+    """GPU kernels vs oracle/_ref (the reference's own feature_alignment.cpp compiled with stand-in headers):
+    bit-identical pixel estimates and convergence flags."""
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not present on this box")
+    c = case
+    fr = ctx.frame(c["pyr"])
+    conv, px = ctx.align2d_batch(fr, c["level"], c["pwb"], c["patch"], 10, c["px_start"])
+    conv1, px1, h1 = ctx.align1d_batch(fr, c["level"], c["dir"], c["pwb"], c["patch"], 10, c["px_start"])
+    for i in range(len(c["level"])):
+        img = c["pyr"][c["level"][i]]
+        ok, p = oracle.ref_align2d(img, c["pwb"][i], c["patch"][i], 10, c["px_start"][i])
+        assert ok == conv[i] and np.array_equal(p, px[i]), i
+        ok, p, h = oracle.ref_align1d(img, c["dir"][i], c["pwb"][i], c["patch"][i], 10, c["px_start"][i])
+        assert ok == conv1[i] and np.array_equal(p, px1[i]) and h == h1[i], i
+    fr.destroy()

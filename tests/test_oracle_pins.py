@@ -187,3 +187,21 @@ def test_pose_optimizer_recovers_pose(oracle):
     assert dt < 1e-6 and dr < 1e-6
     assert o["num_obs"] == int(c["has_point"].sum()) and o["error_final"] < 1e-3
     assert np.allclose(o["cov"], o["cov"].T, rtol=1e-6)
+
+
+def test_oracle_align_equals_reference_source_compiled_here(oracle):
+    """oracle/_ref = the reference's OWN svo/src/feature_alignment.cpp compiled in place with GCC -O3 -mfma
+    (default -ffp-contract=fast) against the stand-in Eigen / cv::Mat headers in oracle/shim.  The oracle's
+    restatement -- including its explicit-fma contraction pattern -- must reproduce it bit for bit."""
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+    c = synth.make_align_case(11, 300)
+    for n_iter in (3, 10):
+        for i in range(len(c["level"])):
+            img = c["pyr"][c["level"][i]]
+            ok_o, px_o = oracle.align2d(img, c["pwb"][i], c["patch"][i], n_iter, c["px_start"][i])
+            ok_r, px_r = oracle.ref_align2d(img, c["pwb"][i], c["patch"][i], n_iter, c["px_start"][i])
+            assert ok_o == ok_r and np.array_equal(px_o, px_r), ("align2D", i, n_iter)
+            ok_o, px_o, h_o = oracle.align1d(img, c["dir"][i], c["pwb"][i], c["patch"][i], n_iter, c["px_start"][i])
+            ok_r, px_r, h_r = oracle.ref_align1d(img, c["dir"][i], c["pwb"][i], c["patch"][i], n_iter, c["px_start"][i])
+            assert ok_o == ok_r and np.array_equal(px_o, px_r) and h_o == h_r, ("align1D", i, n_iter)
