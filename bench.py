@@ -13,7 +13,7 @@ ranks):
   e2e   : through the C ABI with HOST (pinned) buffers: per step every frame's level-0 image is
           copied host->device and its pyramid built on the GPU, features are packed + copied, the
           kernel runs, poses / masks / counters are copied back.
-`--impl reference` times the CPU oracle port (the reference cannot be built here: Eigen, OpenCV,
+`--impl reference` times oracle/_ref (the reference's own sparse_img_align.cpp compiled in place; its build system cannot run here: Eigen, OpenCV,
 Sophus, vikit, Boost are absent) on all host cores, on a bounded sample of the same pairs.
 
 L2 policy: inputs larger than L2 (592 pairs x 2 pyramids ~ 243 MB of distinct images per step vs
@@ -124,7 +124,32 @@ def make_inputs(rank: int, B: int, device: str):
     T0 = np.tile(synth.se3_identity()[None], (B, 1, 1))
     T_gt = np.stack([synth.se3_mul(st["poses"][k + 1], synth.se3_inv(st["poses"][k])) for k in range(B)])
     return dict(cam=st["cam"], level0=st["level0"], px=px, f=f, pos=pos, hp=hp, off=off, ref_pos=ref_pos,
-                T0=T0, T_gt=T_gt)
+                T0=T0, T_gt=T_gt, poses=np.stack(st["poses"]))
+
+
+def cpu_runner(ob, synth, inp, n: int):
+    """The CPU implementation of the step's first n frame pairs: returns (kind, note, run(n_threads) -> seconds).
+    kind "reference" = oracle/_ref, svo::SparseImgAlign::run of the reference's own sparse_img_align.cpp/frame.cpp
+    compiled in place (stand-in third-party headers); "port" = the oracle restatement when
+    oracle/_ref was never built."""
+    sl = slice(0, n * NFEAT)
+    if ob.ref_lib() is not None:
+        rs = ob.RefStream(inp["level0"][:n + 1].cpu().numpy(), inp["cam"], NLEVELS, inp["poses"][:n + 1], inp["off"][:n + 1],
+                          inp["px"][sl], inp["f"][sl], inp["pos"][sl], inp["hp"][sl])
+        note = ("svo::SparseImgAlign::run from the reference's own svo/src/sparse_img_align.cpp + frame.cpp, compiled in "
+                "place with g++ -O3 -mfma -mavx2 against stand-in Eigen/Sophus/vikit/OpenCV headers (oracle/shim); "
+                "a fresh SparseImgAlign per frame as in FrameHandlerMono::processFrame; pyramids prebuilt")
+        return "reference", note, lambda n_threads: rs.run(n_threads, MAX_LEVEL, MIN_LEVEL, NITER)["seconds"]
+    pyrs = [synth.build_pyramid(inp["level0"][i].cpu().numpy(), NLEVELS) for i in range(n + 1)]
+
+    def run(n_threads):
+        t0 = time.perf_counter()
+        ob.sparse_img_align_batch(pyrs[:n], pyrs[1:n + 1], inp["cam"], inp["T0"][:n], inp["off"][:n + 1], inp["px"][sl],
+                                  inp["f"][sl], inp["pos"][sl], inp["hp"][sl], inp["ref_pos"][:n], MAX_LEVEL, MIN_LEVEL,
+                                  NITER, n_threads=n_threads)
+        return time.perf_counter() - t0
+
+    return "port", "CPU oracle port of svo::SparseImgAlign::run (oracle/_ref not built on this box)", run
 
 
 def oracle_pair(ob, synth, inp, pyr_cache, k):
@@ -138,7 +163,7 @@ def oracle_pair(ob, synth, inp, pyr_cache, k):
 
 
 def run_reference(args, rank: int, world: int):
-    """CPU arm: the oracle port on all host cores (rank 0 only)."""
+    """CPU arm (rank 0 only): the reference's own SparseImgAlign (oracle/_ref) on all host cores, else the oracle port."""
     if rank != 0:
         return
     from oracle import binding as ob
@@ -148,28 +173,20 @@ def run_reference(args, rank: int, world: int):
     cores = os.cpu_count() or 1
     sample = args.pairs_per_gpu  # the whole window of the step (bounded: ~1 s of CPU work on 1 core per 500 pairs)
     inp = make_inputs(0, sample, "cuda" if _has_cuda() else "cpu")
-    pyrs = [synth.build_pyramid(inp["level0"][i].numpy(), NLEVELS) for i in range(sample + 1)]
-
-    def step():
-        return ob.sparse_img_align_batch(pyrs[:sample], pyrs[1:sample + 1], inp["cam"], inp["T0"], inp["off"],
-                                         inp["px"], inp["f"], inp["pos"], inp["hp"], inp["ref_pos"], MAX_LEVEL,
-                                         MIN_LEVEL, NITER, n_threads=cores)
-
+    kind, note, run = cpu_runner(ob, synth, inp, sample)
     for _ in range(args.warmup):
-        step()
-    t0 = time.perf_counter()
+        run(cores)
+    dt = 0.0
     for _ in range(args.steps):
-        step()
-    dt = time.perf_counter() - t0
+        dt += run(cores)
     fps = sample * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/f64",
             "data": "synthetic",
             "config": {"workload": "C1 single stream 640x480 / 300 feats / levels 4..0 / 30 GN iters",
-                       "pairs_per_step": sample, "note": "CPU oracle port of svo::SparseImgAlign::run; the "
-                       "reference itself cannot be built here (Eigen/OpenCV/Sophus/vikit absent)"},
-            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
+                       "pairs_per_step": sample, "note": note},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind,
                              "sample": f"{sample} frame pairs of the step x {args.steps} steps, {cores} threads"},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -414,26 +431,15 @@ def main():
         from rpg_svo_b200 import synth
 
         n = min(args.cpu_sample, B)
-        pyrs = [synth.build_pyramid(inp["level0"][i].numpy(), NLEVELS) for i in range(n + 1)]
-
-        sl = slice(0, n * NFEAT)
-
-        def run_sample():
-            ob.sparse_img_align_batch(pyrs[:n], pyrs[1:n + 1], inp["cam"], inp["T0"][:n], inp["off"][:n + 1],
-                                      inp["px"][sl], inp["f"][sl], inp["pos"][sl], inp["hp"][sl],
-                                      inp["ref_pos"][:n], MAX_LEVEL, MIN_LEVEL, NITER, n_threads=1)
-
-        run_sample()
-        reps = 0
-        t0 = time.perf_counter()
-        while True:
-            run_sample()
+        kind, note, run = cpu_runner(ob, synth, inp, n)
+        run(1)
+        reps, dt = 0, 0.0
+        while dt < 10.0 and reps < 40:
+            dt += run(1)
             reps += 1
-            if time.perf_counter() - t0 > 10.0 or reps >= 40:
-                break
-        dt = time.perf_counter() - t0
-        cpu = {"value": n * reps / dt, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"first {n} frame pairs of the step x {reps} passes, single thread, {os.cpu_count()} host cores present"}
+        cpu = {"value": n * reps / dt, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": f"first {n} frame pairs of the step x {reps} passes, single thread, {os.cpu_count()} host cores present",
+               "note": note}
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")

@@ -17,9 +17,10 @@ MAX_LEVELS = 8
 
 
 def build_ref() -> str | None:
-    """oracle/_ref: the reference's own feature_alignment.cpp compiled against oracle/shim (only where
+    """oracle/_ref: the reference's own hot-path sources (feature_alignment, sparse_img_align, matcher,
+    pose_optimizer, point, frame, config .cpp) compiled where they lie against oracle/shim (only where
     /root/reference exists; the GPU box uses the prebuilt .so that travels with the snapshot)."""
-    out = os.path.join(_HERE, "_ref", "libsvo_ref_align.so")
+    out = os.path.join(_HERE, "_ref", "libsvo_ref.so")
     if os.path.isdir("/root/reference/svo/src"):
         subprocess.check_call(["make", "-s", "-C", _HERE, "ref"])
     return out if os.path.exists(out) else None
@@ -355,20 +356,81 @@ def point_optimize(n_iter, pos, obs_T_f_w, obs_f):
     return p
 
 
-# ---- oracle/_ref: the reference's own align1D/align2D (compiled from /root/reference with stand-in headers) ----
+# ---- oracle/_ref: the reference's own classes (compiled from /root/reference with stand-in headers) ----
 _ref_lib = None
 
 
 def ref_lib():
-    """CDLL of oracle/_ref/libsvo_ref_align.so or None when it has not been built."""
+    """CDLL of oracle/_ref/libsvo_ref.so or None when it has not been built."""
     global _ref_lib
     if _ref_lib is None:
-        path = os.path.join(_HERE, "_ref", "libsvo_ref_align.so")
+        path = os.path.join(_HERE, "_ref", "libsvo_ref.so")
         if not os.path.exists(path):
             build_ref()
         if os.path.exists(path):
             _ref_lib = C.CDLL(path)
+            _ref_lib.ref_sparse_img_align.restype = C.c_longlong
     return _ref_lib
+
+
+def _cam4(cam):
+    return c64([cam.fx, cam.fy, cam.cx, cam.cy])
+
+
+def ref_sparse_img_align(ref_l0, cur_l0, n_levels, cam, T_ref_w, T_cur_w, px, f, pos, has_point, max_level, min_level,
+                         n_iter=30):
+    """svo::SparseImgAlign(max, min, n_iter, GaussNewton, false, false).run(ref, cur) of the compiled reference; the
+    frames' pyramids are built by the reference's own frame_utils::createImgPyramid."""
+    h, w = ref_l0.shape
+    T = c64(T_cur_w).copy().reshape(12)
+    px, f, pos = c64(px), c64(f), c64(pos)
+    hp = np.ascontiguousarray(has_point, np.uint8)
+    n = len(hp)
+    vis = np.zeros(n, np.uint8)
+    H = np.zeros(36)
+    cache = np.zeros((n, 16), np.float32)
+    ret = ref_lib().ref_sparse_img_align(_p(np.ascontiguousarray(ref_l0)), _p(np.ascontiguousarray(cur_l0)), w, h, n_levels,
+                                         _p(_cam4(cam)), _p(c64(T_ref_w).reshape(12)), _p(T), _p(px), _p(f), _p(pos), _p(hp),
+                                         n, max_level, min_level, n_iter, _p(vis), _p(H), _p(cache))
+    return dict(T_cur_w=T.reshape(3, 4), n_tracked=int(ret), visible=vis, H=H.reshape(6, 6), ref_patch=cache)
+
+
+def ref_pose_optimize(reproj_thresh, n_iter, cam, T_f_w, f, pos, level, has_point):
+    T = c64(T_f_w).copy().reshape(12)
+    hp = np.ascontiguousarray(has_point, np.uint8).copy()
+    sc = np.zeros(4)
+    cov = np.zeros(36)
+    ref_lib().ref_pose_optimize(C.c_double(reproj_thresh), n_iter, _p(_cam4(cam)), cam.width, cam.height, _p(T), _p(c64(f)),
+                                _p(c64(pos)), _p(np.ascontiguousarray(level, np.int32)), _p(hp), len(hp), _p(sc), _p(cov))
+    return dict(T=T.reshape(3, 4), has_point=hp, estimated_scale=sc[0], error_init=sc[1], error_final=sc[2],
+                num_obs=int(sc[3]), cov=cov.reshape(6, 6))
+
+
+def ref_point_optimize(n_iter, pos, obs_T_f_w, obs_f):
+    p = c64(pos).copy()
+    f = c64(obs_f)
+    ref_lib().ref_point_optimize(int(n_iter), _p(p), len(f), _p(c64(np.asarray(obs_T_f_w)).reshape(-1)), _p(f))
+    return p
+
+
+class RefMatchOut(C.Structure):
+    _fields_ = [("success", C.c_int), ("search_level", C.c_int), ("reject", C.c_int), ("px_cur", C.c_double * 2),
+                ("A", C.c_double * 4), ("h_inv", C.c_double), ("epi_length", C.c_double), ("depth", C.c_double)]
+
+
+def ref_matcher(mode, ref_l0, cur_l0, n_levels, cam, T_ref_w, T_cur_w, ref_px, ref_f, ref_level, ftr_type, ref_grad,
+                point_pos, px_cur=(0, 0), d_est=0.0, d_min=0.0, d_max=0.0, n_pyr_levels=3):
+    """mode 0: svo::Matcher::findMatchDirect(pt, cur, px_cur); mode 1: findEpipolarMatchDirect(ref, cur, ftr, d_est,
+    d_min, d_max) of the compiled reference (default Matcher::Options)."""
+    h, w = ref_l0.shape
+    out = RefMatchOut()
+    ref_lib().ref_matcher(mode, _p(np.ascontiguousarray(ref_l0)), _p(np.ascontiguousarray(cur_l0)), w, h, n_levels,
+                          _p(_cam4(cam)), _p(c64(T_ref_w).reshape(12)), _p(c64(T_cur_w).reshape(12)), _p(c64(ref_px)),
+                          _p(c64(ref_f)), ref_level, ftr_type, _p(c64(ref_grad)), _p(c64(point_pos)), _p(c64(px_cur)),
+                          C.c_double(d_est), C.c_double(d_min), C.c_double(d_max), n_pyr_levels, C.byref(out))
+    return dict(success=bool(out.success), search_level=out.search_level, reject=bool(out.reject),
+                px_cur=np.array(out.px_cur[:]), A_cur_ref=np.array(out.A[:]).reshape(2, 2), h_inv=out.h_inv,
+                epi_length=out.epi_length, depth=out.depth)
 
 
 def ref_align2d(cur_img, pwb, ref_patch, n_iter, px):
@@ -387,3 +449,64 @@ def ref_align1d(cur_img, direction, pwb, ref_patch, n_iter, px):
     ok = ref_lib().ref_align1d(_p(cur_img), cur_img.shape[1], cur_img.shape[0], cur_img.strides[0], _p(d), _p(pwb),
                                _p(ref_patch), n_iter, _p(px), C.byref(h))
     return bool(ok), px, h.value
+
+
+def ref_update_seed(x, tau2, a, b, mu, z_range, sigma2):
+    s = np.array([a, b, mu, z_range, sigma2], dtype=np.float32)
+    base = s.ctypes.data
+    ref_lib().ref_update_seed(C.c_float(x), C.c_float(tau2), base, base + 4, base + 8, base + 12, base + 16)
+    return s
+
+
+def ref_compute_tau(T_ref_cur, f, z, px_error_angle):
+    fn = ref_lib().ref_compute_tau
+    fn.restype = C.c_double
+    return fn(_p(c64(T_ref_cur).reshape(12)), _p(c64(f)), C.c_double(z), C.c_double(px_error_angle))
+
+
+def ref_depth_filter_update(ref_l0s, ref_T_f_w, cur_l0, cur_T_f_w, n_levels, cam, ref_index, ftr_px, ftr_f, ftr_level,
+                            ftr_type, ftr_grad, batch_id, batch_counter, seeds, n_pyr_levels=3):
+    """svo::DepthFilter::updateSeeds of the compiled reference.  status: 0 kept, 1 converged, 2 erased."""
+    imgs = np.ascontiguousarray(np.stack(ref_l0s))
+    h, w = cur_l0.shape
+    M = len(ref_index)
+    out = {k: np.ascontiguousarray(seeds[k], np.float32).copy() for k in ("a", "b", "mu", "z_range", "sigma2")}
+    status = np.zeros(M, np.uint8)
+    xyz = np.zeros((M, 3))
+    i32 = lambda a: np.ascontiguousarray(a, np.int32)
+    ref_lib().ref_depth_filter_update(_p(imgs), _p(c64(np.asarray(ref_T_f_w)).reshape(-1)), len(ref_l0s),
+                                      _p(np.ascontiguousarray(cur_l0)), _p(c64(cur_T_f_w).reshape(12)), w, h, n_levels,
+                                      _p(_cam4(cam)), M, _p(i32(ref_index)), _p(c64(ftr_px)), _p(c64(ftr_f)),
+                                      _p(i32(ftr_level)), _p(i32(ftr_type)), _p(c64(ftr_grad)), _p(i32(batch_id)),
+                                      batch_counter, n_pyr_levels, _p(out["a"]), _p(out["b"]), _p(out["mu"]),
+                                      _p(out["z_range"]), _p(out["sigma2"]), _p(status), _p(xyz))
+    out.update(status=status, xyz_world=xyz)
+    return out
+
+
+class RefStream:
+    """B frame pairs (frame k, frame k+1) held by the compiled reference; run() times svo::SparseImgAlign::run alone."""
+
+    def __init__(self, level0s, cam, n_levels, T_f_w, feat_offset, px, f, pos, has_point):
+        L = ref_lib()
+        L.ref_stream_create.restype = C.c_void_p
+        L.ref_stream_run.restype = C.c_double
+        imgs = self._imgs = np.ascontiguousarray(level0s, np.uint8)  # level 0 of the frames aliases this memory
+        self.B = imgs.shape[0] - 1
+        h, w = imgs.shape[1:]
+        self._h = C.c_void_p(L.ref_stream_create(_p(imgs), self.B, w, h, n_levels, _p(_cam4(cam)),
+                                                 _p(c64(np.asarray(T_f_w)).reshape(-1)),
+                                                 _p(np.ascontiguousarray(feat_offset, np.int32)), _p(c64(px)), _p(c64(f)),
+                                                 _p(c64(pos)), _p(np.ascontiguousarray(has_point, np.uint8))))
+
+    def run(self, n_threads, max_level, min_level, n_iter=30, want_poses=False):
+        T = np.zeros((self.B, 3, 4)) if want_poses else None
+        nt = np.zeros(self.B, np.int64)
+        sec = ref_lib().ref_stream_run(self._h, int(n_threads), max_level, min_level, n_iter, _p(T) if want_poses else None,
+                                       _p(nt))
+        return dict(seconds=sec, T=T, n_tracked=nt)
+
+    def destroy(self):
+        if self._h:
+            ref_lib().ref_stream_destroy(self._h)
+            self._h = None

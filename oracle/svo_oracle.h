@@ -5,11 +5,14 @@
  * and bench.py's cpu_baseline / --impl reference legs may load this library.  The product
  * (rpg_svo_b200/, include/svo_b200.h) never links, imports or calls it.
  *
- * PARITY UNPINNED: the reference cannot be built in this container (Eigen, OpenCV, Sophus,
- * rpg_vikit, Boost are absent and un-vendored) and its own tests are print-only programs that
- * need an external dataset, so no golden vector of the reference pins these functions.  What can
- * be pinned is pinned in tests/: closed-form identities, independent numpy/scipy re-derivations,
- * and the sanity band of svo/test/test_feature_alignment.cpp.
+ * PINNING: everything that lives in the reference tree is pinned by executing it -- oracle/_ref is the
+ * reference's own svo/src/*.cpp of this path compiled where they lie (oracle/Makefile target `ref`,
+ * oracle/ref_wrap.cpp) and tests/test_oracle_pins.py compares every function below with it.
+ * PARITY UNPINNED at the third-party boundary: Eigen, OpenCV, Sophus, rpg_vikit, Boost are absent and
+ * un-vendored, so oracle/_ref is built against stand-in headers (oracle/shim/) and the arithmetic inside
+ * those libraries ([EXT] in the sources) is restated from their published algorithms, here and in the
+ * stand-ins alike; the reference's own tests are print-only programs on an external dataset, so no
+ * golden vector of the reference exists for those pieces.
  *
  * All SE3 arguments are row-major 3x4 [R|t] doubles; images are 8-bit, row pitch == cols
  * (the reference indexes with `cols` as stride: svo/src/sparse_img_align.cpp:88,165).

@@ -205,3 +205,168 @@ def test_oracle_align_equals_reference_source_compiled_here(oracle):
             ok_o, px_o, h_o = oracle.align1d(img, c["dir"][i], c["pwb"][i], c["patch"][i], n_iter, c["px_start"][i])
             ok_r, px_r, h_r = oracle.ref_align1d(img, c["dir"][i], c["pwb"][i], c["patch"][i], n_iter, c["px_start"][i])
             assert ok_o == ok_r and np.array_equal(px_o, px_r) and h_o == h_r, ("align1D", i, n_iter)
+
+
+# ---- oracle/_ref: the reference's own classes compiled from /root/reference/svo/src (stand-in third-party headers) ----
+def _need_ref(oracle):
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not built (needs /root/reference)")
+
+
+@pytest.mark.parametrize("seed,levels", [(11, (4, 2)), (12, (4, 0)), (13, (2, 1))])
+def test_oracle_sparse_img_align_equals_reference_source_compiled_here(oracle, seed, levels):
+    """svo::SparseImgAlign::run of the compiled reference (sparse_img_align.cpp + frame.cpp + config.cpp, driven by
+    the stand-in vk::NLLSSolver) vs the oracle's restatement: same visibility, same reference patches bit for bit,
+    same final pose."""
+    _need_ref(oracle)
+    p = synth.make_frame_pair(seed, n_feat=200)
+    p["has_point"][::17] = 0
+    r = oracle.ref_sparse_img_align(p["ref_pyr"][0], p["cur_pyr"][0], p["n_levels"], p["cam"], p["T_ref_w"], p["T_ref_w"],
+                                    p["px"], p["f"], p["pos"], p["has_point"], levels[0], levels[1])
+    o = oracle.sparse_img_align(p["ref_pyr"], p["cur_pyr"], p["cam"], synth.se3_identity(), p["px"], p["f"], p["pos"],
+                                p["has_point"], p["ref_pos"], levels[0], levels[1])
+    T_cur_w = synth.se3_mul(o["T"], p["T_ref_w"])
+    assert r["n_tracked"] == o["n_tracked"]
+    assert np.array_equal(r["visible"], o["visible"])
+    assert np.allclose(r["T_cur_w"], T_cur_w, rtol=0, atol=1e-9)
+    assert np.allclose(r["H"], o["H"], rtol=1e-9, atol=1e-9)
+    # the reference patch cache of the last level (f32 bilinear) matches the oracle's residual-stage patches
+    q = oracle.sparse_residuals(p["ref_pyr"][levels[1]], p["cur_pyr"][levels[1]], levels[1], p["cam"], o["T"], p["px"],
+                                p["f"], p["pos"], p["has_point"], p["ref_pos"])
+    v = r["visible"].astype(bool)
+    assert np.array_equal(r["ref_patch"][v], q["ref_patch"][v])
+
+
+def test_oracle_pose_optimizer_equals_reference_source_compiled_here(oracle):
+    _need_ref(oracle)
+    for seed in (3, 4):
+        c = synth.make_pose_opt_case(seed, n=400)
+        r = oracle.ref_pose_optimize(2.0, 10, c["cam"], c["T_init"], c["f"], c["pos"], c["level"], c["has_point"])
+        o = oracle.pose_optimize(2.0, 10, c["cam"].fx, c["T_init"], c["f"], c["pos"], c["level"], c["has_point"])
+        assert np.array_equal(r["has_point"], o["has_point"])
+        assert r["num_obs"] == o["num_obs"]
+        assert np.allclose(r["T"], o["T"], rtol=0, atol=1e-10)
+        for k in ("estimated_scale", "error_init", "error_final"):
+            assert np.isclose(r[k], o[k], rtol=1e-9), k
+        assert np.allclose(r["cov"], o["cov"], rtol=1e-6, atol=1e-12)
+
+
+def test_oracle_point_optimize_equals_reference_source_compiled_here(oracle):
+    _need_ref(oracle)
+    rng = np.random.default_rng(5)
+    for _ in range(20):
+        pos = np.array([rng.uniform(-1, 1), rng.uniform(-1, 1), rng.uniform(3, 6)])
+        Ts, fs = [], []
+        for _ in range(int(rng.integers(2, 7))):
+            T = synth.se3_exp(np.concatenate([rng.uniform(-0.5, 0.5, 3), rng.uniform(-0.05, 0.05, 3)]))
+            pc = T[:, :3] @ pos + T[:, 3]
+            f = pc / np.linalg.norm(pc) + rng.normal(0, 1e-3, 3)
+            Ts.append(T.reshape(12)); fs.append(f / np.linalg.norm(f))
+        start = pos + rng.normal(0, 0.05, 3)
+        for n_iter, tol in ((1, 1e-13), (3, 1e-13), (5, 1e-8)):
+            # at convergence "new_chi2 > chi2" (point.cpp:152) compares rounding noise, so the roll-back of the last
+            # ~1e-9 step can differ between two compilations of the same source; before that the runs agree to the ulp
+            a = oracle.ref_point_optimize(n_iter, start, np.array(Ts), np.array(fs))
+            b = oracle.point_optimize(n_iter, start, np.array(Ts), np.array(fs))
+            assert np.allclose(a, b, rtol=0, atol=tol), (n_iter, a - b)
+
+
+def test_oracle_matcher_equals_reference_source_compiled_here(oracle):
+    """svo::Matcher::findMatchDirect (matcher.cpp:142-186: warp matrix, search level, warped patch, align1D/2D) of the
+    compiled reference vs the oracle."""
+    _need_ref(oracle)
+    c = synth.make_match_case(21, 120)
+    T_cur_ref = synth.se3_mul(c["T_cur_w"], synth.se3_inv(c["T_ref_w"]))
+    ref_pos = synth.se3_inv(c["T_ref_w"])[:, 3]
+    n_ok = 0
+    for i in range(c["M"]):
+        r = oracle.ref_matcher(0, c["ref_pyr"][0], c["cur_pyr"][0], c["n_levels"], c["cam"], c["T_ref_w"], c["T_cur_w"],
+                               c["ref_px"][i], c["ref_f"][i], int(c["ref_level"][i]), int(c["ftr_type"][i]), c["ref_grad"][i],
+                               c["point_pos"][i], px_cur=c["px_cur"][i], n_pyr_levels=3)
+        depth = np.linalg.norm(c["point_pos"][i] - ref_pos)
+        o = oracle.find_match_direct(c["ref_pyr"], c["cur_pyr"], c["cam"], T_cur_ref, c["ref_px"][i], c["ref_f"][i],
+                                     int(c["ref_level"][i]), int(c["ftr_type"][i]), c["ref_grad"][i], depth, 2, 10,
+                                     c["px_cur"][i])
+        assert r["success"] == o["success"], i
+        assert r["search_level"] == o["search_level"], i
+        assert np.allclose(r["A_cur_ref"], o["A_cur_ref"], rtol=1e-9, atol=1e-12), i
+        if r["success"]:
+            n_ok += 1
+            assert np.allclose(r["px_cur"], o["px_cur"], rtol=0, atol=1e-9), i
+    assert n_ok > c["M"] // 2
+
+
+def test_oracle_epipolar_matcher_equals_reference_source_compiled_here(oracle):
+    """svo::Matcher::findEpipolarMatchDirect (matcher.cpp:188-330) of the compiled reference vs the oracle."""
+    _need_ref(oracle)
+    c = synth.make_depth_case(22, n_seeds=150)
+    T_cur_ref = synth.se3_mul(c["T_cur_w"], synth.se3_inv(c["T_ref_w"]))
+    n_ok = 0
+    for i in range(c["M"]):
+        mu, sig = 0.5, np.sqrt(float(c["seeds"]["sigma2"][i]))
+        d_est, d_min, d_max = 1.0 / mu, 1.0 / (mu + sig), 1.0 / max(mu - sig, 1e-7)
+        pos = synth.se3_inv(c["T_ref_w"])[:, :3] @ (c["ftr_f"][i] * d_est) + synth.se3_inv(c["T_ref_w"])[:, 3]
+        r = oracle.ref_matcher(1, c["ref_pyr"][0], c["cur_pyr"][0], c["n_levels"], c["cam"], c["T_ref_w"], c["T_cur_w"],
+                               c["ftr_px"][i], c["ftr_f"][i], int(c["ftr_level"][i]), int(c["ftr_type"][i]), c["ftr_grad"][i],
+                               pos, d_est=d_est, d_min=d_min, d_max=d_max, n_pyr_levels=3)
+        o = oracle.find_epipolar_match_direct(c["ref_pyr"], c["cur_pyr"], c["cam"], T_cur_ref, c["ftr_px"][i], c["ftr_f"][i],
+                                              int(c["ftr_level"][i]), int(c["ftr_type"][i]), c["ftr_grad"][i], d_est, d_min,
+                                              d_max, 2)
+        assert r["success"] == o["success"], i
+        assert r["reject"] == o["reject"], i
+        if r["success"]:
+            n_ok += 1
+            assert r["search_level"] == o["search_level"], i
+            assert np.allclose(r["px_cur"], o["px_cur"], rtol=0, atol=1e-9), i
+            assert np.isclose(r["depth"], o["depth"], rtol=1e-9), i
+            assert np.isclose(r["epi_length"], o["epi_length"], rtol=1e-9), i
+    assert n_ok > c["M"] // 4
+
+
+def test_oracle_update_seed_equals_reference_source_compiled_here(oracle):
+    """DepthFilter::updateSeed / computeTau (depth_filter.cpp:309-357) as GCC compiles the reference source (default
+    -ffp-contract=fast with FMA) vs the oracle's explicit-fma restatement: every f32 field bit for bit."""
+    _need_ref(oracle)
+    rng = np.random.default_rng(9)
+    for _ in range(3000):
+        a, b = np.float32(rng.uniform(1, 40)), np.float32(rng.uniform(1, 40))
+        mu, zr = np.float32(rng.uniform(0.05, 2.0)), np.float32(rng.uniform(0.5, 4.0))
+        s2 = np.float32(rng.uniform(1e-5, 1.0))
+        x, tau2 = np.float32(mu + rng.normal(0, 0.3)), np.float32(10 ** rng.uniform(-7, -1))
+        r = oracle.ref_update_seed(x, tau2, a, b, mu, zr, s2)
+        o = oracle.update_seed(x, tau2, a, b, mu, zr, s2)
+        assert np.array_equal(r.view(np.uint32), o.view(np.uint32)), (r, o)
+    for _ in range(500):
+        T = synth.se3_exp(np.concatenate([rng.uniform(-0.5, 0.5, 3), rng.uniform(-0.1, 0.1, 3)]))
+        f = rng.normal(size=3) * [0.3, 0.3, 0] + [0, 0, 1]
+        f /= np.linalg.norm(f)
+        z = rng.uniform(0.5, 10)
+        # norms / dot products run inside the (stand-in) Eigen, whose summation order is [EXT]: equal to rounding
+        assert np.isclose(oracle.ref_compute_tau(T, f, z, 0.002), oracle.compute_tau(T, f, z, 0.002), rtol=1e-10, atol=0)
+
+
+def test_oracle_depth_filter_equals_reference_source_compiled_here(oracle):
+    """svo::DepthFilter::updateSeeds of the compiled reference (depth_filter.cpp + matcher.cpp + feature_alignment.cpp)
+    vs the oracle: same erase/converge/keep decision per seed and the same seed state bit for bit."""
+    _need_ref(oracle)
+    c = synth.make_depth_case(31, n_seeds=400)
+    c["seeds"]["sigma2"][::5] *= np.float32(1e-3)   # some seeds close to convergence
+    c["seeds"]["mu"][::5] = (1.0 / c["depth_gt"][::5]).astype(np.float32)
+    r = oracle.ref_depth_filter_update([c["ref_pyr"][0]], [c["T_ref_w"]], c["cur_pyr"][0], c["T_cur_w"], c["n_levels"], c["cam"],
+                                       c["ref_index"], c["ftr_px"], c["ftr_f"], c["ftr_level"], c["ftr_type"], c["ftr_grad"],
+                                       c["batch_id"], c["batch_counter"], c["seeds"])
+    o = oracle.depth_filter_update([c["ref_pyr"]], [c["T_ref_w"]], c["cur_pyr"], c["T_cur_w"], c["cam"], c["ref_index"],
+                                   c["ftr_px"], c["ftr_f"], c["ftr_level"], c["ftr_type"], c["ftr_grad"], c["batch_id"],
+                                   c["batch_counter"], c["seeds"])
+    st = o["status"]
+    expect = np.where(st == 6, 1, np.where((st == 1) | (st == 7), 2, 0))
+    assert np.array_equal(r["status"], expect)
+    assert (st == 6).sum() > 5 and (st == 5).sum() > 50 and (st == 4).sum() > 0 and (st == 1).sum() > 0
+    keep = expect == 0
+    for k in ("a", "b", "mu", "z_range", "sigma2"):
+        assert np.array_equal(r[k][keep].view(np.uint32), o[k][keep].view(np.uint32)), k
+    conv = expect == 1
+    assert np.array_equal(r["sigma2"][conv].view(np.uint32), o["sigma2"][conv].view(np.uint32))
+    Tinv = synth.se3_inv(c["T_ref_w"])
+    xyz = (c["ftr_f"][conv] / o["mu"][conv][:, None].astype(np.float64)) @ Tinv[:, :3].T + Tinv[:, 3]
+    assert np.allclose(r["xyz_world"][conv], xyz, rtol=1e-12, atol=1e-12)
