@@ -6,7 +6,7 @@
  * (rpg_svo_b200/, include/svo_b200.h) never links, imports or calls it.
  *
  * PINNING: everything that lives in the reference tree is pinned by executing it -- oracle/_ref is the
- * reference's own svo/src/*.cpp of this path compiled where they lie (oracle/Makefile target `ref`,
+ * reference's own svo/src .cpp files of this path compiled where they lie (oracle/Makefile target `ref`,
  * oracle/ref_wrap.cpp) and tests/test_oracle_pins.py compares every function below with it.
  * PARITY UNPINNED at the third-party boundary: Eigen, OpenCV, Sophus, rpg_vikit, Boost are absent and
  * un-vendored, so oracle/_ref is built against stand-in headers (oracle/shim/) and the arithmetic inside
