@@ -7,6 +7,7 @@
  *   svo_b200_sparse_residuals       <- SparseImgAlign::computeResiduals       svo/src/sparse_img_align.cpp:147-243
  *   svo_b200_align2d_batch/_1d      <- feature_alignment::align2D / align1D   svo/include/svo/feature_alignment.h:29-44
  *   svo_b200_find_match_direct      <- Matcher::findMatchDirect               svo/include/svo/matcher.h:109-112
+ *   svo_b200_reproject_map          <- Reprojector::reprojectMap              svo/include/svo/reprojector.h:58-62, svo/src/reprojector.cpp:64-217
  *   svo_b200_pose_optimize          <- pose_optimizer::optimizeGaussNewton    svo/include/svo/pose_optimizer.h:37-45
  *   svo_b200_point_optimize_batch   <- Point::optimize                        svo/include/svo/point.h:86, svo/src/point.cpp:119-177
  *   svo_b200_depth_filter_update    <- DepthFilter::updateSeeds               svo/include/svo/depth_filter.h:155
@@ -199,6 +200,67 @@ int svo_b200_pose_optimize(svo_b200_ctx* ctx, double reproj_thresh, int n_iter,
 int svo_b200_point_optimize_batch(svo_b200_ctx* ctx, int P, int n_iter, const int* obs_offset,
                                   const int* obs_frame, const double* obs_f, const double* frame_T_f_w,
                                   int n_frames, double* pos_io);
+
+/* ------------------------------------------------------------------ reprojector ("next" row f2) -------- */
+/* Flat, read-only view of the map's pointer graph (Map::keyframes_, Frame::fts_, Feature, Point::obs_,
+ * MapPointCandidates::candidates_), gathered by the host wrapper (rpg_svo_b200/host/svo_host.h: svo::Reprojector). */
+typedef struct svo_b200_map_view {
+  int n_kfs;                     /* Map::keyframes_ in list order (map.h:74) */
+  const double* kf_T_f_w;        /* n_kfs*12 */
+  const double* kf_keypt_pos;    /* n_kfs*5*3: key_pts_[i]->point->pos_ (frame.h:53) */
+  const uint8_t* kf_keypt_valid; /* n_kfs*5: key_pts_[i] != NULL */
+  const int* kf_fts_offset;      /* n_kfs+1: Frame::fts_ of keyframe k = kf_fts[offset[k] .. offset[k+1]) */
+  const int* kf_fts;             /* indices into the feature table, fts_ list order */
+  int n_ftrs;                    /* feature table: every Feature a Frame::fts_ or Point::obs_ entry refers to */
+  const int* ftr_kf;             /* Feature::frame as keyframe index */
+  const double* ftr_px;          /* n_ftrs*2 */
+  const double* ftr_f;           /* n_ftrs*3 */
+  const int* ftr_level;
+  const int* ftr_type;           /* 0 CORNER, 1 EDGELET (feature.h:29-32) */
+  const double* ftr_grad;        /* n_ftrs*2 */
+  const int* ftr_point;          /* Feature::point as point index, -1 = NULL */
+  int n_points;
+  const double* pt_pos;          /* n_points*3 */
+  const int* pt_obs_offset;      /* n_points+1 */
+  const int* pt_obs;             /* Point::obs_ in list order, as feature-table indices */
+  int n_candidates;
+  const int* cand_point;         /* MapPointCandidates::candidates_ in list order, as point indices (map.h:44) */
+} svo_b200_map_view;
+typedef struct svo_b200_reproject_options {
+  int grid_size;         /* Config::gridSize()  (config.cpp:32: 30) */
+  int max_fts;           /* Config::maxFts()    (config.cpp:52: 120) */
+  int max_n_kfs;         /* Reprojector::Options::max_n_kfs (reprojector.h:44: 10) */
+  int find_match_direct; /* Reprojector::Options::find_match_direct (reprojector.h:45: true) */
+  int max_search_level;  /* Config::nPyrLevels()-1 (matcher.cpp:153) */
+  int align_max_iter;    /* Matcher::Options::align_max_iter (matcher.h:77: 10) */
+} svo_b200_reproject_options;
+typedef struct svo_b200_reproject_stats {
+  int64_t n_matches, n_trials; /* Reprojector::n_matches_, n_trials_ (reprojector.h:51-52) */
+  int n_new;                   /* features added to the frame */
+  int n_overlap;               /* overlap_kfs.size() */
+  int n_projected;             /* points that fell into a grid cell */
+  int n_speculative;           /* matches computed on the device (>= n_trials: every in-frame point is aligned) */
+} svo_b200_reproject_stats;
+#define SVO_B200_PT_NONE 0
+#define SVO_B200_PT_SAFE_DELETE 1      /* caller must run map_.safeDeletePoint(pt)               (reprojector.cpp:173-174) */
+#define SVO_B200_PT_DELETE_CANDIDATE 2 /* caller must run point_candidates_.deleteCandidatePoint (reprojector.cpp:175-176) */
+#define SVO_B200_PT_CANDIDATE_ERASED 3 /* candidate erased while projecting: deleteCandidate+erase (reprojector.cpp:117-122) */
+/* Reprojector::reprojectMap.  The device projects every map point of the closest keyframes and every candidate into
+ * `cur`, and aligns ALL in-frame points speculatively in one launch (getCloseViewObs + findMatchDirect per warp); the
+ * host then replays the reference's one-match-per-cell policy over those results in `cell_order`
+ * (Reprojector::Grid::cell_order, shuffled once by the caller as initializeGrid does), applying the reference's side
+ * effects only to the candidates the sequential code would have reached.
+ *   kf_frames: n_kfs uploaded keyframe pyramids.  Point types: 0 DELETED, 1 CANDIDATE, 2 UNKNOWN, 3 GOOD (point.h:40-45).
+ *   pt_*_io: Point::type_, n_failed_reproj_, n_succeeded_reproj_ per point, updated in place; pt_action_out: SVO_B200_PT_*.
+ *   overlap_kf_out / overlap_count_out: max_n_kfs entries (overlap_kfs of the reference, keyframe index + count).
+ *   new_*: the Features the reference would add to the frame, in order (max_fts+1 entries): point index, px, level,
+ *   type, grad. */
+int svo_b200_reproject_map(svo_b200_ctx* ctx, const svo_b200_map_view* map, const svo_b200_frame* const* kf_frames,
+                           const svo_b200_frame* cur, const double* cur_T_f_w, const svo_b200_camera* cam,
+                           const svo_b200_reproject_options* opt, const int* cell_order, int* pt_type_io,
+                           int* pt_n_failed_io, int* pt_n_succeeded_io, uint8_t* pt_action_out, int* overlap_kf_out,
+                           int64_t* overlap_count_out, int* new_point_out, double* new_px_out, int* new_level_out,
+                           int* new_type_out, double* new_grad_out, svo_b200_reproject_stats* stats);
 
 /* ------------------------------------------------------------------ depth filter -------- */
 #define SVO_B200_SEED_TOO_OLD 1

@@ -27,7 +27,7 @@ def build_ref() -> str | None:
 
 
 def build(force: bool = False) -> str:
-    srcs = ["svo_oracle.cpp", "svo_oracle_align.inc", "svo_oracle_depth.inc", "svo_oracle_pose.inc",
+    srcs = ["svo_oracle.cpp", "svo_oracle_align.inc", "svo_oracle_depth.inc", "svo_oracle_pose.inc", "svo_oracle_reproject.inc",
             "oracle_math.h", "svo_oracle.h", "Makefile"]
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(os.path.join(_HERE, s)) > os.path.getmtime(_LIB_PATH) for s in srcs)
@@ -510,3 +510,101 @@ class RefStream:
         if self._h:
             ref_lib().ref_stream_destroy(self._h)
             self._h = None
+
+
+# ---- Reprojector::reprojectMap on a flat map view ----
+class MapView(C.Structure):
+    _fields_ = [("n_kfs", C.c_int), ("kf_T_f_w", C.c_void_p), ("kf_keypt_pos", C.c_void_p), ("kf_keypt_valid", C.c_void_p),
+                ("kf_fts_offset", C.c_void_p), ("kf_fts", C.c_void_p), ("n_ftrs", C.c_int), ("ftr_kf", C.c_void_p),
+                ("ftr_px", C.c_void_p), ("ftr_f", C.c_void_p), ("ftr_level", C.c_void_p), ("ftr_type", C.c_void_p),
+                ("ftr_grad", C.c_void_p), ("ftr_point", C.c_void_p), ("n_points", C.c_int), ("pt_pos", C.c_void_p),
+                ("pt_obs_offset", C.c_void_p), ("pt_obs", C.c_void_p), ("n_candidates", C.c_int), ("cand_point", C.c_void_p)]
+
+
+class ReprojectOptions(C.Structure):
+    _fields_ = [("grid_size", C.c_int), ("max_fts", C.c_int), ("max_n_kfs", C.c_int), ("find_match_direct", C.c_int),
+                ("max_search_level", C.c_int), ("align_max_iter", C.c_int)]
+
+
+class ReprojectStats(C.Structure):
+    _fields_ = [("n_matches", C.c_int64), ("n_trials", C.c_int64), ("n_new", C.c_int), ("n_overlap", C.c_int),
+                ("n_projected", C.c_int), ("n_speculative", C.c_int)]
+
+
+_MV_DTYPES = dict(kf_T_f_w=np.float64, kf_keypt_pos=np.float64, kf_keypt_valid=np.uint8, kf_fts_offset=np.int32,
+                  kf_fts=np.int32, ftr_kf=np.int32, ftr_px=np.float64, ftr_f=np.float64, ftr_level=np.int32,
+                  ftr_type=np.int32, ftr_grad=np.float64, ftr_point=np.int32, pt_pos=np.float64, pt_obs_offset=np.int32,
+                  pt_obs=np.int32, cand_point=np.int32)
+
+
+def pack_map_view(view, struct_cls=MapView):
+    """dict of arrays -> (ctypes struct, keep-alive list)."""
+    mv, keep = struct_cls(), []
+    for k, v in view.items():
+        if k in _MV_DTYPES:
+            a = np.ascontiguousarray(v, _MV_DTYPES[k])
+            keep.append(a)
+            setattr(mv, k, a.ctypes.data)
+        else:
+            setattr(mv, k, int(v))
+    return mv, keep
+
+
+def reproject_outputs(view, options, pt_type, pt_n_failed, pt_n_succeeded):
+    P, cap = int(view["n_points"]), int(options["max_fts"]) + 1
+    return dict(pt_type=np.ascontiguousarray(pt_type, np.int32).copy(), pt_n_failed=np.ascontiguousarray(pt_n_failed, np.int32).copy(),
+                pt_n_succeeded=np.ascontiguousarray(pt_n_succeeded, np.int32).copy(), pt_action=np.zeros(P, np.uint8),
+                overlap_kf=np.full(int(options["max_n_kfs"]), -1, np.int32), overlap_count=np.zeros(int(options["max_n_kfs"]), np.int64),
+                new_point=np.full(cap, -1, np.int32), new_px=np.zeros((cap, 2)), new_level=np.zeros(cap, np.int32),
+                new_type=np.zeros(cap, np.int32), new_grad=np.zeros((cap, 2)))
+
+
+def trim_reproject(o, st):
+    n, k = st.n_new, st.n_overlap
+    for key in ("new_point", "new_px", "new_level", "new_type", "new_grad"):
+        o[key] = o[key][:n]
+    o["overlap_kf"], o["overlap_count"] = o["overlap_kf"][:k], o["overlap_count"][:k]
+    o.update(n_matches=st.n_matches, n_trials=st.n_trials, n_new=n, n_overlap=k, n_projected=st.n_projected,
+             n_speculative=st.n_speculative)
+    return o
+
+
+def reproject_map(case):
+    """Reprojector::reprojectMap restated (sequential cell policy)."""
+    v = case["view"]
+    mv, keep = pack_map_view(v)
+    nl = case["n_levels"]
+    flat = (C.c_void_p * (v["n_kfs"] * nl))()
+    for k, pyr in enumerate(case["kf_pyr"]):
+        for l, im in enumerate(pyr):
+            flat[k * nl + l] = im.ctypes.data
+    cp, cols, rows = _level_ptrs(case["cur_pyr"])
+    opt = ReprojectOptions(**case["options"])
+    o = reproject_outputs(v, case["options"], case["pt_type"], case["pt_n_failed"], case["pt_n_succeeded"])
+    st = ReprojectStats()
+    cs = cam_struct(case["cam"])
+    co = np.ascontiguousarray(case["cell_order"], np.int32)
+    lib().orc_reproject_map(C.byref(mv), flat, cp, _p(cols), _p(rows), nl, C.byref(cs), _p(c64(case["cur_T_f_w"]).reshape(12)),
+                            C.byref(opt), _p(co), _p(o["pt_type"]), _p(o["pt_n_failed"]), _p(o["pt_n_succeeded"]),
+                            _p(o["pt_action"]), _p(o["overlap_kf"]), _p(o["overlap_count"]), _p(o["new_point"]), _p(o["new_px"]),
+                            _p(o["new_level"]), _p(o["new_type"]), _p(o["new_grad"]), C.byref(st))
+    return trim_reproject(o, st)
+
+
+def ref_reproject_map(case):
+    """svo::Reprojector::reprojectMap of the compiled reference (oracle/_ref) on the same flat map view."""
+    v = case["view"]
+    mv, keep = pack_map_view(v)
+    kf_l0 = np.ascontiguousarray(np.stack([pyr[0] for pyr in case["kf_pyr"]]))
+    cur_l0 = np.ascontiguousarray(case["cur_pyr"][0])
+    h, w = cur_l0.shape
+    opt = ReprojectOptions(**case["options"])
+    o = reproject_outputs(v, case["options"], case["pt_type"], case["pt_n_failed"], case["pt_n_succeeded"])
+    st = ReprojectStats()
+    co = np.ascontiguousarray(case["cell_order"], np.int32)
+    ref_lib().ref_reproject_map(C.byref(mv), _p(kf_l0), _p(cur_l0), w, h, case["n_levels"], _p(_cam4(case["cam"])),
+                                _p(c64(case["cur_T_f_w"]).reshape(12)), C.byref(opt), _p(co), _p(o["pt_type"]),
+                                _p(o["pt_n_failed"]), _p(o["pt_n_succeeded"]), _p(o["pt_action"]), _p(o["overlap_kf"]),
+                                _p(o["overlap_count"]), _p(o["new_point"]), _p(o["new_px"]), _p(o["new_level"]),
+                                _p(o["new_type"]), _p(o["new_grad"]), C.byref(st))
+    return trim_reproject(o, st)

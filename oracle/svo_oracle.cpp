@@ -19,6 +19,7 @@
 #include <thread>
 #include <cmath>
 #include <cstdio>
+#include <list>
 #include <vector>
 
 #include "oracle_math.h"
@@ -521,3 +522,4 @@ void orc_ldlt6_solve(const double* H36, const double* b6, double* x6_out) {
 #include "svo_oracle_align.inc"
 #include "svo_oracle_depth.inc"
 #include "svo_oracle_pose.inc"
+#include "svo_oracle_reproject.inc"

@@ -183,6 +183,59 @@ void orc_pose_optimize(double reproj_thresh, int n_iter, double fx /*errorMultip
 void orc_point_optimize(int n_iter, double* pos_io /*3*/, int n_obs, const double* obs_T_f_w /*n_obs*12*/,
                         const double* obs_f /*n_obs*3*/);
 
+/* ---- Reprojector::reprojectMap (svo/src/reprojector.cpp:64-217) on a flat view of the map ---- */
+typedef struct {
+  int n_kfs;                     /* Map::keyframes_, in list order */
+  const double* kf_T_f_w;        /* n_kfs*12 */
+  const double* kf_keypt_pos;    /* n_kfs*5*3: key_pts_[i]->point->pos_ (frame.h:48) */
+  const uint8_t* kf_keypt_valid; /* n_kfs*5: key_pts_[i] != NULL */
+  const int* kf_fts_offset;      /* n_kfs+1: Frame::fts_ of keyframe k = kf_fts[offset[k]..offset[k+1]) */
+  const int* kf_fts;             /* indices into the feature table */
+  int n_ftrs;                    /* feature table: every Feature some Point::obs_ or Frame::fts_ refers to */
+  const int* ftr_kf;             /* Feature::frame as keyframe index */
+  const double* ftr_px;          /* n_ftrs*2 */
+  const double* ftr_f;           /* n_ftrs*3 */
+  const int* ftr_level;
+  const int* ftr_type;           /* 0 CORNER, 1 EDGELET */
+  const double* ftr_grad;        /* n_ftrs*2 */
+  const int* ftr_point;          /* Feature::point as point index, -1 = NULL */
+  int n_points;
+  const double* pt_pos;          /* n_points*3 */
+  const int* pt_obs_offset;      /* n_points+1 */
+  const int* pt_obs;             /* Point::obs_ in list order, as feature-table indices */
+  int n_candidates;
+  const int* cand_point;         /* MapPointCandidates::candidates_ in list order, as point indices */
+} orc_map_view;
+typedef struct {
+  int grid_size;         /* Config::gridSize() (config.cpp:32: 30) */
+  int max_fts;           /* Config::maxFts() (config.cpp:52: 120) */
+  int max_n_kfs;         /* Reprojector::Options::max_n_kfs (reprojector.h:44: 10) */
+  int find_match_direct; /* Reprojector::Options::find_match_direct (true) */
+  int max_search_level;  /* Config::nPyrLevels()-1 (matcher.cpp:153) */
+  int align_max_iter;    /* Matcher::Options::align_max_iter (10) */
+} orc_reproject_options;
+typedef struct {
+  int64_t n_matches, n_trials; /* Reprojector::n_matches_, n_trials_ */
+  int n_new;                   /* features added to the frame */
+  int n_overlap;               /* keyframes reprojected from (overlap_kfs.size()) */
+  int n_projected;             /* points that fell into a grid cell */
+  int n_speculative;           /* unused by the oracle (it matches only what the cell policy reaches) */
+} orc_reproject_stats;
+enum {
+  ORC_PT_NONE = 0,
+  ORC_PT_SAFE_DELETE = 1,      /* map_.safeDeletePoint(pt)            (reprojector.cpp:173-174) */
+  ORC_PT_DELETE_CANDIDATE = 2, /* point_candidates_.deleteCandidatePoint (reprojector.cpp:175-176) */
+  ORC_PT_CANDIDATE_ERASED = 3  /* candidate erased while projecting   (reprojector.cpp:117-122) */
+};
+/* Point types: 0 DELETED, 1 CANDIDATE, 2 UNKNOWN, 3 GOOD (point.h:40-45).  new_* arrays hold max_fts+1 entries;
+ * overlap_* hold max_n_kfs entries; cell_order has ceil(w/grid)*ceil(h/grid) entries. */
+void orc_reproject_map(const orc_map_view* map, const uint8_t* const* kf_levels /*n_kfs*n_levels*/,
+                       const uint8_t* const* cur_levels, const int* cols, const int* rows, int n_levels,
+                       const orc_camera* cam, const double* cur_T_f_w, const orc_reproject_options* opt,
+                       const int* cell_order, int* pt_type_io, int* pt_n_failed_io, int* pt_n_succeeded_io,
+                       uint8_t* pt_action_out, int* overlap_kf_out, int64_t* overlap_count_out, int* new_point,
+                       double* new_px, int* new_level, int* new_type, double* new_grad, orc_reproject_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

@@ -410,3 +410,67 @@ def _point_optimize_batch(self, n_iter, pos, obs_offset, obs_frame, obs_f, frame
 
 
 Context.point_optimize_batch = _point_optimize_batch
+
+
+# ---- Reprojector::reprojectMap on a flat map view (svo_b200_reproject_map) ----
+class MapView(C.Structure):
+    _fields_ = [("n_kfs", C.c_int), ("kf_T_f_w", C.c_void_p), ("kf_keypt_pos", C.c_void_p), ("kf_keypt_valid", C.c_void_p),
+                ("kf_fts_offset", C.c_void_p), ("kf_fts", C.c_void_p), ("n_ftrs", C.c_int), ("ftr_kf", C.c_void_p),
+                ("ftr_px", C.c_void_p), ("ftr_f", C.c_void_p), ("ftr_level", C.c_void_p), ("ftr_type", C.c_void_p),
+                ("ftr_grad", C.c_void_p), ("ftr_point", C.c_void_p), ("n_points", C.c_int), ("pt_pos", C.c_void_p),
+                ("pt_obs_offset", C.c_void_p), ("pt_obs", C.c_void_p), ("n_candidates", C.c_int), ("cand_point", C.c_void_p)]
+
+
+class ReprojectOptions(C.Structure):
+    _fields_ = [("grid_size", C.c_int), ("max_fts", C.c_int), ("max_n_kfs", C.c_int), ("find_match_direct", C.c_int),
+                ("max_search_level", C.c_int), ("align_max_iter", C.c_int)]
+
+
+class ReprojectStats(C.Structure):
+    _fields_ = [("n_matches", C.c_int64), ("n_trials", C.c_int64), ("n_new", C.c_int), ("n_overlap", C.c_int),
+                ("n_projected", C.c_int), ("n_speculative", C.c_int)]
+
+
+_MV_DTYPES = dict(kf_T_f_w=np.float64, kf_keypt_pos=np.float64, kf_keypt_valid=np.uint8, kf_fts_offset=np.int32,
+                  kf_fts=np.int32, ftr_kf=np.int32, ftr_px=np.float64, ftr_f=np.float64, ftr_level=np.int32,
+                  ftr_type=np.int32, ftr_grad=np.float64, ftr_point=np.int32, pt_pos=np.float64, pt_obs_offset=np.int32,
+                  pt_obs=np.int32, cand_point=np.int32)
+
+
+def _reproject_map(self, view: dict, kf_frames, cur: Frame, cur_T_f_w, cam, options: dict, cell_order, pt_type, pt_n_failed,
+                   pt_n_succeeded):
+    """Reprojector::reprojectMap: `view` holds the svo_b200_map_view arrays by field name.  Returns the features the
+    reference would add to the frame (new_*), the updated point state, per-point actions and the overlap keyframes."""
+    mv, keep = MapView(), []
+    for k, v in view.items():
+        if k in _MV_DTYPES:
+            a = np.ascontiguousarray(v, _MV_DTYPES[k])
+            keep.append(a)
+            setattr(mv, k, a.ctypes.data)
+        else:
+            setattr(mv, k, int(v))
+    opt = ReprojectOptions(**options)
+    P, cap, nk = int(view["n_points"]), int(options["max_fts"]) + 1, int(options["max_n_kfs"])
+    o = dict(pt_type=_i32(pt_type).copy(), pt_n_failed=_i32(pt_n_failed).copy(), pt_n_succeeded=_i32(pt_n_succeeded).copy(),
+             pt_action=np.zeros(P, np.uint8), overlap_kf=np.full(nk, -1, np.int32), overlap_count=np.zeros(nk, np.int64),
+             new_point=np.full(cap, -1, np.int32), new_px=np.zeros((cap, 2)), new_level=np.zeros(cap, np.int32),
+             new_type=np.zeros(cap, np.int32), new_grad=np.zeros((cap, 2)))
+    st = ReprojectStats()
+    fr = _frame_array(kf_frames)
+    cs = cam_struct(cam)
+    co = _i32(cell_order)
+    self._check(self.lib.svo_b200_reproject_map(self.h, C.byref(mv), fr, cur.h, _p(c64(cur_T_f_w).reshape(12)), C.byref(cs),
+                                                C.byref(opt), _p(co), _p(o["pt_type"]), _p(o["pt_n_failed"]),
+                                                _p(o["pt_n_succeeded"]), _p(o["pt_action"]), _p(o["overlap_kf"]),
+                                                _p(o["overlap_count"]), _p(o["new_point"]), _p(o["new_px"]),
+                                                _p(o["new_level"]), _p(o["new_type"]), _p(o["new_grad"]), C.byref(st)))
+    n, k = st.n_new, st.n_overlap
+    for key in ("new_point", "new_px", "new_level", "new_type", "new_grad"):
+        o[key] = o[key][:n]
+    o["overlap_kf"], o["overlap_count"] = o["overlap_kf"][:k], o["overlap_count"][:k]
+    o.update(n_matches=st.n_matches, n_trials=st.n_trials, n_new=n, n_overlap=k, n_projected=st.n_projected,
+             n_speculative=st.n_speculative)
+    return o
+
+
+Context.reproject_map = _reproject_map

@@ -71,48 +71,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) find_match_direct_kernel(
   const int m = blockIdx.x * kWarpsPerCta + warp;
   if (m >= M) return;
   WarpAlignScratch& S = scratch[warp];
-  for (int i = lane; i < 112; i += 32) S.pwb[i] = 0;  // a fresh Matcher's patch_with_border_
-  __syncwarp();
   const int r = in.ref_index[m];
-  const int lvl = in.ref_level[m];
-  const double pxu = in.ref_px[2 * m], pxv = in.ref_px[2 * m + 1];
+  const double ref_px[2] = {in.ref_px[2 * m], in.ref_px[2 * m + 1]};
   const double f_ref[3] = {in.ref_f[3 * m], in.ref_f[3 * m + 1], in.ref_f[3 * m + 2]};
-  int success = 0, search_level = 0;
+  const double grad[2] = {in.ref_grad[2 * m], in.ref_grad[2 * m + 1]};
+  const double pos[3] = {in.point_pos[3 * m], in.point_pos[3 * m + 1], in.point_pos[3 * m + 2]};
+  int search_level = 0;
   double A[4] = {0, 0, 0, 0}, h_inv = 0.0;
   double pu = out.px_cur[2 * m], pv = out.px_cur[2 * m + 1];
-  // isInFrame(px.cast<int>()/(1<<level), halfpatch_size_+2, level)  (:143-145)
-  const int xi = (int)pxu / (1 << lvl), yi = (int)pxv / (1 << lvl);
-  const bool in_frame = xi >= 6 && xi < cam.width / (1 << lvl) - 6 && yi >= 6 && yi < cam.height / (1 << lvl) - 6;
-  if (in_frame) {
-    const Pose T_ref_w = pose_from_rt12(in.ref_T_f_w + 12 * (size_t)r);
-    const Pose T_cur_w = pose_from_rt12(cur_T_f_w);
-    const Pose T_ref_w_inv = pose_inv(T_ref_w);
-    const Pose T_cur_ref = pose_mul(T_cur_w, T_ref_w_inv);
-    // depth = (ref_frame.pos() - pt.pos_).norm()
-    const double dxp = T_ref_w_inv.t[0] - in.point_pos[3 * m], dyp = T_ref_w_inv.t[1] - in.point_pos[3 * m + 1],
-                 dzp = T_ref_w_inv.t[2] - in.point_pos[3 * m + 2];
-    const double depth = sqrt(dxp * dxp + dyp * dyp + dzp * dzp);
-    get_warp_matrix_affine(cam, pxu, pxv, f_ref, depth, T_cur_ref, lvl, A);
-    search_level = best_search_level(A, max_search_level);
-    const FrameDesc& rf = in.ref_frames[r];
-    ImgView ref_img = {rf.lvl[lvl], rf.w[lvl], rf.h[lvl]};
-    warp_warp_affine(A, ref_img, pxu, pxv, lvl, search_level, S);
-    ImgView cur_img = {cur.lvl[search_level], cur.w[search_level], cur.h[search_level]};
-    double su = pu / (double)(1 << search_level), sv = pv / (double)(1 << search_level);
-    bool nan_exit = false, ok;
-    if (in.ftr_type[m] == 1) {  // EDGELET: dir = normalize(A * grad)  (:158-164)
-      const double gx = in.ref_grad[2 * m], gy = in.ref_grad[2 * m + 1];
-      const double dx = A[0] * gx + A[1] * gy, dy = A[2] * gx + A[3] * gy;
-      const double n = sqrt(dx * dx + dy * dy);
-      ok = warp_align1d(cur_img, S, (float)(dx / n), (float)(dy / n), align_max_iter, su, sv, h_inv, &nan_exit);
-    } else {
-      ok = warp_align2d(cur_img, S, align_max_iter, su, sv, &nan_exit);
-    }
-    // px_cur = px_scaled * (1<<search_level_) -- px_scaled keeps its input value on the NaN exit
-    pu = su * (double)(1 << search_level);
-    pv = sv * (double)(1 << search_level);
-    success = ok ? 1 : 0;
-  }
+  const int success = warp_find_match_direct(cur, cam, in.ref_frames[r], pose_from_rt12(in.ref_T_f_w + 12 * (size_t)r),
+                                             pose_from_rt12(cur_T_f_w), ref_px, f_ref, in.ref_level[m], in.ftr_type[m], grad,
+                                             pos, max_search_level, align_max_iter, S, pu, pv, search_level, A, h_inv)
+                          ? 1 : 0;
   if (lane == 0) {
     out.px_cur[2 * m] = pu;
     out.px_cur[2 * m + 1] = pv;

@@ -347,4 +347,46 @@ __device__ inline bool depth_from_triangulation(const Pose& T_search_ref, const 
   return true;
 }
 
+// Matcher::findMatchDirect (matcher.cpp:135-177) for one candidate, after Point::getCloseViewObs picked the reference
+// observation: one warp, S = its scratch slice.  px_cur (pu, pv) is the initial guess in level-0 pixels and receives the
+// refined position; search_level / A / h_inv are the Matcher members the callers read afterwards.
+__device__ inline bool warp_find_match_direct(const FrameDesc& cur, const Cam& cam, const FrameDesc& rf, const Pose& T_ref_w,
+                                              const Pose& T_cur_w, const double* ref_px, const double* f_ref, int lvl,
+                                              int ftr_type, const double* ref_grad, const double* point_pos,
+                                              int max_search_level, int align_max_iter, WarpAlignScratch& S, double& pu,
+                                              double& pv, int& search_level, double* A, double& h_inv) {
+  const int lane = threadIdx.x & 31;
+  for (int i = lane; i < 112; i += 32) S.pwb[i] = 0;  // a fresh Matcher's patch_with_border_
+  __syncwarp();
+  const double pxu = ref_px[0], pxv = ref_px[1];
+  // isInFrame(px.cast<int>()/(1<<level), halfpatch_size_+2, level)  (:143-145)
+  const int xi = (int)pxu / (1 << lvl), yi = (int)pxv / (1 << lvl);
+  const bool in_frame = xi >= 6 && xi < cam.width / (1 << lvl) - 6 && yi >= 6 && yi < cam.height / (1 << lvl) - 6;
+  if (!in_frame) return false;
+  const Pose T_ref_w_inv = pose_inv(T_ref_w);
+  const Pose T_cur_ref = pose_mul(T_cur_w, T_ref_w_inv);
+  // depth = (ref_frame.pos() - pt.pos_).norm()
+  const double dxp = T_ref_w_inv.t[0] - point_pos[0], dyp = T_ref_w_inv.t[1] - point_pos[1], dzp = T_ref_w_inv.t[2] - point_pos[2];
+  const double depth = sqrt(dxp * dxp + dyp * dyp + dzp * dzp);
+  get_warp_matrix_affine(cam, pxu, pxv, f_ref, depth, T_cur_ref, lvl, A);
+  search_level = best_search_level(A, max_search_level);
+  ImgView ref_img = {rf.lvl[lvl], rf.w[lvl], rf.h[lvl]};
+  warp_warp_affine(A, ref_img, pxu, pxv, lvl, search_level, S);
+  ImgView cur_img = {cur.lvl[search_level], cur.w[search_level], cur.h[search_level]};
+  double su = pu / (double)(1 << search_level), sv = pv / (double)(1 << search_level);
+  bool nan_exit = false, ok;
+  if (ftr_type == 1) {  // EDGELET: dir = normalize(A * grad)  (:158-164)
+    const double gx = ref_grad[0], gy = ref_grad[1];
+    const double dx = A[0] * gx + A[1] * gy, dy = A[2] * gx + A[3] * gy;
+    const double n = sqrt(dx * dx + dy * dy);
+    ok = warp_align1d(cur_img, S, (float)(dx / n), (float)(dy / n), align_max_iter, su, sv, h_inv, &nan_exit);
+  } else {
+    ok = warp_align2d(cur_img, S, align_max_iter, su, sv, &nan_exit);
+  }
+  // px_cur = px_scaled * (1<<search_level_) -- px_scaled keeps its input value on the NaN exit
+  pu = su * (double)(1 << search_level);
+  pv = sv * (double)(1 << search_level);
+  return ok;
+}
+
 }  // namespace svo

@@ -27,6 +27,7 @@
 #include <cstring>
 #include <functional>
 #include <list>
+#include <map>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -94,9 +95,17 @@ class Context {
 };
 
 class Frame;
+struct Feature;
 struct Point {  // svo/include/svo/point.h:35-106 (the fields the hot path reads)
+  enum PointType { TYPE_DELETED, TYPE_CANDIDATE, TYPE_UNKNOWN, TYPE_GOOD };  // point.h:40-45
   Vector3d pos_;
+  std::list<Feature*> obs_;        // references to keyframes which observe the point (point.h:52)
+  PointType type_ = TYPE_UNKNOWN;  // point.h:58
+  int n_failed_reproj_ = 0;        // point.h:59
+  int n_succeeded_reproj_ = 0;     // point.h:60
   explicit Point(const Vector3d& pos) : pos_(pos) {}
+  Point(const Vector3d& pos, Feature* ftr) : pos_(pos) { obs_.push_front(ftr); }  // point.cpp:38-50
+  void addFrameRef(Feature* ftr) { obs_.push_front(ftr); }                        // point.cpp:55-59
 };
 
 struct Feature {  // svo/include/svo/feature.h:25-71
@@ -122,6 +131,7 @@ class Frame {
   SE3 T_f_w_;
   Matrix6d Cov_{};
   Features fts_;
+  std::vector<Feature*> key_pts_ = std::vector<Feature*>(5, nullptr);  // frame.h:53 (maintained by the caller: setKeyPoints)
   bool is_keyframe_ = false;
   Frame(Context& ctx, PinholeCamera* cam, const uint8_t* img, int n_levels, double /*timestamp*/) : cam_(cam), ctx_(ctx) {
     if (!img) throw std::runtime_error("Frame: provided image is empty");  // frame.cpp:51-52
@@ -369,6 +379,176 @@ class DepthFilter {
   callback_t seed_converged_cb_;
   std::list<Seed> seeds_;
   std::list<FramePtr> keyframes_;
+};
+
+// ------------------------------------------------------------------------------------------------
+// svo::Map / MapPointCandidates (svo/include/svo/map.h:32-129): the parts Reprojector::reprojectMap touches.
+// ------------------------------------------------------------------------------------------------
+class MapPointCandidates {
+ public:
+  typedef std::pair<Point*, Feature*> PointCandidate;
+  std::list<PointCandidate> candidates_;
+  std::list<Point*> trash_points_;
+  ~MapPointCandidates() { reset(); }
+  void newCandidatePoint(Point* point, double /*depth_sigma2*/) {  // map.cpp:213-218
+    point->type_ = Point::TYPE_CANDIDATE;
+    candidates_.push_back(PointCandidate(point, point->obs_.front()));
+  }
+  void deleteCandidate(PointCandidate& c) {  // map.cpp:280-287
+    delete c.second; c.second = nullptr;
+    c.first->type_ = Point::TYPE_DELETED;
+    trash_points_.push_back(c.first);
+  }
+  bool deleteCandidatePoint(Point* point) {  // map.cpp:239-252
+    for (auto it = candidates_.begin(); it != candidates_.end(); ++it)
+      if (it->first == point) { deleteCandidate(*it); candidates_.erase(it); return true; }
+    return false;
+  }
+  void emptyTrash() { for (Point* p : trash_points_) delete p; trash_points_.clear(); }
+  void reset() { for (auto& c : candidates_) { delete c.first; delete c.second; } candidates_.clear(); }
+};
+
+class Map {
+ public:
+  std::list<FramePtr> keyframes_;
+  std::list<Point*> trash_points_;
+  MapPointCandidates point_candidates_;
+  void addKeyframe(FramePtr kf) { keyframes_.push_back(kf); }
+  void safeDeletePoint(Point* pt) {  // map.cpp:82-99
+    for (Feature* ftr : pt->obs_) {
+      ftr->point = nullptr;
+      for (Feature*& k : ftr->frame->key_pts_) if (k == ftr) k = nullptr;  // Frame::removeKeyPoint without re-selection
+    }
+    pt->obs_.clear();
+    pt->type_ = Point::TYPE_DELETED;
+    trash_points_.push_back(pt);
+  }
+  void emptyTrash() { for (Point* p : trash_points_) delete p; trash_points_.clear(); point_candidates_.emptyTrash(); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// svo::Reprojector (svo/include/svo/reprojector.h:37-99): reprojectMap gathers the pointer graph into a flat
+// svo_b200_map_view, makes ONE device call (projection + speculative alignment of every in-frame point), and applies
+// the results the C ABI replayed in the reference's cell order: new Features on the frame, point counters / types,
+// safeDeletePoint / deleteCandidatePoint.
+// ------------------------------------------------------------------------------------------------
+struct ReprojectorOptions {
+  size_t max_n_kfs = 10;          // reprojector.h:44
+  bool find_match_direct = true;  // reprojector.h:45
+  int grid_size = 30, max_fts = 120, n_pyr_levels = 3;  // Config::gridSize(), maxFts(), nPyrLevels()
+};
+class Reprojector {
+ public:
+  typedef ReprojectorOptions Options;
+  Options options_;
+  size_t n_matches_ = 0, n_trials_ = 0;
+
+  Reprojector(PinholeCamera* cam, Map& map, Options opt = Options(), unsigned shuffle_seed = 1) : options_(opt), map_(map) {
+    // initializeGrid (reprojector.cpp:47-58); the reference shuffles with rand(), here a seeded LCG Fisher-Yates
+    const int cols = (cam->width_ + options_.grid_size - 1) / options_.grid_size, rows = (cam->height_ + options_.grid_size - 1) / options_.grid_size;
+    cell_order_.resize((size_t)cols * rows);
+    for (size_t i = 0; i < cell_order_.size(); ++i) cell_order_[i] = (int)i;
+    uint64_t s = shuffle_seed;
+    for (size_t i = cell_order_.size(); i > 1; --i) {
+      s = s * 6364136223846793005ULL + 1442695040888963407ULL;
+      std::swap(cell_order_[i - 1], cell_order_[(size_t)((s >> 33) % i)]);
+    }
+  }
+  std::vector<int>& cellOrder() { return cell_order_; }
+
+  void reprojectMap(FramePtr frame, std::vector<std::pair<FramePtr, size_t>>& overlap_kfs) {
+    n_matches_ = n_trials_ = 0;
+    std::vector<FramePtr> kfs(map_.keyframes_.begin(), map_.keyframes_.end());
+    std::map<const Frame*, int> kf_index;
+    for (size_t k = 0; k < kfs.size(); ++k) kf_index[kfs[k].get()] = (int)k;
+    std::map<Feature*, int> ftr_index;
+    std::map<Point*, int> pt_index;
+    std::vector<Feature*> ftrs;
+    std::vector<Point*> pts;
+    auto ftr_id = [&](Feature* f) { auto it = ftr_index.find(f); if (it != ftr_index.end()) return it->second; ftr_index[f] = (int)ftrs.size(); ftrs.push_back(f); return (int)ftrs.size() - 1; };
+    auto pt_id = [&](Point* p) { auto it = pt_index.find(p); if (it != pt_index.end()) return it->second; pt_index[p] = (int)pts.size(); pts.push_back(p); return (int)pts.size() - 1; };
+    std::vector<int> kf_fts_offset(kfs.size() + 1, 0), kf_fts;
+    std::vector<double> kf_T(12 * kfs.size()), keypt_pos(15 * kfs.size(), 0.0);
+    std::vector<uint8_t> keypt_valid(5 * kfs.size(), 0);
+    std::vector<const svo_b200_frame*> kf_dev(kfs.size());
+    for (size_t k = 0; k < kfs.size(); ++k) {
+      kf_dev[k] = kfs[k]->device();
+      std::memcpy(&kf_T[12 * k], kfs[k]->T_f_w_.m, sizeof(double) * 12);
+      for (Feature* f : kfs[k]->fts_) { kf_fts.push_back(ftr_id(f)); if (f->point) pt_id(f->point); }
+      kf_fts_offset[k + 1] = (int)kf_fts.size();
+      for (int i = 0; i < 5; ++i) {
+        Feature* kp = kfs[k]->key_pts_[i];
+        if (!kp || !kp->point) continue;
+        keypt_valid[5 * k + i] = 1;
+        for (int c = 0; c < 3; ++c) keypt_pos[3 * (5 * k + i) + c] = kp->point->pos_[c];
+      }
+    }
+    std::vector<int> cand_point;
+    for (auto& c : map_.point_candidates_.candidates_) cand_point.push_back(pt_id(c.first));
+    std::vector<int> pt_obs_offset(1, 0), pt_obs;
+    for (size_t p = 0; p < pts.size(); ++p) {  // obs_ may reach features outside any fts_ list (candidates) -> extends ftrs
+      for (Feature* f : pts[p]->obs_) pt_obs.push_back(ftr_id(f));
+      pt_obs_offset.push_back((int)pt_obs.size());
+    }
+    const size_t F = ftrs.size(), P = pts.size();
+    std::vector<int> ftr_kf(F), ftr_level(F), ftr_type(F), ftr_point(F), pt_type(P), pt_failed(P), pt_succ(P);
+    std::vector<double> ftr_px(2 * F), ftr_f(3 * F), ftr_grad(2 * F), pt_pos(3 * P);
+    for (size_t i = 0; i < F; ++i) {
+      const Feature* f = ftrs[i];
+      auto it = kf_index.find(f->frame);
+      if (it == kf_index.end()) throw std::runtime_error("Reprojector: a point is observed from a frame that is not a map keyframe");
+      ftr_kf[i] = it->second; ftr_level[i] = f->level; ftr_type[i] = f->type;
+      ftr_point[i] = f->point ? pt_index.at(f->point) : -1;
+      ftr_px[2 * i] = f->px[0]; ftr_px[2 * i + 1] = f->px[1];
+      ftr_grad[2 * i] = f->grad[0]; ftr_grad[2 * i + 1] = f->grad[1];
+      for (int c = 0; c < 3; ++c) ftr_f[3 * i + c] = f->f[c];
+    }
+    for (size_t p = 0; p < P; ++p) {
+      pt_type[p] = pts[p]->type_; pt_failed[p] = pts[p]->n_failed_reproj_; pt_succ[p] = pts[p]->n_succeeded_reproj_;
+      for (int c = 0; c < 3; ++c) pt_pos[3 * p + c] = pts[p]->pos_[c];
+    }
+    const svo_b200_map_view view = {(int)kfs.size(), kf_T.data(), keypt_pos.data(), keypt_valid.data(), kf_fts_offset.data(),
+                                    kf_fts.data(), (int)F, ftr_kf.data(), ftr_px.data(), ftr_f.data(), ftr_level.data(),
+                                    ftr_type.data(), ftr_grad.data(), ftr_point.data(), (int)P, pt_pos.data(),
+                                    pt_obs_offset.data(), pt_obs.data(), (int)cand_point.size(), cand_point.data()};
+    const svo_b200_reproject_options opt = {options_.grid_size, options_.max_fts, (int)options_.max_n_kfs,
+                                            options_.find_match_direct ? 1 : 0, options_.n_pyr_levels - 1, 10};
+    const size_t cap = (size_t)options_.max_fts + 1;
+    std::vector<uint8_t> action(P);
+    std::vector<int> ov_kf(options_.max_n_kfs), new_point(cap), new_level(cap), new_type(cap);
+    std::vector<int64_t> ov_count(options_.max_n_kfs);
+    std::vector<double> new_px(2 * cap), new_grad(2 * cap);
+    svo_b200_reproject_stats st;
+    const svo_b200_camera cam = frame->cam_->c_abi();
+    Context& c = frame->context();
+    c.check(svo_b200_reproject_map(c.get(), &view, kf_dev.data(), frame->device(), frame->T_f_w_.m, &cam, &opt, cell_order_.data(),
+                                   pt_type.data(), pt_failed.data(), pt_succ.data(), action.data(), ov_kf.data(), ov_count.data(),
+                                   new_point.data(), new_px.data(), new_level.data(), new_type.data(), new_grad.data(), &st));
+    n_matches_ = (size_t)st.n_matches;
+    n_trials_ = (size_t)st.n_trials;
+    overlap_kfs.reserve(options_.max_n_kfs);
+    for (int i = 0; i < st.n_overlap; ++i) overlap_kfs.push_back(std::make_pair(kfs[ov_kf[i]], (size_t)ov_count[i]));
+    for (int q = 0; q < st.n_new; ++q) {  // reprojector.cpp:183-196
+      Feature* nf = new Feature(frame.get(), Vector2d{new_px[2 * q], new_px[2 * q + 1]}, new_level[q]);
+      nf->point = pts[new_point[q]];
+      if (new_type[q]) { nf->type = Feature::EDGELET; nf->grad = Vector2d{new_grad[2 * q], new_grad[2 * q + 1]}; }
+      frame->addFeature(nf);
+    }
+    for (size_t p = 0; p < P; ++p) {
+      pts[p]->n_failed_reproj_ = pt_failed[p];
+      pts[p]->n_succeeded_reproj_ = pt_succ[p];
+      switch (action[p]) {
+        case SVO_B200_PT_SAFE_DELETE: map_.safeDeletePoint(pts[p]); break;
+        case SVO_B200_PT_DELETE_CANDIDATE:
+        case SVO_B200_PT_CANDIDATE_ERASED: map_.point_candidates_.deleteCandidatePoint(pts[p]); break;
+        default: pts[p]->type_ = (Point::PointType)pt_type[p];
+      }
+    }
+  }
+
+ private:
+  Map& map_;
+  std::vector<int> cell_order_;
 };
 
 }  // namespace svo

@@ -457,3 +457,123 @@ def make_pose_opt_case(seed: int, n: int = 1000, width: int = 1920, height: int 
     has_point = (rng.uniform(size=n) > 0.02).astype(np.uint8)
     T_init = se3_mul(se3_exp(np.concatenate([rng.uniform(-0.05, 0.05, 3), rng.uniform(-0.01, 0.01, 3)])), T_true)
     return dict(cam=cam, f=f, pos=pos, level=level, has_point=has_point, T_init=T_init, T_true=T_true)
+
+
+def make_map_case(seed: int, n_kfs: int = 8, n_points: int = 700, width: int = 752, height: int = 480, n_levels: int = 5,
+                  n_candidates: int = 80, spread: float = 0.5, bad_frac: float = 0.2) -> dict:
+    """A small map for Reprojector::reprojectMap (svo/src/reprojector.cpp:64-217): n_kfs keyframes on a trajectory above
+    the textured plane, world points on the plane observed by 1..n_kfs keyframes (one Feature per observation, detected
+    on the integer grid of its level), point types / reprojection counters near the reference's thresholds, converged-
+    seed candidates whose single observation is not in its keyframe's fts_ list, five key points per keyframe, a current
+    frame close to the last keyframes, and a shuffled cell order.  Everything is flat arrays (the `map view`)."""
+    rng = np.random.default_rng(seed)
+    cam = camera_for(width, height)
+    plane, tex = Plane.tilted(), make_texture(7)
+    kf_T = []
+    for k in range(n_kfs):
+        xi = np.concatenate([rng.uniform(-spread, spread, 2), rng.uniform(-0.15, 0.15, 1), np.deg2rad(rng.uniform(-3, 3, 3))])
+        kf_T.append(se3_mul(se3_exp(xi), base_pose()))
+    xi = np.concatenate([rng.uniform(-0.1, 0.1, 3), np.deg2rad(rng.uniform(-2, 2, 3))])
+    cur_T = se3_mul(se3_exp(xi), kf_T[-1])
+    kf_pyr = [build_pyramid(render(cam, T, plane, tex), n_levels) for T in kf_T]
+    cur_pyr = build_pyramid(render(cam, cur_T, plane, tex), n_levels)
+
+    # world points: rays of a virtual wide view around the trajectory
+    ext = spread + 2.2
+    P = n_points + n_candidates
+    a, b = rng.uniform(-ext, ext, P), rng.uniform(-ext, ext, P)
+    c0 = se3_inv(base_pose())[:, 3]
+    pos = c0[None, :] * [1, 1, 0] + a[:, None] * plane.e1 + b[:, None] * plane.e2
+    pos -= np.outer(pos @ plane.n - plane.d, plane.n)                       # on the plane
+    pos += rng.normal(0, 0.004, pos.shape)                                 # map noise
+
+    ftr_kf, ftr_px, ftr_f, ftr_level, ftr_type, ftr_grad, ftr_point = [], [], [], [], [], [], []
+    kf_fts = [[] for _ in range(n_kfs)]
+    pt_obs = [[] for _ in range(P)]
+
+    def add_ftr(k, p, in_fts):
+        T = kf_T[k]
+        pc = T[:, :3] @ pos[p] + T[:, 3]
+        if pc[2] <= 0.1:
+            return False
+        px = cam.world2cam(pc)
+        L = int(rng.integers(0, 3))
+        px = np.round(px / (1 << L)) * (1 << L)
+        if not (12 <= px[0] < width - 12 and 12 <= px[1] < height - 12):
+            return False
+        i = len(ftr_kf)
+        ftr_kf.append(k); ftr_px.append(px); ftr_f.append(cam.cam2world(px)); ftr_level.append(L)
+        ftr_type.append(int(rng.uniform() < 0.12))
+        ang = rng.uniform(0, 2 * np.pi)
+        ftr_grad.append([np.cos(ang), np.sin(ang)]); ftr_point.append(p)
+        if in_fts:
+            kf_fts[k].append(i)
+        pt_obs[p].insert(0, i)                                             # Point::addFrameRef pushes to the front
+        return True
+
+    for p in range(n_points):
+        for k in range(n_kfs):
+            if rng.uniform() < 0.45:
+                add_ftr(k, p, True)
+    cand = []
+    for p in range(n_points, P):
+        for k in rng.permutation(n_kfs):
+            if add_ftr(int(k), p, False):                                  # the seed's feature: not in fts_
+                cand.append(p)
+                break
+    # a few features without a point (Feature::point == NULL)
+    for k in range(n_kfs):
+        for _ in range(5):
+            i = len(ftr_kf)
+            px = np.round(rng.uniform([20, 20], [width - 20, height - 20]))
+            ftr_kf.append(k); ftr_px.append(px); ftr_f.append(cam.cam2world(px)); ftr_level.append(0); ftr_type.append(0)
+            ftr_grad.append([1.0, 0.0]); ftr_point.append(-1)
+            kf_fts[k].insert(int(rng.integers(0, len(kf_fts[k]) + 1)), i)
+
+    # map errors: a fraction of the points sits 0.08..0.25 m away from where its features saw it -> failed matches
+    bad = rng.uniform(size=P) < bad_frac
+    ang = rng.uniform(0, 2 * np.pi, P)
+    shift = rng.uniform(0.08, 0.25, P)[:, None] * (np.cos(ang)[:, None] * plane.e1 + np.sin(ang)[:, None] * plane.e2)
+    pos = pos + shift * bad[:, None]
+
+    pt_type = rng.choice([2, 3], P, p=[0.6, 0.4]).astype(np.int32)          # UNKNOWN / GOOD
+    pt_type[rng.choice(n_points, 12, replace=False)] = 0                   # some already TYPE_DELETED
+    pt_type[n_points:] = 1                                                 # TYPE_CANDIDATE
+    n_failed = rng.integers(0, 17, P).astype(np.int32)
+    n_failed[n_points:] = rng.integers(0, 32, n_candidates)
+    n_succ = rng.integers(0, 12, P).astype(np.int32)
+
+    keypt_pos = np.zeros((n_kfs, 5, 3)); keypt_valid = np.zeros((n_kfs, 5), np.uint8)
+    keypt_ftr = np.full((n_kfs, 5), -1, np.int32)
+    for k in range(n_kfs):
+        idx = [i for i in kf_fts[k] if ftr_point[i] >= 0]
+        if not idx:
+            continue
+        pxs = np.array([ftr_px[i] for i in idx]) - [width / 2, height / 2]
+        picks = [int(np.argmin(np.max(np.abs(pxs), axis=1)))]
+        for sx, sy in ((1, 1), (1, -1), (-1, -1), (-1, 1)):
+            picks.append(int(np.argmax(np.where((pxs[:, 0] * sx >= 0) & (pxs[:, 1] * sy >= 0), np.abs(pxs[:, 0] * pxs[:, 1]), -1))))
+        for j, q in enumerate(picks):
+            keypt_pos[k, j] = pos[ftr_point[idx[q]]]
+            keypt_valid[k, j] = 1
+            keypt_ftr[k, j] = idx[q]
+    if n_kfs > 2:
+        keypt_valid[0, :] = 0                                              # one keyframe without key points: never close
+        keypt_ftr[0, :] = -1
+
+    off = np.zeros(n_kfs + 1, np.int32)
+    off[1:] = np.cumsum([len(x) for x in kf_fts])
+    ooff = np.zeros(P + 1, np.int32)
+    ooff[1:] = np.cumsum([len(x) for x in pt_obs])
+    grid = 30
+    n_cells = int(np.ceil(width / grid)) * int(np.ceil(height / grid))
+    view = dict(n_kfs=n_kfs, kf_T_f_w=np.stack(kf_T), kf_keypt_pos=keypt_pos, kf_keypt_valid=keypt_valid, kf_fts_offset=off,
+                kf_fts=np.array([i for x in kf_fts for i in x], np.int32), n_ftrs=len(ftr_kf),
+                ftr_kf=np.array(ftr_kf, np.int32), ftr_px=np.array(ftr_px, np.float64), ftr_f=np.array(ftr_f),
+                ftr_level=np.array(ftr_level, np.int32), ftr_type=np.array(ftr_type, np.int32),
+                ftr_grad=np.array(ftr_grad), ftr_point=np.array(ftr_point, np.int32), n_points=P, pt_pos=pos,
+                pt_obs_offset=ooff, pt_obs=np.array([i for x in pt_obs for i in x], np.int32),
+                n_candidates=len(cand), cand_point=np.array(cand, np.int32))
+    return dict(cam=cam, view=view, kf_pyr=kf_pyr, cur_pyr=cur_pyr, cur_T_f_w=cur_T, n_levels=n_levels, keypt_ftr=keypt_ftr,
+                pt_type=pt_type, pt_n_failed=n_failed, pt_n_succeeded=n_succ, cell_order=rng.permutation(n_cells).astype(np.int32),
+                options=dict(grid_size=grid, max_fts=120, max_n_kfs=10, find_match_direct=1, max_search_level=2, align_max_iter=10))

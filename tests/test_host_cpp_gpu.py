@@ -15,9 +15,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "rpg_svo_b200", "host")
 
 
-def build_demo():
-    exe = os.path.join(HOST, "host_demo")
-    src = os.path.join(HOST, "host_demo.cpp")
+def build_demo(name="host_demo"):
+    exe = os.path.join(HOST, name)
+    src = os.path.join(HOST, name + ".cpp")
     if not os.path.exists(exe) or os.path.getmtime(exe) < max(os.path.getmtime(src), os.path.getmtime(os.path.join(HOST, "svo_host.h"))):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-o", exe, src, "-L" + os.path.join(ROOT, "rpg_svo_b200"),
                                "-lsvo_b200", "-Wl,-rpath,$ORIGIN/.."])
@@ -64,3 +64,48 @@ def test_cpp_host_surface(tmp_path, oracle):
     assert dt < 1e-6 and dr < 1e-6
     assert num_obs == po["num_obs"] and np.array_equal(hp_after, po["has_point"])
     assert np.isclose(e_final, po["error_final"], rtol=1e-6) and np.isclose(est_scale, po["estimated_scale"], rtol=1e-6)
+
+
+def test_cpp_host_reprojector(tmp_path, oracle):
+    """svo::Reprojector of svo_host.h (pointer graph -> flat view -> svo_b200_reproject_map -> side effects applied to
+    the Frame / Point / Map objects) against the sequential oracle."""
+    c = synth.make_map_case(12, n_kfs=6, n_points=500)
+    v, cam, opt = c["view"], c["cam"], c["options"]
+    inp, outp = tmp_path / "in.bin", tmp_path / "out.bin"
+    with open(inp, "wb") as fh:
+        fh.write(struct.pack("14i", cam.width, cam.height, c["n_levels"], v["n_kfs"], v["n_ftrs"], v["n_points"], v["n_candidates"],
+                             len(v["kf_fts"]), len(v["pt_obs"]), len(c["cell_order"]), opt["grid_size"], opt["max_fts"],
+                             opt["max_n_kfs"], opt["max_search_level"] + 1))
+        fh.write(struct.pack("4d", cam.fx, cam.fy, cam.cx, cam.cy))
+        for pyr in c["kf_pyr"]:
+            fh.write(pyr[0].tobytes())
+        fh.write(c["cur_pyr"][0].tobytes())
+        fh.write(np.ascontiguousarray(v["kf_T_f_w"], np.float64).tobytes())
+        fh.write(np.ascontiguousarray(c["cur_T_f_w"], np.float64).tobytes())
+        fh.write(np.ascontiguousarray(c["keypt_ftr"], np.int32).tobytes())
+        for k, dt in (("kf_fts_offset", np.int32), ("kf_fts", np.int32), ("ftr_kf", np.int32), ("ftr_px", np.float64),
+                      ("ftr_f", np.float64), ("ftr_level", np.int32), ("ftr_type", np.int32), ("ftr_grad", np.float64),
+                      ("ftr_point", np.int32), ("pt_pos", np.float64), ("pt_obs_offset", np.int32), ("pt_obs", np.int32),
+                      ("cand_point", np.int32)):
+            fh.write(np.ascontiguousarray(v[k], dt).tobytes())
+        for k in ("pt_type", "pt_n_failed", "pt_n_succeeded", "cell_order"):
+            fh.write(np.ascontiguousarray(c[k], np.int32).tobytes())
+    subprocess.check_call([build_demo("host_reproject_demo"), str(inp), str(outp)])
+    raw = open(outp, "rb").read()
+    n_matches, n_trials, n_new, n_ov = struct.unpack_from("4q", raw, 0)
+    off = 32
+    ov = np.frombuffer(raw, np.int64, 2 * n_ov, off).reshape(n_ov, 2); off += 16 * n_ov
+    rec = np.dtype([("pt", "<i4"), ("level", "<i4"), ("type", "<i4"), ("px", "<f8", 2), ("grad", "<f8", 2)])
+    new = np.frombuffer(raw, rec, n_new, off); off += rec.itemsize * n_new
+    pst = np.frombuffer(raw, np.int32, 3 * v["n_points"], off).reshape(-1, 3)
+
+    o = oracle.reproject_map(c)
+    assert (n_matches, n_trials, n_new, n_ov) == (o["n_matches"], o["n_trials"], o["n_new"], o["n_overlap"])
+    assert np.array_equal(ov[:, 0], o["overlap_kf"]) and np.array_equal(ov[:, 1], o["overlap_count"])
+    assert np.array_equal(new["pt"], o["new_point"]) and np.array_equal(new["level"], o["new_level"])
+    assert np.array_equal(new["type"], o["new_type"])
+    assert np.max(np.abs(new["px"] - o["new_px"])) <= 1e-4
+    edge = o["new_type"] == 1
+    assert np.allclose(new["grad"][edge], o["new_grad"][edge], atol=1e-9)
+    assert np.array_equal(pst[:, 0], o["pt_type"]) and np.array_equal(pst[:, 1], o["pt_n_failed"])
+    assert np.array_equal(pst[:, 2], o["pt_n_succeeded"])

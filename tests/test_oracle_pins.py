@@ -370,3 +370,28 @@ def test_oracle_depth_filter_equals_reference_source_compiled_here(oracle):
     Tinv = synth.se3_inv(c["T_ref_w"])
     xyz = (c["ftr_f"][conv] / o["mu"][conv][:, None].astype(np.float64)) @ Tinv[:, :3].T + Tinv[:, 3]
     assert np.allclose(r["xyz_world"][conv], xyz, rtol=1e-12, atol=1e-12)
+
+
+def _same_reprojection(a, b, px_tol=0.0):
+    for k in ("n_matches", "n_trials", "n_new", "n_overlap"):
+        assert a[k] == b[k], k
+    for k in ("overlap_kf", "overlap_count", "new_point", "new_level", "new_type", "pt_type", "pt_n_failed", "pt_n_succeeded"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.max(np.abs(a["new_px"] - b["new_px"]), initial=0.0) <= px_tol
+    assert np.allclose(a["new_grad"], b["new_grad"], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("seed,kw", [(5, {}), (6, dict(n_kfs=12, n_points=900)), (7, dict(bad_frac=0.5)),
+                                     (8, dict(n_kfs=3, n_points=150, n_candidates=20))])
+def test_oracle_reprojector_equals_reference_source_compiled_here(oracle, seed, kw):
+    """Reprojector::reprojectMap of the compiled reference (reprojector.cpp + map.cpp + matcher.cpp, real svo::Map /
+    Frame / Feature / Point objects rebuilt from the flat view) vs the oracle's restatement: same overlap keyframes, same
+    features added to the frame in the same order with identical pixels, same point counters / types / deletions."""
+    _need_ref(oracle)
+    c = synth.make_map_case(seed, **kw)
+    o, r = oracle.reproject_map(c), oracle.ref_reproject_map(c)
+    _same_reprojection(o, r)
+    # the reference cannot tell "erased while projecting" from "deleteCandidatePoint": both end in the candidates' trash
+    assert np.array_equal(np.minimum(o["pt_action"], 2), np.minimum(r["pt_action"], 2))
+    if not kw.get("n_kfs", 8) == 3:
+        assert o["n_matches"] > 60 and o["n_trials"] > o["n_matches"]
