@@ -264,6 +264,28 @@ def measure_other_paths(ctx, rank: int) -> dict:
                                 "ms_per_call_e2e": 1e3 * t_gpu, "iterations": int(gp["n_iter_done"]),
                                 "pose_diff_vs_oracle_m": float(synth.pose_error(gp["T"], op["T"])[0]),
                                 "algorithmic_bytes": 52 * 1000 * (int(gp["n_iter_done"]) + 2)}
+
+    # ---- row f2: Reprojector::reprojectMap on a 10-keyframe map (speculative device alignment + host policy replay) ----
+    m = synth.make_map_case(4001, n_kfs=10, n_points=1200, n_candidates=150)
+    kfs, curf = [ctx.frame(p) for p in m["kf_pyr"]], ctx.frame(m["cur_pyr"])
+    rargs = (m["view"], kfs, curf, m["cur_T_f_w"], m["cam"], m["options"], m["cell_order"], m["pt_type"], m["pt_n_failed"],
+             m["pt_n_succeeded"])
+    gr = ctx.reproject_map(*rargs)
+    t_gpu = timeit(lambda: ctx.reproject_map(*rargs), 20)
+    orp = ob.reproject_map(m)
+    t_cpu = timeit(lambda: ob.reproject_map(m), 10)
+    t_ref = timeit(lambda: ob.ref_reproject_map(m), 3) if ob.ref_lib() is not None else None
+    out["reprojector_f2"] = {"map_points": int(m["view"]["n_points"]), "keyframes": 10, "matches": int(gr["n_matches"]),
+                             "trials_sequential": int(gr["n_trials"]), "aligned_speculatively": int(gr["n_speculative"]),
+                             "ms_per_call_e2e": 1e3 * t_gpu, "cpu_port_ms_1thread": 1e3 * t_cpu,
+                             "cpu_reference_ms_incl_graph_build": None if t_ref is None else 1e3 * t_ref,
+                             "same_features_as_oracle": bool(np.array_equal(gr["new_point"], orp["new_point"]) and
+                                                             np.array_equal(gr["pt_type"], orp["pt_type"])),
+                             "note": "the CPU matches only the ~130 candidates the cell policy reaches; the GPU aligns every "
+                                     "in-frame point in one launch and replays the policy on the host"}
+    for fr_ in kfs:
+        fr_.destroy()
+    curf.destroy()
     return out
 
 
