@@ -8,6 +8,7 @@
  *   svo_b200_align2d_batch/_1d      <- feature_alignment::align2D / align1D   svo/include/svo/feature_alignment.h:29-44
  *   svo_b200_find_match_direct      <- Matcher::findMatchDirect               svo/include/svo/matcher.h:109-112
  *   svo_b200_reproject_map          <- Reprojector::reprojectMap              svo/include/svo/reprojector.h:58-62, svo/src/reprojector.cpp:64-217
+ *   svo_b200_fast_detect            <- feature_detection::FastDetector::detect svo/include/svo/feature_detection.h:107-122, svo/src/feature_detection.cpp:66-115
  *   svo_b200_pose_optimize          <- pose_optimizer::optimizeGaussNewton    svo/include/svo/pose_optimizer.h:37-45
  *   svo_b200_point_optimize_batch   <- Point::optimize                        svo/include/svo/point.h:86, svo/src/point.cpp:119-177
  *   svo_b200_depth_filter_update    <- DepthFilter::updateSeeds               svo/include/svo/depth_filter.h:155
@@ -261,6 +262,23 @@ int svo_b200_reproject_map(svo_b200_ctx* ctx, const svo_b200_map_view* map, cons
                            int* pt_n_failed_io, int* pt_n_succeeded_io, uint8_t* pt_action_out, int* overlap_kf_out,
                            int64_t* overlap_count_out, int* new_point_out, double* new_px_out, int* new_level_out,
                            int* new_type_out, double* new_grad_out, svo_b200_reproject_stats* stats);
+
+/* ------------------------------------------------------------------ FAST detector ("next" row f4) -------- */
+typedef struct svo_b200_detect_options {
+  int cell_size;               /* Config::gridSize() (config.cpp:32: 30) */
+  int n_pyr_levels;            /* Config::nPyrLevels() (config.cpp:30: 3): levels searched */
+  int fast_threshold;          /* the literal 20 of feature_detection.cpp:78-92 */
+  int nonmax_ties_suppress;    /* [EXT] fast_nonmax_3x3: 0 = only a larger neighbour suppresses (libCVD non-strict, default); 1 = ties too */
+  double detection_threshold;  /* Config::triangMinCornerScore() (config.cpp:44: 20.0); must be >= 0 */
+} svo_b200_detect_options;
+/* FastDetector::detect: FAST-10 + score + 3x3 non-maximum suppression on levels 0..n_pyr_levels-1, Shi-Tomasi score of
+ * every surviving corner, the best corner of every grid cell that is not flagged in grid_occupancy (ceil(w/cell) *
+ * ceil(h/cell) bytes, NULL = all free; AbstractDetector::setExistingFeatures / setGridOccpuancy are the caller's).
+ * Outputs in cell order, level-0 pixel coordinates (the reference then builds Feature(frame, Vector2d(x, y), level));
+ * *n_out is the number found, at most `cap` of them are written; score_out may be NULL. */
+int svo_b200_fast_detect(svo_b200_ctx* ctx, const svo_b200_frame* frame, const svo_b200_detect_options* opt,
+                         const uint8_t* grid_occupancy, int cap, int* x_out, int* y_out, int* level_out, float* score_out,
+                         int* n_out);
 
 /* ------------------------------------------------------------------ depth filter -------- */
 #define SVO_B200_SEED_TOO_OLD 1

@@ -27,7 +27,7 @@ def build_ref() -> str | None:
 
 
 def build(force: bool = False) -> str:
-    srcs = ["svo_oracle.cpp", "svo_oracle_align.inc", "svo_oracle_depth.inc", "svo_oracle_pose.inc", "svo_oracle_reproject.inc",
+    srcs = ["svo_oracle.cpp", "svo_oracle_align.inc", "svo_oracle_depth.inc", "svo_oracle_pose.inc", "svo_oracle_reproject.inc", "svo_oracle_detect.inc", "fast_ext.h",
             "oracle_math.h", "svo_oracle.h", "Makefile"]
     stale = force or not os.path.exists(_LIB_PATH) or any(
         os.path.getmtime(os.path.join(_HERE, s)) > os.path.getmtime(_LIB_PATH) for s in srcs)
@@ -608,3 +608,26 @@ def ref_reproject_map(case):
                                 _p(o["overlap_count"]), _p(o["new_point"]), _p(o["new_px"]), _p(o["new_level"]),
                                 _p(o["new_type"]), _p(o["new_grad"]), C.byref(st))
     return trim_reproject(o, st)
+
+
+def fast_detect(pyr, n_pyr_levels, cell_size, detection_threshold, grid_occupancy=None, cap=4096, nonmax_ties_suppress=0):
+    """FastDetector::detect restated: returns dict(x, y, level, score) in grid-cell order."""
+    lp, cols, rows = _level_ptrs(pyr)
+    h, w = pyr[0].shape
+    x, y, lv = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    sc = np.zeros(cap, np.float32)
+    occ = None if grid_occupancy is None else np.ascontiguousarray(grid_occupancy, np.uint8)
+    n = lib().orc_fast_detect(lp, _p(cols), _p(rows), n_pyr_levels, w, h, cell_size, _p(occ) if occ is not None else None,
+                              C.c_double(detection_threshold), int(nonmax_ties_suppress), _p(x), _p(y), _p(lv), _p(sc), cap)
+    assert n <= cap
+    return dict(x=x[:n], y=y[:n], level=lv[:n], score=sc[:n])
+
+
+def ref_fast_detect(l0, n_levels, n_pyr_levels, cell_size, detection_threshold, grid_occupancy=None, cap=4096):
+    """feature_detection::FastDetector::detect of the compiled reference (with the [EXT] fast library restated)."""
+    h, w = l0.shape
+    x, y, lv = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    occ = None if grid_occupancy is None else np.ascontiguousarray(grid_occupancy, np.uint8)
+    n = ref_lib().ref_fast_detect(_p(np.ascontiguousarray(l0)), w, h, n_levels, n_pyr_levels, cell_size,
+                                  _p(occ) if occ is not None else None, C.c_double(detection_threshold), _p(x), _p(y), _p(lv), cap)
+    return dict(x=x[:n], y=y[:n], level=lv[:n])

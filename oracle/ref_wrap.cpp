@@ -8,6 +8,7 @@
 #include <svo/depth_filter.h>
 #include <svo/feature.h>
 #include <svo/feature_alignment.h>
+#include <svo/feature_detection.h>
 #include <svo/frame.h>
 #include <svo/matcher.h>
 #include <svo/point.h>
@@ -49,19 +50,35 @@ FramePtr make_frame(vk::AbstractCamera* cam, const uint8_t* img, int w, int h, i
 }
 }  // namespace
 
-// [EXT] corner detection (fast, vk::shiTomasiScore) is outside the hot path: link-only definitions.
-#include <cstdlib>
+// [EXT] the `fast` library and vk::shiTomasiScore behind the reference's feature_detection.cpp: the restatement of
+// oracle/fast_ext.h (PARITY UNPINNED there; what oracle/_ref pins is FastDetector::detect itself).
 #include <fast/fast.h>
 #include <vikit/vision.h>
+#include "fast_ext.h"
 namespace fast {
-#define SVO_REF_NO_FAST { fprintf(stderr, "oracle/_ref: the fast detector is not part of this build\n"); abort(); }
-void fast_corner_detect_10(const fast_byte*, int, int, int, short, std::vector<fast_xy>&) SVO_REF_NO_FAST
-void fast_corner_detect_10_sse2(const fast_byte*, int, int, int, short, std::vector<fast_xy>&) SVO_REF_NO_FAST
-void fast_corner_detect_10_neon(const fast_byte*, int, int, int, short, std::vector<fast_xy>&) SVO_REF_NO_FAST
-void fast_corner_score_10(const fast_byte*, int, const std::vector<fast_xy>&, int, std::vector<int>&) SVO_REF_NO_FAST
-void fast_nonmax_3x3(const std::vector<fast_xy>&, const std::vector<int>&, std::vector<int>&) SVO_REF_NO_FAST
+static void detect_any(const fast_byte* img, int w, int h, int stride, short b, std::vector<fast_xy>& corners) {
+  std::vector<fast_ext::xy> c;
+  fast_ext::detect10(img, w, h, stride, b, c);
+  corners.clear();
+  for (auto& q : c) corners.push_back(fast_xy(q.x, q.y));
+}
+void fast_corner_detect_10(const fast_byte* img, int w, int h, int stride, short b, std::vector<fast_xy>& c) { detect_any(img, w, h, stride, b, c); }
+void fast_corner_detect_10_sse2(const fast_byte* img, int w, int h, int stride, short b, std::vector<fast_xy>& c) { detect_any(img, w, h, stride, b, c); }
+void fast_corner_detect_10_neon(const fast_byte* img, int w, int h, int stride, short b, std::vector<fast_xy>& c) { detect_any(img, w, h, stride, b, c); }
+void fast_corner_score_10(const fast_byte* img, int stride, const std::vector<fast_xy>& corners, int b, std::vector<int>& scores) {
+  std::vector<fast_ext::xy> c;
+  for (auto& q : corners) c.push_back(fast_ext::xy{q.x, q.y});
+  fast_ext::score10(img, stride, c, b, scores);
+}
+void fast_nonmax_3x3(const std::vector<fast_xy>& corners, const std::vector<int>& scores, std::vector<int>& nonmax) {
+  std::vector<fast_ext::xy> c;
+  for (auto& q : corners) c.push_back(fast_ext::xy{q.x, q.y});
+  fast_ext::nonmax3x3(c, scores, nonmax);
+}
 }  // namespace fast
-namespace vk { float shiTomasiScore(const cv::Mat&, int, int) SVO_REF_NO_FAST }
+namespace vk {
+float shiTomasiScore(const cv::Mat& img, int u, int v) { return fast_ext::shiTomasiScore(img.data, img.cols, img.rows, (int)img.step.p[0], u, v); }
+}
 
 extern "C" {
 
@@ -284,6 +301,29 @@ void ref_depth_filter_update(const uint8_t* ref_l0s /*n_ref images*/, const doub
     for (int k = 0; k < 3; ++k) xyz_world_out[3 * i + k] = fts[i]->point->pos_[k];
   }
   for (Point* p : made) delete p;
+}
+
+// feature_detection::FastDetector::detect on a frame built from a level-0 image (pyramid by createImgPyramid).
+int ref_fast_detect(const uint8_t* l0, int w, int h, int n_levels, int n_pyr_levels, int cell_size, const uint8_t* grid_occupancy,
+                    double detection_threshold, int* out_x, int* out_y, int* out_level, int cap) {
+  vk::PinholeCamera cam(w, h, 300, 300, w / 2.0, h / 2.0);
+  const double I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  FramePtr fr = make_frame(&cam, l0, w, h, n_levels, I);
+  feature_detection::FastDetector det(w, h, cell_size, n_pyr_levels);
+  const int n_cols = (int)ceil((double)w / cell_size), n_rows = (int)ceil((double)h / cell_size);
+  if (grid_occupancy)
+    for (int r = 0; r < n_rows; ++r)
+      for (int c = 0; c < n_cols; ++c)
+        if (grid_occupancy[r * n_cols + c]) det.setGridOccpuancy(Vector2d(c * cell_size + 0.5, r * cell_size + 0.5));
+  Features fts;
+  det.detect(fr.get(), fr->img_pyr_, detection_threshold, fts);
+  int n = 0;
+  for (Feature* f : fts) {
+    if (n < cap) { out_x[n] = (int)f->px[0]; out_y[n] = (int)f->px[1]; out_level[n] = f->level; }
+    ++n;
+    delete f;
+  }
+  return n;
 }
 
 void ref_update_seed(float x, float tau2, float* a, float* b, float* mu, float* z_range, float* sigma2) {

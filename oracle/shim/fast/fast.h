@@ -1,6 +1,6 @@
 // oracle/shim/fast/fast.h -- TEST INFRASTRUCTURE ONLY: declarations of the [EXT] `fast` corner detector library
 // (uzh-rpg/fast) so that svo/src/feature_detection.cpp compiles and links; corner detection itself is outside the
-// hot path and the definitions in oracle/ref_wrap.cpp abort if ever called.
+// hot path proper; the definitions live in oracle/ref_wrap.cpp (restated in oracle/fast_ext.h).
 #pragma once
 #include <vector>
 namespace fast {

@@ -24,7 +24,6 @@ inline void halfSample(const cv::Mat& in, cv::Mat& out) {
       out.data[y * out.step.p[0] + x] = static_cast<uint8_t>((uint16_t(top[0]) + top[1] + top[stride] + top[stride + 1]) / 4);
     }
 }
-// [EXT] vk::shiTomasiScore: declared only (corner scoring belongs to the detector, outside the hot path); defined in
-// oracle/ref_wrap.cpp to abort if ever called.
+// [EXT] vk::shiTomasiScore: defined in oracle/ref_wrap.cpp from the restatement in oracle/fast_ext.h.
 float shiTomasiScore(const cv::Mat& img, int u, int v);
 }  // namespace vk

@@ -523,3 +523,5 @@ void orc_ldlt6_solve(const double* H36, const double* b6, double* x6_out) {
 #include "svo_oracle_depth.inc"
 #include "svo_oracle_pose.inc"
 #include "svo_oracle_reproject.inc"
+#include "fast_ext.h"
+#include "svo_oracle_detect.inc"

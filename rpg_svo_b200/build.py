@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libsvo_b200.so")
-SOURCES = ["context.cu", "sparse_align.cu", "align.cu", "pose_opt.cu", "depth_filter.cu", "reproject.cu"]
+SOURCES = ["context.cu", "sparse_align.cu", "align.cu", "pose_opt.cu", "depth_filter.cu", "reproject.cu", "detect.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false",
               "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-cudart", "static"]
 
@@ -39,7 +39,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(objdir, os.path.basename(s).replace(".cu", ".o"))
         objs.append(o)
         if force or not os.path.exists(o) or any(os.path.getmtime(d) > os.path.getmtime(o) for d in deps if not d.endswith(".cu") or d == s):
-            cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            extra = os.environ.get("SVO_B200_EXTRA_NVCC_FLAGS", "").split()  # e.g. -DSVO_SIA_DEBUG=1 for the clock64 section timers
+            cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((cmd, subprocess.Popen(cmd)))
     for cmd, p in procs:
         if p.wait() != 0:

@@ -474,3 +474,25 @@ def _reproject_map(self, view: dict, kf_frames, cur: Frame, cur_T_f_w, cam, opti
 
 
 Context.reproject_map = _reproject_map
+
+
+class DetectOptions(C.Structure):
+    _fields_ = [("cell_size", C.c_int), ("n_pyr_levels", C.c_int), ("fast_threshold", C.c_int),
+                ("nonmax_ties_suppress", C.c_int), ("detection_threshold", C.c_double)]
+
+
+def _fast_detect(self, frame: Frame, cell_size, n_pyr_levels, detection_threshold, grid_occupancy=None, fast_threshold=20,
+                 nonmax_ties_suppress=0, cap=8192):
+    """FastDetector::detect: dict(x, y, level, score) of the best corner per free grid cell, cell order."""
+    opt = DetectOptions(int(cell_size), int(n_pyr_levels), int(fast_threshold), int(nonmax_ties_suppress), float(detection_threshold))
+    x, y, lv = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    sc = np.zeros(cap, np.float32)
+    occ = None if grid_occupancy is None else _u8(grid_occupancy)
+    n = C.c_int(0)
+    self._check(self.lib.svo_b200_fast_detect(self.h, frame.h, C.byref(opt), _p(occ) if occ is not None else None, cap, _p(x),
+                                              _p(y), _p(lv), _p(sc), C.byref(n)))
+    k = min(n.value, cap)
+    return dict(x=x[:k], y=y[:k], level=lv[:k], score=sc[:k], n=n.value)
+
+
+Context.fast_detect = _fast_detect

@@ -397,9 +397,13 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         // r, r+1; patch row y needs Bq rows y, y+1, y+2.
         float pr0[7], pr1[7], b0[6], b1[6], b2[6];
         double sxx = 0, sxy = 0, syy = 0;
+        // all seven footprint rows are requested before the first use: one exposed L2/HBM latency per level instead
+        // of seven dependent ones
+        uint32_t rlo[7], rhi[7];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) fetch12<false>(ref_img, (vi - 3 + r) * W + (ui - 3), rlo[r], rhi[r]);
         auto load_row = [&](int r, float (&dst)[7]) {
-          uint32_t lo, hi;
-          fetch12<false>(ref_img, (vi - 3 + r) * W + (ui - 3), lo, hi);
+          const uint32_t lo = rlo[r], hi = rhi[r];
           dst[0] = byte_to_float<0>(lo); dst[1] = byte_to_float<1>(lo); dst[2] = byte_to_float<2>(lo);
           dst[3] = byte_to_float<3>(lo); dst[4] = byte_to_float<0>(hi); dst[5] = byte_to_float<1>(hi);
           dst[6] = byte_to_float<2>(hi);

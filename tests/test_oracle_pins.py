@@ -395,3 +395,32 @@ def test_oracle_reprojector_equals_reference_source_compiled_here(oracle, seed, 
     assert np.array_equal(np.minimum(o["pt_action"], 2), np.minimum(r["pt_action"], 2))
     if not kw.get("n_kfs", 8) == 3:
         assert o["n_matches"] > 60 and o["n_trials"] > o["n_matches"]
+
+
+def test_oracle_fast_detector_equals_reference_source_compiled_here(oracle):
+    """FastDetector::detect of the compiled reference (feature_detection.cpp; the un-vendored `fast` library and
+    vk::shiTomasiScore restated once in oracle/fast_ext.h and linked behind both) vs the oracle's restatement of the grid
+    logic: per-level scale, occupancy, strict best-score-per-cell, threshold."""
+    _need_ref(oracle)
+    for seed in (3, 4):
+        d = synth.make_two_view(seed, n_levels=5)
+        occ = (np.random.default_rng(seed).uniform(size=26 * 16) < 0.3).astype(np.uint8)
+        for o_ in (None, occ):
+            for thr in (20.0, 200.0):
+                a = oracle.fast_detect(d["ref_pyr"], 3, 30, thr, o_)
+                b = oracle.ref_fast_detect(d["ref_pyr"][0], 5, 3, 30, thr, o_)
+                assert all(np.array_equal(a[k], b[k]) for k in ("x", "y", "level"))
+        assert len(a["x"]) > 20
+
+
+def test_fast_ext_segment_test_properties(oracle):
+    """Known answers of the [EXT] FAST restatement: a bright 3x3 blob corner on a dark background is a corner with score
+    = contrast-1; straight edges and flat regions are not; detections keep a 3-pixel border."""
+    img = np.full((40, 40), 50, np.uint8)
+    img[20:, 20:] = 200                                                      # one L-corner at (20, 20)
+    r = oracle.fast_detect([img], 1, 40, 0.0)
+    assert len(r["x"]) == 1 and abs(int(r["x"][0]) - 20) <= 2 and abs(int(r["y"][0]) - 20) <= 2
+    edge = np.full((40, 40), 50, np.uint8)
+    edge[:, 20:] = 200                                                       # a straight edge: no FAST-10 corner
+    assert len(oracle.fast_detect([edge], 1, 40, 0.0)["x"]) == 0
+    assert len(oracle.fast_detect([np.full((40, 40), 9, np.uint8)], 1, 40, 0.0)["x"]) == 0
