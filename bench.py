@@ -283,6 +283,18 @@ def measure_other_paths(ctx, rank: int) -> dict:
                                                              np.array_equal(gr["pt_type"], orp["pt_type"])),
                              "note": "the CPU matches only the ~130 candidates the cell policy reaches; the GPU aligns every "
                                      "in-frame point in one launch and replays the policy on the host"}
+    # ---- row f4: FastDetector::detect on a 752x480 keyframe, 3 levels (svo/test/test_feature_detection.cpp:47-55) ----
+    det_args = (curf, 30, 3, 20.0)
+    gd = ctx.fast_detect(*det_args)
+    t_gpu = timeit(lambda: ctx.fast_detect(*det_args), 50)
+    od = ob.fast_detect(m["cur_pyr"], 3, 30, 20.0)
+    t_cpu = timeit(lambda: ob.fast_detect(m["cur_pyr"], 3, 30, 20.0), 5)
+    out["fast_detector_f4"] = {"image": "752x480, levels 0..2, 30 px cells", "corners": int(gd["n"]), "ms_per_call_e2e": 1e3 * t_gpu,
+                               "cpu_port_ms_1thread": 1e3 * t_cpu, "reference_published_ms": 7.17,
+                               "reference_published_source": "svo/test/test_feature_detection.cpp:55 (i7-W520, SSE2 fast library)",
+                               "same_corners_as_oracle": bool(np.array_equal(gd["x"], od["x"]) and np.array_equal(gd["y"], od["y"])
+                                                              and np.array_equal(gd["level"], od["level"])),
+                               "algorithmic_bytes": int(sum(im.size for im in m["cur_pyr"][:3]) + 8 * 26 * 16)}
     for fr_ in kfs:
         fr_.destroy()
     curf.destroy()

@@ -2,6 +2,7 @@
 // own programs drive SVO: build two Frames with Features/Points, then
 //   svo::SparseImgAlign(max, min, 30, GaussNewton, false, false).run(ref, cur)   (svo/test/test_sparse_img_align.cpp:121-123)
 //   svo::pose_optimizer::optimizeGaussNewton(2.0, 10, false, frame, ...)          (svo/test/test_pose_optimizer.cpp:99-104)
+//   svo::feature_detection::FastDetector(w, h, 30, 3).detect(frame, 20.0, fts)    (svo/test/test_feature_detection.cpp, depth_filter.cpp:114-119)
 // Inputs come from a binary dump written by tests/test_host_cpp_gpu.py, results go to a second file that
 // the test compares with the CPU oracle.   usage: host_demo in.bin out.bin
 #include <cstdio>
@@ -65,6 +66,12 @@ int main(int argc, char** argv) {
     std::vector<uint8_t> hp_after;
     for (svo::Feature* ft : frame_cur->fts_) hp_after.push_back(ft->point != nullptr);
 
+    // seed initialisation on a keyframe (depth_filter.cpp:114-119): new corners away from the existing features
+    svo::feature_detection::FastDetector detector(w, h, 30, 3);
+    svo::Features new_features;
+    detector.setExistingFeatures(frame_ref->fts_);
+    detector.detect(frame_ref.get(), 20.0, new_features);
+
     FILE* fo = fopen(argv[2], "wb");
     if (!fo) { perror("open output"); return 2; }
     long long nt = (long long)n_tracked, no = (long long)num_obs;
@@ -76,6 +83,13 @@ int main(int argc, char** argv) {
     fwrite(sc, sizeof(double), 3, fo);
     fwrite(&no, sizeof(no), 1, fo);
     fwrite(hp_after.data(), 1, hp_after.size(), fo);
+    const int n_new = (int)new_features.size();
+    fwrite(&n_new, sizeof(int), 1, fo);
+    for (svo::Feature* nf : new_features) {
+      const int rec[3] = {(int)nf->px[0], (int)nf->px[1], nf->level};
+      fwrite(rec, sizeof(int), 3, fo);
+      delete nf;
+    }
     fclose(fo);
     printf("host_demo: tracked %zu patches, pose-opt kept %zu observations (err %.3f -> %.3f px)\n", n_tracked, num_obs,
            error_init, error_final);

@@ -21,6 +21,7 @@
 //     thread / halt flag are the caller's (updateSeeds is synchronous, as in the reference when
 //     thread_ == NULL, depth_filter.cpp:95-96).
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cmath>
 #include <cstdint>
@@ -279,6 +280,48 @@ inline bool align1D(const Frame& cur_frame, int level, const std::array<float, 2
 // ------------------------------------------------------------------------------------------------
 // svo::DepthFilter (svo/include/svo/depth_filter.h:35-51,53-158)
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// svo::feature_detection (svo/include/svo/feature_detection.h:28-125): grid bookkeeping on the host, FAST-10 + score +
+// non-maximum suppression + Shi-Tomasi + per-cell selection in one device launch (svo_b200_fast_detect).
+// ------------------------------------------------------------------------------------------------
+namespace feature_detection {
+class AbstractDetector {
+ public:
+  AbstractDetector(int img_width, int img_height, int cell_size, int n_pyr_levels)
+      : cell_size_(cell_size), n_pyr_levels_(n_pyr_levels), grid_n_cols_((int)std::ceil((double)img_width / cell_size)),
+        grid_n_rows_((int)std::ceil((double)img_height / cell_size)), grid_occupancy_((size_t)grid_n_cols_ * grid_n_rows_, 0) {}
+  virtual ~AbstractDetector() {}
+  virtual void detect(Frame* frame, const double detection_threshold, Features& fts) = 0;  // img_pyr = the frame's device pyramid
+  void setGridOccpuancy(const Vector2d& px) {  // feature_detection.cpp:51-56 (spelling as in the reference)
+    grid_occupancy_.at((size_t)((int)(px[1] / cell_size_) * grid_n_cols_ + (int)(px[0] / cell_size_))) = 1;
+  }
+  void setExistingFeatures(const Features& fts) { for (Feature* f : fts) setGridOccpuancy(f->px); }  // :42-49
+
+ protected:
+  const int cell_size_, n_pyr_levels_, grid_n_cols_, grid_n_rows_;
+  std::vector<uint8_t> grid_occupancy_;
+  void resetGrid() { std::fill(grid_occupancy_.begin(), grid_occupancy_.end(), 0); }
+};
+typedef std::shared_ptr<AbstractDetector> DetectorPtr;
+
+class FastDetector : public AbstractDetector {
+ public:
+  FastDetector(int img_width, int img_height, int cell_size, int n_pyr_levels)
+      : AbstractDetector(img_width, img_height, cell_size, n_pyr_levels) {}
+  void detect(Frame* frame, const double detection_threshold, Features& fts) override {  // feature_detection.cpp:66-115
+    const svo_b200_detect_options opt = {cell_size_, n_pyr_levels_, 20, 0, detection_threshold};
+    const int cap = (int)grid_occupancy_.size();
+    std::vector<int> x(cap), y(cap), level(cap);
+    int n = 0;
+    Context& c = frame->context();
+    c.check(svo_b200_fast_detect(c.get(), frame->device(), &opt, grid_occupancy_.data(), cap, x.data(), y.data(), level.data(),
+                                 nullptr, &n));
+    for (int i = 0; i < n; ++i) fts.push_back(new Feature(frame, Vector2d{(double)x[i], (double)y[i]}, level[i]));
+    resetGrid();
+  }
+};
+}  // namespace feature_detection
+
 struct Seed {
   static int& batch_counter() { static int c = 0; return c; }
   static int& seed_counter() { static int c = 0; return c; }
@@ -299,7 +342,17 @@ class DepthFilter {
     int max_search_level = 2;  // Config::nPyrLevels()-1 with the non-ROS default n_pyr_levels = 3
   } options_;
   explicit DepthFilter(callback_t seed_converged_cb) : seed_converged_cb_(seed_converged_cb) {}
-  // addKeyframe + initializeSeeds (depth_filter.cpp:101-132) with the detector's output passed in
+  DepthFilter(feature_detection::DetectorPtr feature_detector, callback_t seed_converged_cb)  // depth_filter.h:88-90
+      : seed_converged_cb_(seed_converged_cb), feature_detector_(feature_detector) {}
+  // addKeyframe + initializeSeeds (depth_filter.cpp:101-132): detect new corners away from the frame's features
+  void addKeyframe(FramePtr frame, double depth_mean, double depth_min, double triang_min_corner_score = 20.0) {
+    if (!feature_detector_) throw std::runtime_error("DepthFilter: no feature detector (use the overload that takes the features)");
+    Features new_features;
+    feature_detector_->setExistingFeatures(frame->fts_);
+    feature_detector_->detect(frame.get(), triang_min_corner_score, new_features);
+    addKeyframe(frame, std::vector<Feature*>(new_features.begin(), new_features.end()), depth_mean, depth_min);
+  }
+  // the same with the detector's output passed in
   void addKeyframe(FramePtr frame, const std::vector<Feature*>& new_features, double depth_mean, double depth_min) {
     keyframes_.push_back(frame);
     ++Seed::batch_counter();
@@ -377,6 +430,7 @@ class DepthFilter {
 
  protected:
   callback_t seed_converged_cb_;
+  feature_detection::DetectorPtr feature_detector_;
   std::list<Seed> seeds_;
   std::list<FramePtr> keyframes_;
 };

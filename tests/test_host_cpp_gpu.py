@@ -64,6 +64,15 @@ def test_cpp_host_surface(tmp_path, oracle):
     assert dt < 1e-6 and dr < 1e-6
     assert num_obs == po["num_obs"] and np.array_equal(hp_after, po["has_point"])
     assert np.isclose(e_final, po["error_final"], rtol=1e-6) and np.isclose(est_scale, po["estimated_scale"], rtol=1e-6)
+    # FastDetector over the frame's device pyramid, cells of the existing features excluded
+    n_new = struct.unpack_from("i", raw, 520 + N)[0]
+    new = np.frombuffer(raw, np.int32, 3 * n_new, 524 + N).reshape(n_new, 3)
+    n_cols = int(np.ceil(cam.width / 30))
+    occ = np.zeros(n_cols * int(np.ceil(cam.height / 30)), np.uint8)
+    occ[(d["px"][:, 1] / 30).astype(int) * n_cols + (d["px"][:, 0] / 30).astype(int)] = 1
+    fo = oracle.fast_detect(d["ref_pyr"], 3, 30, 20.0, occ)
+    assert n_new == len(fo["x"]) and n_new > 20
+    assert np.array_equal(new[:, 0], fo["x"]) and np.array_equal(new[:, 1], fo["y"]) and np.array_equal(new[:, 2], fo["level"])
 
 
 def test_cpp_host_reprojector(tmp_path, oracle):
