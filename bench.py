@@ -16,7 +16,7 @@ ranks):
 `--impl reference` times oracle/_ref (the reference's own sparse_img_align.cpp compiled in place; its build system cannot run here: Eigen, OpenCV,
 Sophus, vikit, Boost are absent) on all host cores, on a bounded sample of the same pairs.
 
-L2 policy: inputs larger than L2 (592 pairs x 2 pyramids ~ 243 MB of distinct images per step vs
+L2 policy: inputs larger than L2 (2368 pairs, 2369 distinct pyramids ~ 970 MB of images per step vs
 126 MB of L2); no explicit flush.
 """
 from __future__ import annotations
@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--pairs-per-gpu", type=int, default=592)
+    ap.add_argument("--pairs-per-gpu", type=int, default=2368)  # 8 full waves of 2 CTAs x 148 SMs
     ap.add_argument("--cpu-sample", type=int, default=256, help="pairs timed by the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks of the window in the e2e leg (copy/compute overlap)")
