@@ -450,8 +450,19 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         },
         s, nwarps);
     if (tid == 0) {
+      if (SVO_SIA_DEBUG && P.debug) s.tk[0] += clock64() - tq0;
+      s.sum_vis += (int)s.sums[21];
+      s.done = 0;
+    }
+    if (staged) mbar_wait(&s.mbar, s.mbar_phase);
+    __syncthreads();
+    // The scaling and LDL^T factorisation of this level's H is serial work nobody needs before the first solve: the
+    // last thread of the block (a spare lane whenever the pair has fewer features than slots) does it while the other
+    // warps already run the first residual pass; it rejoins its warp at the pass reduction, i.e. before the
+    // iteration's first __syncthreads, after which thread 0 reads s.sol_tot.
+    if (tid == T - 1) {
       long long tq1 = 0;
-      if (SVO_SIA_DEBUG && P.debug) { tq1 = clock64(); s.tk[0] += tq1 - tq0; }
+      if (SVO_SIA_DEBUG && P.debug) tq1 = clock64();
       const double s2 = jscale * jscale;
       int idx = 0;
       for (int r = 0; r < 6; ++r)
@@ -461,12 +472,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           s.Htot[c * 6 + r] = v;
         }
       solver_factor(s.sol_tot, s.Htot);
-      s.sum_vis += (int)s.sums[21];
-      s.done = 0;
       if (SVO_SIA_DEBUG && P.debug) s.tk[1] += clock64() - tq1;
     }
-    if (staged) mbar_wait(&s.mbar, s.mbar_phase);
-    __syncthreads();
 
     // ---- Gauss-Newton iterations at this level ---------------------------------------------
     const int n_iter = EVAL ? 1 : P.n_iter;
