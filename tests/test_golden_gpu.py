@@ -51,3 +51,28 @@ def test_pose_opt_golden(ctx):
     assert dt < 1e-8 and dr < 1e-8
     assert np.array_equal(o["has_point"], g["has_point_out"]) and o["num_obs"] == int(g["num_obs"])
     assert np.isclose(o["error_final"], g["error_final"], rtol=1e-9)
+
+
+def test_detect_golden(ctx):
+    g = load("detect.npz")
+    fr = ctx.frame(synth.build_pyramid(g["img"], 3))
+    r = ctx.fast_detect(fr, 30, 3, 20.0, g["occupancy"])
+    assert all(np.array_equal(r[k], g[k]) for k in ("x", "y", "level"))
+    assert np.array_equal(r["score"].view(np.uint32), g["score"].view(np.uint32))
+    fr.destroy()
+
+
+def test_reproject_golden(ctx):
+    from tests.test_golden_cpu import _map_case_for
+
+    g = load("reproject.npz")
+    c = _map_case_for(g)
+    kfs, cur = [ctx.frame(p) for p in c["kf_pyr"]], ctx.frame(c["cur_pyr"])
+    r = ctx.reproject_map(c["view"], kfs, cur, c["cur_T_f_w"], c["cam"], c["options"], c["cell_order"], c["pt_type"],
+                          c["pt_n_failed"], c["pt_n_succeeded"])
+    assert r["n_matches"] == int(g["n_matches"]) and r["n_trials"] == int(g["n_trials"])
+    for k in ("new_point", "new_level", "new_type", "pt_type", "pt_n_failed", "pt_n_succeeded", "pt_action", "overlap_kf", "overlap_count"):
+        assert np.array_equal(r[k], g[k]), k
+    assert np.max(np.abs(r["new_px"] - g["new_px"]), initial=0.0) <= 1e-4
+    for f in kfs + [cur]:
+        f.destroy()
