@@ -137,19 +137,28 @@ extern "C" int svo_b200_reproject_map(svo_b200_ctx* ctx, const svo_b200_map_view
     return set_err(ctx, SVO_B200_EINVAL, "reproject_map: NULL argument");
   if (m->n_kfs < 0 || m->n_ftrs < 0 || m->n_points < 0 || m->n_candidates < 0 || (m->n_kfs > 0 && !kf_frames))
     return set_err(ctx, SVO_B200_EINVAL, "reproject_map: negative sizes / missing keyframe handles");
+  if ((m->n_kfs > 0 && (!m->kf_T_f_w || !m->kf_keypt_pos || !m->kf_keypt_valid || !m->kf_fts_offset)) ||
+      (m->n_ftrs > 0 && (!m->ftr_kf || !m->ftr_px || !m->ftr_f || !m->ftr_level || !m->ftr_type || !m->ftr_grad || !m->ftr_point)) ||
+      (m->n_points > 0 && (!m->pt_pos || !m->pt_obs_offset)) || (m->n_candidates > 0 && !m->cand_point))
+    return set_err(ctx, SVO_B200_EINVAL, "reproject_map: NULL array in the map view");
+  for (int k = 0; k < m->n_kfs; ++k)
+    if (!kf_frames[k]) return set_err(ctx, SVO_B200_EINVAL, "reproject_map: kf_frames[%d] is NULL", k);
+  const int n_kf_fts = m->n_kfs ? m->kf_fts_offset[m->n_kfs] : 0, n_obs_total = m->n_points ? m->pt_obs_offset[m->n_points] : 0;
+  if (n_kf_fts < 0 || n_obs_total < 0 || (n_kf_fts > 0 && !m->kf_fts) || (n_obs_total > 0 && !m->pt_obs))
+    return set_err(ctx, SVO_B200_EINVAL, "reproject_map: inconsistent offsets in the map view");
   if (opt->grid_size <= 0 || opt->max_fts < 0 || opt->max_n_kfs < 0 || opt->max_search_level < 0 ||
       opt->max_search_level >= cur->n_levels)
     return set_err(ctx, SVO_B200_EINVAL, "reproject_map: bad options (grid_size %d, max_search_level %d of %d levels)",
                    opt->grid_size, opt->max_search_level, cur->n_levels);
   for (int i = 0; i < m->n_ftrs; ++i) {
-    if (m->ftr_kf[i] < 0 || m->ftr_kf[i] >= m->n_kfs || m->ftr_point[i] >= m->n_points)
+    if (m->ftr_kf[i] < 0 || m->ftr_kf[i] >= m->n_kfs || m->ftr_point[i] >= m->n_points || m->ftr_point[i] < -1)
       return set_err(ctx, SVO_B200_EINVAL, "reproject_map: feature %d refers outside the map view", i);
     if (m->ftr_level[i] < 0 || m->ftr_level[i] >= kf_frames[m->ftr_kf[i]]->n_levels)
       return set_err(ctx, SVO_B200_EINVAL, "reproject_map: ftr_level[%d] outside the pyramid", i);
   }
-  for (int j = 0; j < (m->n_kfs ? m->kf_fts_offset[m->n_kfs] : 0); ++j)
+  for (int j = 0; j < n_kf_fts; ++j)
     if (m->kf_fts[j] < 0 || m->kf_fts[j] >= m->n_ftrs) return set_err(ctx, SVO_B200_EINVAL, "reproject_map: kf_fts[%d] out of range", j);
-  for (int j = 0; j < (m->n_points ? m->pt_obs_offset[m->n_points] : 0); ++j)
+  for (int j = 0; j < n_obs_total; ++j)
     if (m->pt_obs[j] < 0 || m->pt_obs[j] >= m->n_ftrs) return set_err(ctx, SVO_B200_EINVAL, "reproject_map: pt_obs[%d] out of range", j);
   for (int c = 0; c < m->n_candidates; ++c)
     if (m->cand_point[c] < 0 || m->cand_point[c] >= m->n_points) return set_err(ctx, SVO_B200_EINVAL, "reproject_map: cand_point[%d] out of range", c);
@@ -209,7 +218,7 @@ extern "C" int svo_b200_reproject_map(svo_b200_ctx* ctx, const svo_b200_map_view
 
   // ---- device: project + speculative getCloseViewObs / findMatchDirect for every enumerated point ----
   cudaSetDevice(ctx->device);
-  const int n_obs = m->pt_obs_offset[m->n_points];
+  const int n_obs = n_obs_total;
   Carver c;
   const size_t o_ept = c.take(sizeof(int) * E), o_skip = c.take(E), o_pos = c.take(sizeof(double) * 3 * m->n_points),
                o_ooff = c.take(sizeof(int) * (m->n_points + 1)), o_obs = c.take(sizeof(int) * n_obs),
@@ -228,20 +237,21 @@ extern "C" int svo_b200_reproject_map(svo_b200_ctx* ctx, const svo_b200_map_view
   SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   uint8_t* h = static_cast<uint8_t*>(ctx->h_in.p);
   uint8_t* d = static_cast<uint8_t*>(ctx->d_in.p);
-  memcpy(h + o_ept, e_pt.data(), sizeof(int) * E);
+  auto cp = [&](size_t off, const void* src, size_t bytes) { if (bytes) memcpy(h + off, src, bytes); };  // empty tables may be NULL
+  cp(o_ept, e_pt.data(), sizeof(int) * E);
   for (int e = 0; e < E; ++e) (h + o_skip)[e] = pt_type_io[e_pt[e]] == 0;
-  memcpy(h + o_pos, m->pt_pos, sizeof(double) * 3 * m->n_points);
-  memcpy(h + o_ooff, m->pt_obs_offset, sizeof(int) * (m->n_points + 1));
-  memcpy(h + o_obs, m->pt_obs, sizeof(int) * n_obs);
-  memcpy(h + o_fkf, m->ftr_kf, sizeof(int) * m->n_ftrs);
-  memcpy(h + o_fpx, m->ftr_px, sizeof(double) * 2 * m->n_ftrs);
-  memcpy(h + o_ff, m->ftr_f, sizeof(double) * 3 * m->n_ftrs);
-  memcpy(h + o_flv, m->ftr_level, sizeof(int) * m->n_ftrs);
-  memcpy(h + o_fty, m->ftr_type, sizeof(int) * m->n_ftrs);
-  memcpy(h + o_fgr, m->ftr_grad, sizeof(double) * 2 * m->n_ftrs);
-  memcpy(h + o_kT, m->kf_T_f_w, sizeof(double) * 12 * m->n_kfs);
+  cp(o_pos, m->pt_pos, sizeof(double) * 3 * m->n_points);
+  cp(o_ooff, m->pt_obs_offset, sizeof(int) * (m->n_points + 1));
+  cp(o_obs, m->pt_obs, sizeof(int) * n_obs);
+  cp(o_fkf, m->ftr_kf, sizeof(int) * m->n_ftrs);
+  cp(o_fpx, m->ftr_px, sizeof(double) * 2 * m->n_ftrs);
+  cp(o_ff, m->ftr_f, sizeof(double) * 3 * m->n_ftrs);
+  cp(o_flv, m->ftr_level, sizeof(int) * m->n_ftrs);
+  cp(o_fty, m->ftr_type, sizeof(int) * m->n_ftrs);
+  cp(o_fgr, m->ftr_grad, sizeof(double) * 2 * m->n_ftrs);
+  cp(o_kT, m->kf_T_f_w, sizeof(double) * 12 * m->n_kfs);
   for (int k = 0; k < m->n_kfs; ++k) reinterpret_cast<FrameDesc*>(h + o_kfr)[k] = make_desc(kf_frames[k]);
-  memcpy(h + o_cT, cur_T_f_w, sizeof(double) * 12);
+  cp(o_cT, cur_T_f_w, sizeof(double) * 12);
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
   ReprojIn in = {reinterpret_cast<const int*>(d + o_ept), d + o_skip, reinterpret_cast<const double*>(d + o_pos),
                  reinterpret_cast<const int*>(d + o_ooff), reinterpret_cast<const int*>(d + o_obs),
