@@ -231,7 +231,9 @@ __device__ inline void publish_model(SiaShared& s) {
 // when H_ is exactly zero), run the tail of one NLLSSolver::optimizeGaussNewton iteration [EXT]:
 // solve, accept/rollback, update.  Everything is pulled into registers first (independent loads),
 // the dependent chain is FMAs only.
-static __device__ __noinline__ void gn_finish(SiaShared& s, const SiaParams& P, const Solver6* S, int level,
+// (eps / trace are passed by value: taking the kernel's parameter struct by reference here would force every thread to
+// copy all of it to local memory at kernel entry -- 632 B/thread of stores that end up as DRAM write traffic)
+static __device__ __noinline__ void gn_finish(SiaShared& s, double eps, svo_b200_sia_iter* trace, int trace_cap, const Solver6* S, int level,
                                           int iter, double chi2sum, int n_in) {
   const int n_meas = n_in * kPatchArea;
   const float chi2f = (float)chi2sum;
@@ -269,7 +271,7 @@ static __device__ __noinline__ void gn_finish(SiaShared& s, const SiaParams& P, 
     s.chi2_prev = new_chi2;
     accepted = 1;
     const double m = fmax(fmax(fmax(fabs(x[0]), fabs(x[1])), fmax(fabs(x[2]), fabs(x[3]))), fmax(fabs(x[4]), fabs(x[5])));
-    if (m <= P.eps) done = 1;
+    if (m <= eps) done = 1;
   }
   s.model = out;
   qmatrix(out.q, s.R);
@@ -279,9 +281,9 @@ static __device__ __noinline__ void gn_finish(SiaShared& s, const SiaParams& P, 
   s.n_in_last = n_in;
   s.n_iters++;
   s.sum_in += n_in;
-  if (P.trace) {
-    if (s.n_trace < P.trace_cap) {
-      svo_b200_sia_iter& r = P.trace[s.n_trace];
+  if (trace) {
+    if (s.n_trace < trace_cap) {
+      svo_b200_sia_iter& r = trace[s.n_trace];
       r.level = level; r.iter = iter; r.accepted = accepted; r.n_meas = n_meas; r.chi2 = new_chi2;
       for (int k = 0; k < 6; ++k) r.x[k] = x[k];
       pose_to_rt12(out, r.T);
@@ -447,6 +449,9 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
     block_sum_h_to_warp0<FPT>(
         [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
           x = fx_[k]; y = fy_[k]; zi = fzi_[k]; sxx = m_sxx[k]; sxy = m_sxy[k]; syy = m_syy[k]; cnt = m_cnt[k];
+          // opaque to the optimiser: otherwise the level-invariant Jacobian rows are hoisted out of the level loop and
+          // parked in local memory (17 doubles per thread, written once and re-read every level)
+          asm volatile("" : "+d"(x), "+d"(y), "+d"(zi));
         },
         s, nwarps);
     if (tid == 0) {
@@ -574,10 +579,10 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           if (n_in == 0) {  // H_ == 0 exactly: Eigen's LDLT yields x = 0
             for (int k = 0; k < 36; ++k) s.Hs[k] = 0.0;
             s.h_is_tot = 0;
-            gn_finish(s, P, nullptr, level, iter, s.sums[6], n_in);
+            gn_finish(s, P.eps, P.trace, P.trace_cap, nullptr, level, iter, s.sums[6], n_in);
           } else {
             s.h_is_tot = 1;
-            gn_finish(s, P, &s.sol_tot, level, iter, s.sums[6], n_in);
+            gn_finish(s, P.eps, P.trace, P.trace_cap, &s.sol_tot, level, iter, s.sums[6], n_in);
           }
         }
         if (SVO_SIA_DEBUG && P.debug) s.tk[4] += clock64() - ti2;
@@ -604,6 +609,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         block_sum_h_to_warp0<FPT>(
             [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
               x = fx_[k]; y = fy_[k]; zi = fzi_[k]; sxx = q_sxx[k]; sxy = q_sxy[k]; syy = q_syy[k]; cnt = 0.0;
+              asm volatile("" : "+d"(x), "+d"(y), "+d"(zi));  // see the per-level call: no hoisting into local memory
             },
             s, nwarps);
         if (tid == 0) {
@@ -627,7 +633,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
             s.done = 1;
           } else {
             solver_factor(s.sol_cur, s.Hs);
-            gn_finish(s, P, &s.sol_cur, level, iter, chi2_keep, n_in_keep);
+            gn_finish(s, P.eps, P.trace, P.trace_cap, &s.sol_cur, level, iter, chi2_keep, n_in_keep);
           }
         }
         __syncthreads();
