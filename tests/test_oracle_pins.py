@@ -424,3 +424,67 @@ def test_fast_ext_segment_test_properties(oracle):
     edge[:, 20:] = 200                                                       # a straight edge: no FAST-10 corner
     assert len(oracle.fast_detect([edge], 1, 40, 0.0)["x"]) == 0
     assert len(oracle.fast_detect([np.full((40, 40), 9, np.uint8)], 1, 40, 0.0)["x"]) == 0
+
+
+@pytest.mark.parametrize("seed,trans,rot", [(51, 0.12, 2.5), (52, 0.2, 4.0)])
+def test_oracle_sia_large_motion_equals_reference_source_compiled_here(oracle, seed, trans, rot):
+    """Large inter-frame motion: patches leave the current image at the fine levels (the H of a pass then sums only the
+    patches that contributed), levels end on rejected iterations, visibility flags stay set -- all reference behaviours
+    the compiled reference and the oracle must share."""
+    _need_ref(oracle)
+    p = synth.make_frame_pair(seed, n_feat=250, trans=trans, rot_deg=rot)
+    r = oracle.ref_sparse_img_align(p["ref_pyr"][0], p["cur_pyr"][0], p["n_levels"], p["cam"], p["T_ref_w"], p["T_ref_w"],
+                                    p["px"], p["f"], p["pos"], p["has_point"], 4, 0)
+    o = oracle.sparse_img_align(p["ref_pyr"], p["cur_pyr"], p["cam"], synth.se3_identity(), p["px"], p["f"], p["pos"],
+                                p["has_point"], p["ref_pos"], 4, 0)
+    assert r["n_tracked"] == o["n_tracked"] and np.array_equal(r["visible"], o["visible"])
+    assert np.allclose(r["T_cur_w"], synth.se3_mul(o["T"], p["T_ref_w"]), rtol=0, atol=1e-8)
+    assert np.allclose(r["H"], o["H"], rtol=1e-8, atol=1e-8)
+    n_vis = int(o["visible"].sum())
+    assert any(t["n_meas"] // 16 < n_vis for t in o["trace"])               # some pass really lost patches
+
+
+def test_oracle_depth_filter_two_keyframes_equals_reference_source_compiled_here(oracle):
+    """Seeds of two different keyframes updated by one frame (ref_index per seed), wide baseline, many edgelets."""
+    _need_ref(oracle)
+    a = synth.make_depth_case(61, n_seeds=300, baseline=0.5)
+    b = synth.make_two_view(62, baseline=0.25)
+    rng = np.random.default_rng(3)
+    ref_index = rng.integers(0, 2, a["M"]).astype(np.int32)
+    ftr_type = (rng.uniform(size=a["M"]) < 0.5).astype(np.int32)
+    # keyframe 1 = the reference frame of a second two-view set rendered from the same plane; seeds keep their pixels
+    kf_pyr, kf_T = [a["ref_pyr"], b["ref_pyr"]], [a["T_ref_w"], b["T_ref_w"]]
+    r = oracle.ref_depth_filter_update([k[0] for k in kf_pyr], kf_T, a["cur_pyr"][0], a["T_cur_w"], a["n_levels"], a["cam"],
+                                       ref_index, a["ftr_px"], a["ftr_f"], a["ftr_level"], ftr_type, a["ftr_grad"], a["batch_id"],
+                                       a["batch_counter"], a["seeds"])
+    o = oracle.depth_filter_update(kf_pyr, kf_T, a["cur_pyr"], a["T_cur_w"], a["cam"], ref_index, a["ftr_px"], a["ftr_f"],
+                                   a["ftr_level"], ftr_type, a["ftr_grad"], a["batch_id"], a["batch_counter"], a["seeds"])
+    st = o["status"]
+    assert np.array_equal(r["status"], np.where(st == 6, 1, np.where((st == 1) | (st == 7), 2, 0)))
+    keep = r["status"] == 0
+    for k in ("a", "b", "mu", "z_range", "sigma2"):
+        assert np.array_equal(r[k][keep].view(np.uint32), o[k][keep].view(np.uint32)), k
+    assert (st >= 5).sum() > 50
+
+
+def test_oracle_matcher_wide_baseline_equals_reference_source_compiled_here(oracle):
+    """findMatchDirect under a strong affine warp (wide baseline, rotation about the optical axis): the search level leaves
+    0 and the 10x10 warped patch samples the reference image far from the feature."""
+    _need_ref(oracle)
+    c = synth.make_match_case(71, 100, baseline=0.9, rot_deg=12.0)
+    T_cur_ref = synth.se3_mul(c["T_cur_w"], synth.se3_inv(c["T_ref_w"]))
+    ref_pos = synth.se3_inv(c["T_ref_w"])[:, 3]
+    levels = []
+    for i in range(c["M"]):
+        r = oracle.ref_matcher(0, c["ref_pyr"][0], c["cur_pyr"][0], c["n_levels"], c["cam"], c["T_ref_w"], c["T_cur_w"],
+                               c["ref_px"][i], c["ref_f"][i], int(c["ref_level"][i]), int(c["ftr_type"][i]), c["ref_grad"][i],
+                               c["point_pos"][i], px_cur=c["px_cur"][i], n_pyr_levels=3)
+        o = oracle.find_match_direct(c["ref_pyr"], c["cur_pyr"], c["cam"], T_cur_ref, c["ref_px"][i], c["ref_f"][i],
+                                     int(c["ref_level"][i]), int(c["ftr_type"][i]), c["ref_grad"][i],
+                                     np.linalg.norm(c["point_pos"][i] - ref_pos), 2, 10, c["px_cur"][i])
+        assert r["success"] == o["success"] and r["search_level"] == o["search_level"], i
+        assert np.allclose(r["A_cur_ref"], o["A_cur_ref"], rtol=1e-9, atol=1e-12), i
+        if r["success"]:
+            assert np.allclose(r["px_cur"], o["px_cur"], rtol=0, atol=1e-9), i
+        levels.append(o["search_level"])
+    assert len(set(levels)) > 1
