@@ -60,3 +60,15 @@ def test_product_never_imports_the_oracle():
                 assert "oracle" not in txt.replace("the oracle", "").replace("CPU oracle", "").replace("oracle's", "").replace("oracle/", "") \
                     or "import oracle" not in txt and "from oracle" not in txt, f
                 assert "from oracle" not in txt and "import oracle" not in txt and "libsvo_oracle" not in txt, f
+
+
+def test_public_header_is_plain_c99(tmp_path):
+    """The drop-in boundary is a C ABI: include/svo_b200.h must compile as C99 with no C++ / torch types."""
+    import subprocess
+
+    src = tmp_path / "c.c"
+    src.write_text('#include "svo_b200.h"\nint main(void){ svo_b200_map_view v; svo_b200_detect_options o; '
+                   'svo_b200_sia_options s; (void)v; (void)o; (void)s; return 0; }\n')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                           "-I", os.path.join(root, "include"), str(src)])
