@@ -701,10 +701,19 @@ void sia_batch_free(svo_b200_ctx* ctx) {
   ctx->sia = nullptr;
 }
 
+static int g_sia_spare = 0;     // env SVO_B200_SIA_SPARE=1 (experimental): 352-thread CTAs for <= 320 features, so that the last warp owns
+                                // no feature and the per-level LDL^T truly overlaps the first residual pass
 static int g_sia_minb = 2;      // tuning knobs (env SVO_B200_SIA_MINB / SVO_B200_SIA_STAGE_KB), read once
 static int g_sia_stage_kb = 20;
 
 static int pick_launch(svo_b200_ctx* ctx, int max_feat, int& threads, int& fpt, int& stage_cap, size_t& smem) {
+  static bool env_read = false;
+  if (!env_read) {
+    env_read = true;
+    if (const char* e = getenv("SVO_B200_SIA_MINB")) g_sia_minb = atoi(e) == 3 ? 3 : 2;
+    if (const char* e = getenv("SVO_B200_SIA_SPARE")) g_sia_spare = atoi(e) != 0;
+    if (const char* e = getenv("SVO_B200_SIA_STAGE_KB")) g_sia_stage_kb = atoi(e) > 0 ? atoi(e) : 20;
+  }
   if (max_feat <= 512) fpt = 1;
   else if (max_feat <= 1024) fpt = 2;
   else if (max_feat <= 2048) fpt = 4;
@@ -712,17 +721,11 @@ static int pick_launch(svo_b200_ctx* ctx, int max_feat, int& threads, int& fpt, 
   threads = ((max_feat + fpt - 1) / fpt + 31) / 32 * 32;
   // the kernels are instantiated for MAXT in {320, 384, 512}; launching exactly MAXT threads makes the
   // slot count S = MAXT*FPT a compile-time constant (immediate shared-memory offsets)
-  threads = fpt == 1 ? (threads <= 320 ? 320 : threads <= 384 ? 384 : 512) : 512;
+  threads = fpt == 1 ? (threads <= 320 ? (g_sia_spare ? 352 : 320) : threads <= 384 ? 384 : 512) : 512;
   const size_t base = ((sizeof(SiaShared) + 15) & ~size_t(15)) + (size_t)3 * kPatchArea * threads * fpt * sizeof(float);
   const size_t budget = (size_t)ctx->max_smem_optin;
   if (base + 1024 > budget)
     return set_err(ctx, SVO_B200_ELIMIT, "sparse_img_align: %d features need %zu B of shared memory", max_feat, base);
-  static bool env_read = false;
-  if (!env_read) {
-    env_read = true;
-    if (const char* e = getenv("SVO_B200_SIA_MINB")) g_sia_minb = atoi(e) == 3 ? 3 : 2;
-    if (const char* e = getenv("SVO_B200_SIA_STAGE_KB")) g_sia_stage_kb = atoi(e) > 0 ? atoi(e) : 20;
-  }
   // staging region for the coarse current-level images (TMA); default 20 KB holds level >= 2 of 640x480
   size_t cap = (size_t)g_sia_stage_kb * 1024;
   if (base + cap > budget) cap = (budget - base) & ~size_t(15);
@@ -747,6 +750,7 @@ static int launch_sia(svo_b200_ctx* ctx, const SiaParams& P, int B, int threads,
   if (fpt == 1) {
     if (threads <= 320 && g_sia_minb == 3) return go(sia_kernel<1, EVAL, 320, 3>);
     if (threads <= 320) return go(sia_kernel<1, EVAL, 320, 2>);
+    if (threads == 352) return go(sia_kernel<1, EVAL, 352, 2>);
     if (threads <= 384) return go(sia_kernel<1, EVAL, 384, 2>);
     return go(sia_kernel<1, EVAL, 512, 1>);
   }
