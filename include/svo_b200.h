@@ -45,10 +45,22 @@ extern "C" {
 typedef struct svo_b200_ctx svo_b200_ctx;
 typedef struct svo_b200_frame svo_b200_frame;
 
-/* [EXT] vk::PinholeCamera without distortion (the only model the hot path's synthetic configs use) */
+/* [EXT] vk::AbstractCamera: the two models the reference ships parameter files for
+ * (svo_ros/param/camera_pinhole.yaml, camera_atan.yaml; svo/include/svo/frame_handler_mono.h:64).
+ *   SVO_B200_CAM_PINHOLE  vk::PinholeCamera(width, height, fx, fy, cx, cy, d0, d1, d2, d3, d4): d = radial-tangential
+ *                         coefficients (k1, k2, p1, p2, k3); all zero = no distortion.
+ *   SVO_B200_CAM_ATAN     vk::ATANCamera(width, height, fx, fy, cx, cy, s) (PTAM's FOV model): fx, fy, cx, cy are the
+ *                         PIXEL values the vikit constructor derives (fx_ = width*fx, cx_ = width*cx - 0.5, ...),
+ *                         d[0] = s (0 = no distortion).
+ * Zero-initialising model and d gives the undistorted pinhole camera. */
+#define SVO_B200_CAM_PINHOLE 0
+#define SVO_B200_CAM_ATAN 1
 typedef struct {
   double fx, fy, cx, cy;
   int width, height;
+  int model; /* SVO_B200_CAM_* */
+  int reserved_;
+  double d[5];
 } svo_b200_camera;
 
 /* ------------------------------------------------------------------ context ------------- */
@@ -130,7 +142,7 @@ int svo_b200_sparse_img_align(svo_b200_ctx* ctx, const svo_b200_frame* ref, cons
                               svo_b200_sia_stats* stats_out, svo_b200_sia_iter* trace_out,
                               int trace_cap, int* n_trace_out);
 
-/* Batch of B independent frame pairs (one CTA each).  Three-phase API so that the caller can
+/* Batch of B independent frame pairs (one CTA -- or, for small B, one thread-block cluster -- each).  Three-phase API so that the caller can
  * time the device part alone: stage (H2D of poses + features), run (kernels), fetch (D2H).
  * feat_offset has B+1 entries; pair b owns features [feat_offset[b], feat_offset[b+1]). */
 int svo_b200_sia_batch_stage(svo_b200_ctx* ctx, int B, const svo_b200_frame* const* ref,
@@ -142,6 +154,12 @@ int svo_b200_sia_batch_stage(svo_b200_ctx* ctx, int B, const svo_b200_frame* con
 int svo_b200_sia_batch_run(svo_b200_ctx* ctx);
 int svo_b200_sia_batch_fetch(svo_b200_ctx* ctx, double* T_out /*B*12*/, uint8_t* visible_out,
                              double* H_out /*B*36 or NULL*/, svo_b200_sia_stats* stats_out /*B or NULL*/);
+
+/* Launch geometry of the alignment kernel (tuning / tests; results agree to rounding between geometries).
+ *   ctas_per_pair: -1 = automatic (a 4-CTA thread-block cluster per pair while 4*B <= #SMs, i.e. live streams and
+ *                  small batches; one CTA per pair otherwise), or 1, 2, 4, 8 (clusters need <= 96*ctas features per pair).
+ *   features_per_thread: 0 = automatic, 1, 2 (one CTA per pair only). */
+int svo_b200_sia_config(svo_b200_ctx* ctx, int ctas_per_pair, int features_per_thread);
 
 /* computeResiduals(model, linearize=true) at one level and pose, exposing the caches; visible_io
  * carries the set-only visibility flags in and out. */

@@ -21,7 +21,8 @@ class SvoB200Error(RuntimeError):
 
 class Camera(C.Structure):
     _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
-                ("width", C.c_int), ("height", C.c_int)]
+                ("width", C.c_int), ("height", C.c_int), ("model", C.c_int), ("reserved_", C.c_int),
+                ("d", C.c_double * 5)]
 
 
 class SiaOptions(C.Structure):
@@ -62,10 +63,11 @@ def load() -> C.CDLL:
     """Load the CUDA library; fail loudly if it is missing (no fallback of any kind)."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
-            raise SvoB200Error(f"{LIB_PATH} is missing: build it with `python -m rpg_svo_b200.build` "
+        path = os.environ.get("SVO_B200_LIB", LIB_PATH)  # override: instrumented builds of the same library
+        if not os.path.exists(path):
+            raise SvoB200Error(f"{path} is missing: build it with `python -m rpg_svo_b200.build` "
                                "(there is no CPU fallback)")
-        _lib = C.CDLL(LIB_PATH)
+        _lib = C.CDLL(path)
         _lib.svo_b200_last_error.restype = C.c_char_p
         _lib.svo_b200_version.restype = C.c_char_p
         _lib.svo_b200_stream.restype = C.c_void_p
@@ -91,8 +93,13 @@ def c64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
+CAM_PINHOLE, CAM_ATAN = 0, 1
+
+
 def cam_struct(cam) -> Camera:
-    return Camera(cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height)
+    """`cam` needs fx, fy, cx, cy, width, height; optional `model` (CAM_*) and `d` (up to 5 coefficients)."""
+    d = (C.c_double * 5)(*([float(x) for x in getattr(cam, "d", ())] + [0.0] * 5)[:5])
+    return Camera(cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height, int(getattr(cam, "model", 0)), 0, d)
 
 
 class Frame:
@@ -261,6 +268,10 @@ class Context:
         hp = np.ascontiguousarray(has_point, np.uint8)
         self._check(self.lib.svo_b200_sia_batch_stage(self.h, B, ra, ca, C.byref(cs), C.byref(opt), _p(T),
                                                       _p(fo), _p(px), _p(f), _p(pos), _p(hp), _p(rpos)))
+
+    def sia_config(self, ctas_per_pair=-1, features_per_thread=0):
+        """Launch geometry of the alignment kernel (svo_b200_sia_config): -1 / 0 = automatic."""
+        self._check(self.lib.svo_b200_sia_config(self.h, int(ctas_per_pair), int(features_per_thread)))
 
     def sia_batch_run(self):
         self._check(self.lib.svo_b200_sia_batch_run(self.h))

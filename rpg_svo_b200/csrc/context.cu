@@ -33,6 +33,32 @@ int ensure_dev(svo_b200_ctx* ctx, DevBuf& b, size_t bytes) {
   return 0;
 }
 
+// [EXT] the constants vk::PinholeCamera / vk::ATANCamera derive in their constructors
+int cam_to_dev(svo_b200_ctx* ctx, const svo_b200_camera* cam, CamDev& o) {
+  memset(&o, 0, sizeof(o));
+  if (!cam || cam->width <= 0 || cam->height <= 0 || cam->fx == 0.0 || cam->fy == 0.0)
+    return set_err(ctx, SVO_B200_EINVAL, "camera: bad parameters");
+  if (cam->model != SVO_B200_CAM_PINHOLE && cam->model != SVO_B200_CAM_ATAN)
+    return set_err(ctx, SVO_B200_EINVAL, "camera: unknown model %d", cam->model);
+  o.fx = cam->fx; o.fy = cam->fy; o.cx = cam->cx; o.cy = cam->cy;
+  o.fx_inv = 1.0 / cam->fx; o.fy_inv = 1.0 / cam->fy;
+  o.width = cam->width; o.height = cam->height;
+  o.model = cam->model;
+  for (int k = 0; k < 5; ++k) o.d[k] = cam->d[k];
+  if (cam->model == SVO_B200_CAM_PINHOLE) {
+    o.distorted = fabs(cam->d[0]) > 0.0000001;  // vk::PinholeCamera: distortion_(fabs(d0) > 0.0000001)
+  } else {
+    const double sv = cam->d[0];
+    if (sv != 0.0) {  // vk::ATANCamera ctor
+      o.tans = 2.0 * tan(sv / 2.0);
+      o.tans_inv = 1.0 / o.tans;
+      o.s_inv = 1.0 / sv;
+      o.distorted = 1;
+    }
+  }
+  return 0;
+}
+
 int ensure_host(svo_b200_ctx* ctx, HostBuf& b, size_t bytes) {
   if (bytes <= b.cap) return 0;
   if (b.p) {

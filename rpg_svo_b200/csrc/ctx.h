@@ -56,6 +56,8 @@ struct svo_b200_ctx {
   DevBuf d_in, d_out, d_scratch;
   HostBuf h_in, h_out;
   svo::SiaBatchState* sia = nullptr;
+  int sia_cluster = -1;  // svo_b200_sia_config: CTAs per pair (-1 = by batch size)
+  int sia_fpt = 0;       //                      features per thread (0 = automatic)
 };
 
 namespace svo {
@@ -84,5 +86,17 @@ struct Carver {
 };
 
 void sia_batch_free(svo_b200_ctx* ctx);
+
+// Device-side camera ([EXT] vk::PinholeCamera / vk::ATANCamera): the C-ABI parameters plus the derived constants
+// the vikit constructors precompute.  Passed by value inside kernel parameter structs.
+struct CamDev {
+  double fx, fy, cx, cy;
+  double fx_inv, fy_inv;
+  double d[5];       // pinhole: k1 k2 p1 p2 k3;  ATAN: d[0] = s
+  double s_inv, tans, tans_inv;  // ATAN: 1/s, 2 tan(s/2), 1/tans
+  int model, distorted;
+  int width, height;
+};
+int cam_to_dev(svo_b200_ctx* ctx, const svo_b200_camera* cam, CamDev& out);
 
 }  // namespace svo

@@ -5,8 +5,9 @@
 // vk::NLLSSolver<6,SE3>::optimizeGaussNewton [EXT] that the class derives from.
 //
 // Design (B200-first, not a translation):
-//   * one CTA per frame pair runs the WHOLE coarse-to-fine loop on the device: no host round trip
-//     per Gauss-Newton iteration, batches of pairs fill the 148 SMs (grid = #pairs).
+//   * one CTA per frame pair -- or, for small batches, one thread-block CLUSTER per pair with the
+//     features split over its CTAs -- runs the WHOLE coarse-to-fine loop on the device: no host
+//     round trip per Gauss-Newton iteration, batches of pairs fill the 148 SMs.
 //   * one thread owns one feature (FPT features when N > blockDim): its bearing/depth state lives in
 //     registers for the whole run; the 4x4 reference patch, and its two gradient images, live in
 //     shared memory in pixel-major (SoA) order so a warp's accesses are conflict free.
@@ -17,11 +18,16 @@
 //     so the 6x6 normal matrix is reduced and factorised ONCE per level (and re-formed only in the
 //     iterations where some patch leaves the current image), and an iteration costs 3 f32 FMAs per
 //     pixel plus ~15 f64 FMAs per feature instead of the reference's 27 f64 MACs per pixel.
-//   * the packed feature records of the pair and the coarse current-level images are staged into
-//     shared memory with TMA bulk copies (cp.async.bulk + mbarrier); fine levels are gathered with
-//     two aligned 32-bit read-only loads per 5-byte footprint row.
-//   * each warp folds its partial sums (6 Jres + chi2 + counts) with __shfl_down; one thread does
-//     the 6x6 substitution, SE3 exp and the accept / rollback decision and broadcasts the new pose.
+//   * the current image is staged in shared memory at every level: whole coarse levels with one TMA
+//     bulk copy (cp.async.bulk + mbarrier), at the fine levels a 16x8-byte window around each
+//     feature's projection with cp.async (once per level; a footprint that drifts out of its window
+//     falls back to global loads).  The packed feature records of the pair arrive by TMA as well.
+//     While a level iterates, the next level's reference footprints / windows are prefetched into L2.
+//   * ONE block barrier per iteration: each warp folds its partial sums (6 Jres + chi2 + counts)
+//     with a transposed shuffle reduction and parks them in a double-buffered shared array; after
+//     the barrier EVERY warp adds the per-warp partials in the same order and runs the 6x6
+//     substitution, SE3 exp and the accept / rollback decision redundantly in registers (bit-identical
+//     in all lanes), so the new pose never has to be published through shared memory.
 // Precision follows the reference per quantity: f32 interpolation/residual/chi2, f64 geometry and
 // normal equations.
 #include <cstdio>
@@ -38,9 +44,15 @@ namespace svo {
 #ifndef SVO_SIA_DEBUG
 #define SVO_SIA_DEBUG 0  // 1: thread 0 accumulates clock64 section timings and a few CTAs print them
 #endif
+#if SVO_SIA_DEBUG
+#define SIA_DBG(...) __VA_ARGS__
+#else
+#define SIA_DBG(...)
+#endif
 constexpr int kPatchArea = 16;
-constexpr int kPartK = 24;  // widest block reduction: 21 unique H entries + 1 count, padded to 16 + 8
-constexpr int kMaxWarps = 16;  // blockDim <= 512
+constexpr int kPartK = 24;     // widest block reduction: 21 unique H entries + 1 count, padded to 16 + 8
+constexpr int kWinRows = 8;    // per-feature window of the current image: 8 rows x 16 bytes
+constexpr int kWinBytes = kWinRows * 16;  // 128 B per feature slot
 
 struct SiaJob {  // one frame pair; array lives in device memory
   const uint8_t* ref_lvl[SVO_B200_MAX_LEVELS];
@@ -56,11 +68,12 @@ struct SiaJob {  // one frame pair; array lives in device memory
 struct SiaParams {
   const SiaJob* jobs;
   int w[SVO_B200_MAX_LEVELS], h[SVO_B200_MAX_LEVELS];
-  double fx, fy, cx, cy;
+  CamDev cam;
   int max_level, min_level, n_iter;
   double eps;
-  int stage_cap;  // bytes of the TMA staging region in shared memory
-  int slots;      // blockDim * FPT feature slots (patch arrays are [3][16][slots])
+  int stage_cap;  // bytes of the staging region in shared memory (TMA image / cp.async windows)
+  int slots;      // blockDim * FPT feature slots per CTA (patch arrays are [3][16][slots])
+  int use_windows, use_prefetch;
   double* T_out;
   double* H_out;
   uint8_t* visible_out;
@@ -80,27 +93,35 @@ struct SiaParams {
   long long* n_meas_out;
 };
 
-struct SiaShared {
-  uint64_t mbar;
-  double R[9];
-  double t[3];
-  double part[kMaxWarps * kPartK];
-  double Hs[36];       // H_ of the current pass (scaled), full symmetric
-  double Htot[36];     // sum over the level's visible set (scaled)
-  Solver6 sol_cur;     // factorisation used for the current solve (slow path)
-  Solver6 sol_tot;     // factorisation of Htot
-  double x[8];
-  double sums[kPartK];
+struct SiaState {  // model_ / old_model of NLLSSolver::optimizeGaussNewton [EXT]
   Pose model, old_model;
-  double chi2_prev;
-  int stop, done, slow, n_in_last, h_is_tot;
-  int n_iters, sum_vis, sum_in, n_trace;
+};
+
+// Shared-memory control block of one CTA.  NWC = warps of this CTA, CS = CTAs of the pair (cluster size).
+template <int NWC, int CS>
+struct SiaSharedT {
+  static constexpr int kPairWarps = NWC * CS;
+  uint64_t mbar;
+  // per-warp partial sums of one residual pass (6 Jres + chi2, slot 7 unused) for every warp of the
+  // pair (all CTAs of the cluster), double-buffered by the parity of the running iteration counter
+  double part[2][kPairWarps][8];
+  int cnt[2][kPairWarps][2];
+  double hpart[NWC * kPartK];                   // per-warp partials of the 24-value H reduction
+  double hsum_cta[CS > 1 ? CS : 1][kPartK];     // per-CTA H sums (cluster variant: written remotely)
+  double sums[kPartK];                          // H totals of the pair
+  double Hs[36];                                // H_ of the current pass (scaled), full symmetric
+  double Htot[36];                              // sum over the level's visible set (scaled)
+  Solver6 sol_cur;                              // factorisation used for the current solve (slow path)
+  Solver6 sol_tot;                              // factorisation of Htot
+  SiaState st[2];                               // double-buffered like `part`
+  int h_is_tot, n_iters, sum_vis, sum_in, n_in_last, n_trace;  // thread 0 of CTA rank 0 only
   unsigned mbar_phase;
-  int cnt[kMaxWarps][2];
-  double keep_chi2;
-  int keep_n_in;
-  long long tkx[2];
-  long long tk[8];  // debug: cycles in [pre-parallel, pre-serial, pass, pass-reduce, serial, total]
+  double pub[12];      // CS == 1: the pose (R row-major, t) warp 0 publishes after its Gauss-Newton tail
+  int pub_done, pub_slow;
+#if SVO_SIA_DEBUG
+  long long tkx[4];
+  long long tk[8];  // debug: cycles in [level setup, pass, reduce, tail, total]
+#endif
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -119,6 +140,20 @@ __device__ __forceinline__ void fetch8(const uint8_t* base, int off, uint32_t& l
   const uint32_t w0 = ld_word<SMEM>(base, a), w1 = ld_word<SMEM>(base, a + 4);
   lo = __funnelshift_r(w0, w1, sh);
   hi = w1 >> sh;  // byte 4 of the row in its low byte
+}
+// 7 consecutive bytes at byte offset `off` from an 8-byte aligned global base: one aligned 64-bit load, plus the next
+// one only when the span crosses it -- 1.75 memory requests per row on average instead of 3 (the residual loops are
+// bound by the number of uncoalesced requests the L1 can take, not by bytes)
+__device__ __forceinline__ void fetch7_g64(const uint8_t* base, int off, uint32_t& lo, uint32_t& hi) {
+  const int a = off & ~7, p = off & 7;
+  const uint2 A = __ldg(reinterpret_cast<const uint2*>(base + a));
+  uint2 B = make_uint2(0u, 0u);
+  if (p > 1) B = __ldg(reinterpret_cast<const uint2*>(base + a + 8));
+  const bool k = p >= 4;
+  const uint32_t x0 = k ? A.y : A.x, x1 = k ? B.x : A.y, x2 = k ? B.y : B.x;
+  const unsigned sh = (unsigned)(p & 3) * 8u;
+  lo = __funnelshift_r(x0, x1, sh);
+  hi = __funnelshift_r(x1, x2, sh);
 }
 template <bool SMEM>
 __device__ __forceinline__ void fetch12(const uint8_t* base, int off, uint32_t& lo, uint32_t& hi) {
@@ -153,12 +188,41 @@ __device__ __forceinline__ double h_chunk_value(const double (&a)[6], const doub
   else return 0.0;
 }
 
-// Block sum of the 21 unique H entries + one count over per-feature moments, once per level (and in the
-// rare "slow path"): three transposed 8-value warp reductions computed chunk by chunk so that only ~8
-// accumulators are live at a time (no register spills), one shared-memory hop, warp 0 adds the
-// per-warp partials.  ONE __syncthreads.  `get(k, x, y, zi, sxx, sxy, syy, cnt)` yields feature k's data.
-template <int FPT, class Get>
-__device__ __forceinline__ void block_sum_h_to_warp0(Get get, SiaShared& s, int nwarps) {
+// ---- cluster helpers (CS == 1: plain CTA, everything below folds to local shared memory) ------------
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+template <int CS>
+__device__ __forceinline__ void pair_sync() {  // all threads of the pair: the CTA, or every CTA of its cluster
+  if constexpr (CS == 1) {
+    __syncthreads();
+  } else {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+}
+// store a double into the same shared-memory variable of CTA `rank` of the cluster (DSMEM)
+__device__ __forceinline__ void st_cluster_f64(double* local_ptr, unsigned rank, double v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(rank));
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(remote), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v2s32(int* local_ptr, unsigned rank, int a, int b) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(rank));
+  asm volatile("st.shared::cluster.v2.s32 [%0], {%1, %2};" ::"r"(remote), "r"(a), "r"(b) : "memory");
+}
+
+// Sum of the 21 unique H entries + one count over the per-feature moments of the whole pair, once per level
+// (and in the rare "slow path"): three transposed 8-value warp reductions computed chunk by chunk so that
+// only ~8 accumulators are live at a time (no register spills), one shared-memory hop, warp 0 adds the
+// per-warp partials (and, in the cluster variant, CTA rank 0's warp 0 adds the per-CTA sums after a cluster
+// barrier).  On return the totals are in s.sums[0..23] of EVERY CTA of the pair, visible to warp 0 only
+// (callers that need them elsewhere synchronise).  `get(k, x, y, zi, sxx, sxy, syy, cnt)` yields feature k's data.
+template <int FPT, int CS, class SH, class Get>
+__device__ __forceinline__ void pair_sum_h_to_warp0(Get get, SH& s, int nwarps) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   auto do_chunk = [&](auto chunk_tag) {
     constexpr int CH = decltype(chunk_tag)::value;
@@ -181,62 +245,87 @@ __device__ __forceinline__ void block_sum_h_to_warp0(Get get, SiaShared& s, int 
       v[7] += h_chunk_value<CH, 7>(a, b, sxx, sxy, syy, cnt);
     }
     warp_reduce_t<8>(v);
-    if ((lane & 3) == 0) s.part[warp * kPartK + CH * 8 + (lane >> 2)] = v[0];
+    if ((lane & 3) == 0) s.hpart[warp * kPartK + CH * 8 + (lane >> 2)] = v[0];
   };
   do_chunk(std::integral_constant<int, 0>{});
   do_chunk(std::integral_constant<int, 1>{});
   do_chunk(std::integral_constant<int, 2>{});
   __syncthreads();
-  if (warp == 0) {
-    if (lane < kPartK) {
-      double acc = 0.0;
-      for (int wv = 0; wv < nwarps; ++wv) acc += s.part[wv * kPartK + lane];
-      s.sums[lane] = acc;
+  if constexpr (CS == 1) {
+    if (warp == 0) {
+      if (lane < kPartK) {
+        double acc = 0.0;
+        for (int wv = 0; wv < nwarps; ++wv) acc += s.hpart[wv * kPartK + lane];
+        s.sums[lane] = acc;
+      }
+      __syncwarp();
     }
-    __syncwarp();
+  } else {
+    const unsigned rank = cluster_rank();
+    if (warp == 0 && lane < kPartK) {
+      double acc = 0.0;
+      for (int wv = 0; wv < nwarps; ++wv) acc += s.hpart[wv * kPartK + lane];
+#pragma unroll
+      for (int r = 0; r < CS; ++r) st_cluster_f64(&s.hsum_cta[rank][lane], (unsigned)r, acc);
+    }
+    pair_sync<CS>();
+    if (warp == 0) {
+      if (lane < kPartK) {
+        double acc = 0.0;
+#pragma unroll
+        for (int r = 0; r < CS; ++r) acc += s.hsum_cta[r][lane];
+        s.sums[lane] = acc;
+      }
+      __syncwarp();
+    }
   }
 }
 
-// Block sum of the 7 per-iteration doubles (6 Jres + chi2; slot 7 unused) and the two patch counts.
-// ONE __syncthreads; on return (warp 0 only) s.sums[0..6] hold the totals, the counts are returned.
-__device__ __forceinline__ void block_sum8_to_warp0(double (&v)[8], int n_in, int n_out, SiaShared& s, int nwarps,
-                                                    int& tot_in, int& tot_out) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  warp_reduce_t<8>(v);
-  const int w_in = __reduce_add_sync(0xffffffffu, n_in), w_out = __reduce_add_sync(0xffffffffu, n_out);
-  if ((lane & 3) == 0) s.part[warp * kPartK + (lane >> 2)] = v[0];
-  if (lane == 0) { s.cnt[warp][0] = w_in; s.cnt[warp][1] = w_out; }
-  __syncthreads();
-  tot_in = tot_out = 0;
-  if (warp == 0) {
-    const int k = lane & 7;
-    double acc = 0.0;
-    for (int wv = lane >> 3; wv < nwarps; wv += 4) acc += s.part[wv * kPartK + k];
-    acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-    acc += __shfl_xor_sync(0xffffffffu, acc, 16);
-    if (lane < 8) s.sums[lane] = acc;
-    const int ci = lane < nwarps ? s.cnt[lane][0] : 0, co = lane < nwarps ? s.cnt[lane][1] : 0;
-    tot_in = __reduce_add_sync(0xffffffffu, ci);
-    tot_out = __reduce_add_sync(0xffffffffu, co);
-    __syncwarp();
+// Warp 0: scale the 21 summed H entries into the full symmetric 6x6 `Hdst` and factorise it into `S`.
+// Every lane runs the register-resident unpivoted LDL^T redundantly (same cost as one lane), lane 0 stores
+// the factors; the pivoted Eigen-like fallback handles a degenerate H.
+template <class SH>
+__device__ __forceinline__ void warp0_scale_and_factor(SH& s, double s2, double* Hdst, Solver6& S) {
+  const int lane = threadIdx.x & 31;
+  double h[21];
+#pragma unroll
+  for (int k = 0; k < 21; ++k) h[k] = s.sums[k] * s2;
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = r; c < 6; ++c) { Hdst[r * 6 + c] = h[upper_idx(r, c)]; Hdst[c * 6 + r] = h[upper_idx(r, c)]; }
   }
+  Fact6 F;
+  const bool ok = fact6_compute_upper(h, F);
+  if (lane == 0) {
+    if (ok) {
+      S.F = F;
+      S.pivoted = 0;
+    } else {
+      for (int k = 0; k < 36; ++k) S.ldl[k] = Hdst[k];
+      ldlt6_factor(S.ldl, S.tr);
+      S.pivoted = 1;
+    }
+  }
+  __syncwarp();
 }
 
-__device__ inline void publish_model(SiaShared& s) {
-  qmatrix(s.model.q, s.R);
-  s.t[0] = s.model.t[0]; s.t[1] = s.model.t[1]; s.t[2] = s.model.t[2];
-}
-
-// Thread 0: given Jres in s.x (already scaled/negated) and a factorisation of H_ (or S == nullptr
-// when H_ is exactly zero), run the tail of one NLLSSolver::optimizeGaussNewton iteration [EXT]:
-// solve, accept/rollback, update.  Everything is pulled into registers first (independent loads),
-// the dependent chain is FMAs only.
-// (eps / trace are passed by value: taking the kernel's parameter struct by reference here would force every thread to
-// copy all of it to local memory at kernel entry -- 632 B/thread of stores that end up as DRAM write traffic)
-static __device__ __noinline__ void gn_finish(SiaShared& s, double eps, svo_b200_sia_iter* trace, int trace_cap, const Solver6* S, int level,
-                                          int iter, double chi2sum, int n_in) {
+// Tail of one NLLSSolver::optimizeGaussNewton iteration [EXT] -- solve, accept/rollback, update -- executed
+// redundantly by EVERY thread of the pair on bit-identical inputs (tot[], n_in, the shared factorisation and the
+// double-buffered state), so that all threads leave with the same new pose in registers and the same `done`.
+// Thread 0 of every CTA (`cta_leader`) writes that CTA's state buffer of the next iteration; thread 0 of CTA rank 0
+// (`leader`) also keeps the counters and the trace.
+template <class SH>
+__device__ __forceinline__ void gn_tail(SH& s, unsigned g, const Solver6* S, const double (&tot)[7], double jscale,
+                                        int n_in, int iter, int level, double eps, bool cta_leader, bool leader, svo_b200_sia_iter* trace,
+                                        int trace_cap, double& chi2_prev, int& stop, int& done, double (&R)[9],
+                                        double (&t)[3]) {
+#if SVO_SIA_DEBUG
+  long long tg0 = clock64();
+#endif
   const int n_meas = n_in * kPatchArea;
-  const float chi2f = (float)chi2sum;
+  const float chi2f = (float)tot[6];
   const double new_chi2 = (double)(chi2f / (float)n_meas);  // sparse_img_align.cpp:242 (NaN if 0)
   double x[6];
   if (S == nullptr) {  // Eigen's LDLT of an all-zero matrix solves to x = 0
@@ -246,102 +335,151 @@ static __device__ __noinline__ void gn_finish(SiaShared& s, double eps, svo_b200
     const Fact6 F = S->F;
     double b[6];
 #pragma unroll
-    for (int k = 0; k < 6; ++k) b[k] = s.x[k];
+    for (int k = 0; k < 6; ++k) b[k] = -(tot[k] * jscale);  // Jres_ = -sum J r
     fact6_solve(F, b, x);
   } else {
-    ldlt6_solve(S->ldl, S->tr, s.x);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) x[k] = s.x[k];
+    double b[6];
+    for (int k = 0; k < 6; ++k) b[k] = -(tot[k] * jscale);
+    ldlt6_solve(S->ldl, S->tr, b);
+    for (int k = 0; k < 6; ++k) x[k] = b[k];
   }
-  const Pose model = s.model;
-  int stop = s.stop;
-  if (isnan(x[0])) stop = 1;  // solve() == 0 (:248-250)
-  int accepted, done = 0;
+#if SVO_SIA_DEBUG
+  long long tg1 = clock64() + (long long)(x[0] != x[0]) + (long long)(x[3] != x[3]);
+#endif
+  const SiaState& cur = s.st[g & 1u];
+  const Pose model = cur.model;
+  if (isnan(x[0])) stop = 1;  // solve() == 0 (:248-250); stop_ latches
+  int accepted;
   Pose out;
-  if ((iter > 0 && new_chi2 > s.chi2_prev) || stop) {
-    out = s.old_model;  // rollback
+  done = 0;
+  if ((iter > 0 && new_chi2 > chi2_prev) || stop) {
+    out = cur.old_model;  // rollback
     done = 1;
     accepted = 0;
+    if (cta_leader) { s.st[(g + 1u) & 1u].model = out; s.st[(g + 1u) & 1u].old_model = out; }
   } else {
     double mx[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) mx[k] = -x[k];
     out = pose_mul_fast(model, se3_exp_fast(mx));  // T_new = T_old * exp(-x)  (:257)
-    s.old_model = model;
-    s.chi2_prev = new_chi2;
+    chi2_prev = new_chi2;
     accepted = 1;
     const double m = fmax(fmax(fmax(fabs(x[0]), fabs(x[1])), fmax(fabs(x[2]), fabs(x[3]))), fmax(fabs(x[4]), fabs(x[5])));
     if (m <= eps) done = 1;
+    if (cta_leader) { s.st[(g + 1u) & 1u].model = out; s.st[(g + 1u) & 1u].old_model = model; }
   }
-  s.model = out;
-  qmatrix(out.q, s.R);
-  s.t[0] = out.t[0]; s.t[1] = out.t[1]; s.t[2] = out.t[2];
-  s.stop = stop;
-  s.done = done;
-  s.n_in_last = n_in;
-  s.n_iters++;
-  s.sum_in += n_in;
-  if (trace) {
-    if (s.n_trace < trace_cap) {
-      svo_b200_sia_iter& r = trace[s.n_trace];
-      r.level = level; r.iter = iter; r.accepted = accepted; r.n_meas = n_meas; r.chi2 = new_chi2;
-      for (int k = 0; k < 6; ++k) r.x[k] = x[k];
-      pose_to_rt12(out, r.T);
+  qmatrix(out.q, R);
+  t[0] = out.t[0]; t[1] = out.t[1]; t[2] = out.t[2];
+#if SVO_SIA_DEBUG
+  long long tg2 = clock64() + (long long)(R[0] != R[0]) + (long long)(t[0] != t[0]);
+  if (leader) { s.tk[5] += tg1 - tg0; s.tk[6] += tg2 - tg1; }
+#endif
+  if (leader) {
+    s.n_in_last = n_in;
+    s.n_iters++;
+    s.sum_in += n_in;
+    if (trace) {
+      if (s.n_trace < trace_cap) {
+        svo_b200_sia_iter& r = trace[s.n_trace];
+        r.level = level; r.iter = iter; r.accepted = accepted; r.n_meas = n_meas; r.chi2 = new_chi2;
+        for (int k = 0; k < 6; ++k) r.x[k] = x[k];
+        pose_to_rt12(out, r.T);
+      }
+      s.n_trace++;
     }
-    s.n_trace++;
   }
 }
 
-template <int FPT, bool EVAL, int MAXT, int MINB>
+// 4-byte asynchronous global->shared copy (LDGSTS): no register staging, completion per thread
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+enum { kModeGlobal = 0, kModeImage = 1, kModeWindow = 2 };
+
+// One CTA (CS == 1) or one cluster of CS CTAs per frame pair; the pair's features are dealt to the CTAs in
+// contiguous blocks of S = MAXT*FPT slots.
+template <int FPT, bool EVAL, int MAXT, int MINB, int CS>
 __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  SiaShared& s = *reinterpret_cast<SiaShared*>(smem_raw);
-  constexpr int S = MAXT * FPT;  // feature slots (== P.slots, checked on the host)
-  float* pat_ref = reinterpret_cast<float*>(smem_raw + ((sizeof(SiaShared) + 15) & ~size_t(15)));
+  using SH = SiaSharedT<MAXT / 32, CS>;
+  SH& s = *reinterpret_cast<SH*>(smem_raw);
+  constexpr int S = MAXT * FPT;  // feature slots of this CTA (== P.slots, checked on the host)
+  float* pat_ref = reinterpret_cast<float*>(smem_raw + ((sizeof(SH) + 15) & ~size_t(15)));
   float2* pat_dxy = reinterpret_cast<float2*>(pat_ref + kPatchArea * S);
   uint8_t* stage = reinterpret_cast<uint8_t*>(pat_dxy + kPatchArea * S);  // 16-byte aligned
+  uint4* win = reinterpret_cast<uint4*>(stage);                            // [kWinRows][S] 16-byte window rows
 
-  const SiaJob& job = P.jobs[blockIdx.x];
+  const unsigned crank = CS == 1 ? 0u : cluster_rank();
+  const int pair = CS == 1 ? (int)blockIdx.x : (int)(blockIdx.x / CS);
+  const SiaJob& job = P.jobs[pair];
   const int tid = threadIdx.x, T = blockDim.x, nwarps = (T + 31) >> 5;
-  const int N = job.n_feat;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int fbase = (int)crank * S;  // first feature of this CTA
+  const int N = job.n_feat;          // features of the pair
   const int np = job.n_pad;
-  const uint32_t blob_bytes = (uint32_t)np * 65u;  // <= 192*S: the patch arrays are free until the first level
+  const bool cta_leader = tid == 0, leader = tid == 0 && crank == 0;
+  // features of this CTA: [fbase, min(N, fbase + S)); their records are np_loc padded entries of the pair's blob
+  const int n_loc = max(0, min(N - fbase, S));
+  const int np_loc = (n_loc + 15) & ~15;
 
   if (tid == 0) {
     mbar_init(&s.mbar, 1);
     fence_mbar_init();
     s.mbar_phase = 0;  // use k of the barrier completes phase parity k&1; the blob copy is use 0
-    s.model = pose_from_rt12(job.T);
-    s.old_model = s.model;
-    s.chi2_prev = 1e10;  // NLLSSolver::reset() [EXT]
-    s.stop = 0; s.done = 0; s.slow = 0; s.n_in_last = 0; s.h_is_tot = 0;
+    s.st[0].model = pose_from_rt12(job.T);
+    s.st[0].old_model = s.st[0].model;
+    s.h_is_tot = 0; s.n_in_last = 0;
     s.n_iters = 0; s.sum_vis = 0; s.sum_in = 0; s.n_trace = 0;
+#if SVO_SIA_DEBUG
     for (int k = 0; k < 8; ++k) s.tk[k] = 0;
-    s.tkx[0] = s.tkx[1] = 0;
-    s.tk[5] = clock64();
+    for (int k = 0; k < 4; ++k) s.tkx[k] = 0;
+    s.tk[4] = clock64();
+#endif
     for (int k = 0; k < 36; ++k) s.Hs[k] = 0.0;
-    publish_model(s);
-    // ---- TMA: the packed feature records of this pair, one bulk copy into the (idle) patch arrays
+    // ---- TMA: the packed feature records of this CTA's features, four bulk copies (px, f, pos, has_point
+    //      sections of the pair's blob) into the (idle) patch arrays
     fence_proxy_async();
-    mbar_expect_tx(&s.mbar, blob_bytes);
-    tma_bulk_g2s(pat_ref, job.blob, blob_bytes, &s.mbar);
+    if (np_loc > 0) {
+      const uint32_t bytes = (uint32_t)np_loc * 65u;
+      mbar_expect_tx(&s.mbar, bytes);
+      uint8_t* dst = reinterpret_cast<uint8_t*>(pat_ref);
+      const uint8_t* src = job.blob;
+      tma_bulk_g2s(dst, src + (size_t)fbase * 16, (uint32_t)np_loc * 16u, &s.mbar);                                   // px
+      tma_bulk_g2s(dst + (size_t)np_loc * 16, src + (size_t)np * 16 + (size_t)fbase * 24, (uint32_t)np_loc * 24u, &s.mbar);  // f
+      tma_bulk_g2s(dst + (size_t)np_loc * 40, src + (size_t)np * 40 + (size_t)fbase * 24, (uint32_t)np_loc * 24u, &s.mbar);  // pos
+      tma_bulk_g2s(dst + (size_t)np_loc * 64, src + (size_t)np * 64 + (size_t)fbase, (uint32_t)np_loc, &s.mbar);             // has_point
+    } else {
+      mbar_arrive(&s.mbar);  // a CTA without features still completes use 0 of the barrier: the phase parities of the image copies stay in step
+    }
   }
   __syncthreads();
   mbar_wait(&s.mbar, 0);
   const uint8_t* blob = reinterpret_cast<const uint8_t*>(pat_ref);
-  const double* b_px = reinterpret_cast<const double*>(blob);
-  const double* b_f = b_px + 2 * np;
-  const double* b_pos = b_f + 3 * np;
-  const uint8_t* b_hp = reinterpret_cast<const uint8_t*>(b_pos + 3 * np);
+  const double* b_f = reinterpret_cast<const double*>(blob) + 2 * np_loc;
+  const double* b_pos = b_f + 3 * np_loc;
+  const uint8_t* b_hp = reinterpret_cast<const uint8_t*>(b_pos + 3 * np_loc);
 
   // per-feature register state
   double fx_[FPT], fy_[FPT], fz_[FPT], fzi_[FPT];
+  int wx_[FPT], wy_[FPT];  // origin of the feature's current-image window (kModeWindow)
   unsigned hp_mask = 0, vis_mask = 0, in_mask = 0;
 #pragma unroll
   for (int k = 0; k < FPT; ++k) {
     const int i = tid + k * T;
     fx_[k] = fy_[k] = 0.0; fz_[k] = fzi_[k] = 1.0;
-    if (i < N) {
+    wx_[k] = wy_[k] = -(1 << 20);
+    if (i < n_loc) {
       const double dxp = b_pos[3 * i] - job.ref_pos[0], dyp = b_pos[3 * i + 1] - job.ref_pos[1],
                    dzp = b_pos[3 * i + 2] - job.ref_pos[2];
       const double depth = sqrt(dxp * dxp + dyp * dyp + dzp * dzp);  // :107  |pos - ref_pos|
@@ -350,32 +488,64 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       fz_[k] = b_f[3 * i + 2] * depth;
       fzi_[k] = 1.0 / fz_[k];
       if (b_hp[i]) hp_mask |= 1u << k;
-      if (EVAL && P.visible_in[i]) vis_mask |= 1u << k;
+      if (EVAL && P.visible_in[fbase + i]) vis_mask |= 1u << k;
     }
   }
-  __syncthreads();  // everyone is done with the staged blob; the patch arrays may be written
+  // solver state every thread carries (uniform over the pair): chi2_ and stop_ of NLLSSolver (reset(): 1e10 / false
+  // [EXT]), the running iteration counter that selects the state / partial-sum buffers, and the current pose
+  double chi2_prev = 1e10;
+  int stop = 0;
+  unsigned g = 0;
+  double R[9], t[3];
+  {
+    const Pose m0 = pose_from_rt12(job.T);  // same arithmetic as thread 0's s.st[0].model
+    qmatrix(m0.q, R);
+    t[0] = m0.t[0]; t[1] = m0.t[1]; t[2] = m0.t[2];
+    if (CS == 1 && tid == 0) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) s.pub[k] = R[k];
+      s.pub[9] = t[0]; s.pub[10] = t[1]; s.pub[11] = t[2];
+      s.pub_done = 0; s.pub_slow = 0;
+    }
+  }
+  pair_sync<CS>();  // everyone is done with the staged blob (the patch arrays may be written) and, in the cluster
+                    // variant, every CTA's shared memory is initialised before remote stores arrive
 
   const int lvl_hi = EVAL ? P.eval_level : P.max_level;
   const int lvl_lo = EVAL ? P.eval_level : P.min_level;
   for (int level = lvl_hi; level >= lvl_lo; --level) {
     const int W = P.w[level], Hh = P.h[level];
     const float scale = 1.0f / (float)(1 << level);
-    const double jscale = P.fx / (double)(1 << level);  // focal_length / (1<<level_)  (:140)
+    const double jscale = P.cam.fx / (double)(1 << level);  // focal_length / (1<<level_)  (:140)
     const uint8_t* ref_img = job.ref_lvl[level];
     const uint8_t* cur_img = job.cur_lvl[level];
 
-    // ---- TMA: stage the current level image when it fits the staging region -----------------
+    // ---- how the current image of this level reaches the residual loop --------------------------
     const uint32_t img_bytes = ((uint32_t)(W * Hh) + 15u) & ~15u;
-    const bool staged = !EVAL && img_bytes + 16u <= (uint32_t)P.stage_cap;
-    if (staged && tid == 0) {
+    int mode = kModeGlobal;
+    if (img_bytes + 16u <= (uint32_t)P.stage_cap) mode = kModeImage;
+    else if (P.use_windows && (W & 7) == 0 && kWinBytes * S <= P.stage_cap) mode = kModeWindow;
+    if (mode == kModeImage && tid == 0) {
       s.mbar_phase ^= 1u;
       fence_proxy_async();
       mbar_expect_tx(&s.mbar, img_bytes);
       tma_bulk_g2s(stage, cur_img, img_bytes, &s.mbar);
     }
+    if (cta_leader) s.st[g & 1u].old_model = s.st[g & 1u].model;  // optimizeGaussNewton: ModelType old_model(model) [EXT]
+    if constexpr (CS == 1) {
+      // the pose lives in shared memory between uses: re-reading it here keeps 24 registers free during the residual loops
+#pragma unroll
+      for (int k = 0; k < 9; ++k) R[k] = s.pub[k];
+      t[0] = s.pub[9]; t[1] = s.pub[10]; t[2] = s.pub[11];
+    }
+    // next level: pull its current image (coarse levels, staged whole) into L2 while this level iterates
+    if (P.use_prefetch && tid == 0 && crank == 0 && level > lvl_lo) {
+      const uint32_t nb = ((uint32_t)(P.w[level - 1] * P.h[level - 1]) + 15u) & ~15u;
+      if (nb + 16u <= (uint32_t)P.stage_cap) prefetch_l2_bulk(job.cur_lvl[level - 1], nb);
+    }
 
-    long long tq0 = 0;
-    if ((SVO_SIA_DEBUG && P.debug) && tid == 0) tq0 = clock64();
+    SIA_DBG(long long tq0 = 0;)
+      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) tq0 = clock64();)
     // ---- precomputeReferencePatches (:84-145), one feature per thread -----------------------
     double m_sxx[FPT], m_sxy[FPT], m_syy[FPT], m_cnt[FPT];
 #pragma unroll
@@ -383,15 +553,59 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       m_sxx[k] = m_sxy[k] = m_syy[k] = m_cnt[k] = 0.0;
       const int slot = tid + k * T;
       // px is re-read from the pair's blob in global memory (L2) once per level instead of living in registers
-      const double2 pxy = slot < N ? __ldg(reinterpret_cast<const double2*>(job.blob) + slot) : make_double2(-1e6, -1e6);
+      const double2 pxy = slot < n_loc ? __ldg(reinterpret_cast<const double2*>(job.blob) + fbase + slot) : make_double2(-1e6, -1e6);
       const float u_ref = (float)(pxy.x * (double)scale);
       const float v_ref = (float)(pxy.y * (double)scale);
       const bool rng = u_ref >= 0.f && v_ref >= 0.f && u_ref < 1e6f && v_ref < 1e6f;  // else: outside, floor not needed
       float ufl = 0.f, vfl = 0.f;
       const int ui = rng ? floor_pos(u_ref, ufl) : -1, vi = rng ? floor_pos(v_ref, vfl) : -1;
       const bool ok = ((hp_mask >> k) & 1u) && ui - 3 >= 0 && vi - 3 >= 0 && ui + 3 < W && vi + 3 < Hh;
+      // all seven footprint rows are requested before anything else: one exposed L2/HBM latency per level
+      uint32_t rlo[7], rhi[7];
       if (ok) {
         vis_mask |= 1u << k;
+#pragma unroll
+        for (int r = 0; r < 7; ++r) fetch7_g64(ref_img, (vi - 3 + r) * W + (ui - 3), rlo[r], rhi[r]);
+      }
+      // ---- current-image window of this feature (fine levels): projected with the pose the level starts from
+      wx_[k] = wy_[k] = -(1 << 20);
+      if (((vis_mask >> k) & 1u) && mode == kModeWindow) {
+        const double x = fx_[k], y = fy_[k], z = fz_[k];
+        const double xc = fma(R[0], x, fma(R[1], y, fma(R[2], z, t[0])));
+        const double yc = fma(R[3], x, fma(R[4], y, fma(R[5], z, t[1])));
+        const double zc = fma(R[6], x, fma(R[7], y, fma(R[8], z, t[2])));
+        const double rz = fast_rcp(zc);
+        double ud, vd;
+        cam_world2cam(P.cam, div_rn(xc, zc, rz), div_rn(yc, zc, rz), ud, vd);
+        const float u0 = __fmul_rn((float)ud, scale), v0 = __fmul_rn((float)vd, scale);
+        if (u0 >= 0.f && v0 >= 0.f && u0 < 1e6f && v0 < 1e6f) {
+          float tmp;
+          const int cu = floor_pos(__fadd_rn(u0, 0.5f), tmp), cv = floor_pos(__fadd_rn(v0, 0.5f), tmp);
+          if (mode == kModeWindow) {
+            // 16 columns x 8 rows around (round(u), round(v)): the 5x5 footprint stays inside for at least +-1.5 px of
+            // drift.  One 16-byte cp.async per row when columns round(u)-4 .. round(u)+3 fall into one 16-byte aligned
+            // block (and the pitch keeps every row 16-byte aligned), else two 8-byte copies from the 8-byte aligned column.
+            const int c4 = cu - 4, wy = cv - 4;
+            const bool one = ((c4 & 15) <= 8) && (W & 15) == 0;
+            const int wx = one ? (c4 & ~15) : (c4 & ~7);
+            if (wx >= 0 && wy >= 0 && wx + 16 <= W && wy + kWinRows <= Hh) {
+              wx_[k] = wx; wy_[k] = wy;
+              const uint8_t* src = cur_img + (size_t)wy * W + wx;
+              if (one) {
+#pragma unroll
+                for (int r = 0; r < kWinRows; ++r) cp_async16(win + r * S + slot, src + (size_t)r * W);
+              } else {
+#pragma unroll
+                for (int r = 0; r < kWinRows; ++r) {
+                  cp_async8(reinterpret_cast<uint8_t*>(win + r * S + slot), src + (size_t)r * W);
+                  cp_async8(reinterpret_cast<uint8_t*>(win + r * S + slot) + 8, src + (size_t)r * W + 8);
+                }
+              }
+            }
+          }
+        }
+      }
+      if (ok) {
         float wtl, wtr, wbl, wbr;
         bilin_weights(__fsub_rn(u_ref, ufl), __fsub_rn(v_ref, vfl), wtl, wtr, wbl, wbr);
         // 7x7 footprint rows vi-3..vi+3, cols ui-3..ui+3, streamed row by row to keep the register
@@ -399,11 +613,6 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         // r, r+1; patch row y needs Bq rows y, y+1, y+2.
         float pr0[7], pr1[7], b0[6], b1[6], b2[6];
         double sxx = 0, sxy = 0, syy = 0;
-        // all seven footprint rows are requested before the first use: one exposed L2/HBM latency per level instead
-        // of seven dependent ones
-        uint32_t rlo[7], rhi[7];
-#pragma unroll
-        for (int r = 0; r < 7; ++r) fetch12<false>(ref_img, (vi - 3 + r) * W + (ui - 3), rlo[r], rhi[r]);
         auto load_row = [&](int r, float (&dst)[7]) {
           const uint32_t lo = rlo[r], hi = rhi[r];
           dst[0] = byte_to_float<0>(lo); dst[1] = byte_to_float<1>(lo); dst[2] = byte_to_float<2>(lo);
@@ -446,7 +655,9 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         m_cnt[k] = 1.0;
       }
     }
-    block_sum_h_to_warp0<FPT>(
+    SIA_DBG(long long tq1 = 0;)
+      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { tq1 = clock64(); s.tk[7] += tq1 - tq0; })
+    pair_sum_h_to_warp0<FPT, CS, SH>(
         [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
           x = fx_[k]; y = fy_[k]; zi = fzi_[k]; sxx = m_sxx[k]; sxy = m_sxy[k]; syy = m_syy[k]; cnt = m_cnt[k];
           // opaque to the optimiser: otherwise the level-invariant Jacobian rows are hoisted out of the level loop and
@@ -454,37 +665,24 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           asm volatile("" : "+d"(x), "+d"(y), "+d"(zi));
         },
         s, nwarps);
-    if (tid == 0) {
-      if (SVO_SIA_DEBUG && P.debug) s.tk[0] += clock64() - tq0;
-      s.sum_vis += (int)s.sums[21];
-      s.done = 0;
+    // The scaling and LDL^T factorisation of this level's H is serial work nobody needs before the first solve: warp 0
+    // does it while the other warps already run the first residual pass; its results (s.sol_tot, s.Htot) become
+    // visible to everybody through the barrier of that pass.
+    SIA_DBG(long long tq2 = 0;)
+      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { tq2 = clock64(); s.tkx[0] += tq2 - tq1; })
+    if (warp == 0) {
+      if (leader) s.sum_vis += (int)s.sums[21];
+      warp0_scale_and_factor(s, jscale * jscale, s.Htot, s.sol_tot);
     }
-    if (staged) mbar_wait(&s.mbar, s.mbar_phase);
-    __syncthreads();
-    // The scaling and LDL^T factorisation of this level's H is serial work nobody needs before the first solve: the
-    // last thread of the block (a spare lane whenever the pair has fewer features than slots) does it while the other
-    // warps already run the first residual pass; it rejoins its warp at the pass reduction, i.e. before the
-    // iteration's first __syncthreads, after which thread 0 reads s.sol_tot.
-    if (tid == T - 1) {
-      long long tq1 = 0;
-      if (SVO_SIA_DEBUG && P.debug) tq1 = clock64();
-      const double s2 = jscale * jscale;
-      int idx = 0;
-      for (int r = 0; r < 6; ++r)
-        for (int c = r; c < 6; ++c, ++idx) {
-          const double v = s.sums[idx] * s2;
-          s.Htot[r * 6 + c] = v;
-          s.Htot[c * 6 + r] = v;
-        }
-      solver_factor(s.sol_tot, s.Htot);
-      if (SVO_SIA_DEBUG && P.debug) s.tk[1] += clock64() - tq1;
-    }
+    if (mode == kModeImage) mbar_wait(&s.mbar, s.mbar_phase);
+    if (mode == kModeWindow) cp_async_wait_all();  // each thread reads only the window it copied itself
+      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { s.tk[0] += clock64() - tq0; s.tkx[1] += clock64() - tq2; })
 
     // ---- Gauss-Newton iterations at this level ---------------------------------------------
     const int n_iter = EVAL ? 1 : P.n_iter;
     for (int iter = 0; iter < n_iter; ++iter) {
-      long long ti0 = 0;
-      if ((SVO_SIA_DEBUG && P.debug) && tid == 0) ti0 = clock64();
+      SIA_DBG(long long ti0 = 0;)
+      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) ti0 = clock64();)
       double acc[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) acc[k] = 0.0;
@@ -494,15 +692,13 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       for (int k = 0; k < FPT; ++k) {
         if (!((vis_mask >> k) & 1u)) continue;
         const int slot = tid + k * T;
-        long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0;
-        if ((SVO_SIA_DEBUG && P.debug) && tid == 0) tp0 = clock64();
         const double x = fx_[k], y = fy_[k], z = fz_[k];
-        const double xc = fma(s.R[0], x, fma(s.R[1], y, fma(s.R[2], z, s.t[0])));
-        const double yc = fma(s.R[3], x, fma(s.R[4], y, fma(s.R[5], z, s.t[1])));
-        const double zc = fma(s.R[6], x, fma(s.R[7], y, fma(s.R[8], z, s.t[2])));
+        const double xc = fma(R[0], x, fma(R[1], y, fma(R[2], z, t[0])));
+        const double yc = fma(R[3], x, fma(R[4], y, fma(R[5], z, t[1])));
+        const double zc = fma(R[6], x, fma(R[7], y, fma(R[8], z, t[2])));
         const double rz = fast_rcp(zc);
-        const double ud = fma(P.fx, xc * rz, P.cx);  // [EXT] world2cam: fx * (x/z) + cx
-        const double vd = fma(P.fy, yc * rz, P.cy);
+        double ud, vd;
+        cam_world2cam(P.cam, div_rn(xc, zc, rz), div_rn(yc, zc, rz), ud, vd);  // [EXT] world2cam(project2d(xyz))
         const float u_cur = __fmul_rn((float)ud, scale);  // .cast<float>() * scale (:183)
         const float v_cur = __fmul_rn((float)vd, scale);
         // negative / non-finite / huge coordinates can never pass the border test (:190)
@@ -514,25 +710,38 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           ++n_out_t;
           if (EVAL) {
             for (int p = 0; p < kPatchArea; ++p)
-              P.residuals_out[(size_t)slot * kPatchArea + p] = __int_as_float(0x7fc00000);
+              P.residuals_out[(size_t)(fbase + slot) * kPatchArea + p] = __int_as_float(0x7fc00000);
           }
           continue;
         }
         in_mask |= 1u << k;
         ++n_in_t;
-        if ((SVO_SIA_DEBUG && P.debug) && tid == 0) tp1 = clock64();
         float wtl, wtr, wbl, wbr;
         bilin_weights(__fsub_rn(u_cur, ufl), __fsub_rn(v_cur, vfl), wtl, wtr, wbl, wbr);
         uint32_t lo[5], hi[5];
+        if (mode == kModeImage) {
 #pragma unroll
-        for (int r = 0; r < 5; ++r) {
-          const int off = (vi - 2 + r) * W + (ui - 2);
-          if (staged) fetch8<true>(stage, off, lo[r], hi[r]);
-          else fetch8<false>(cur_img, off, lo[r], hi[r]);
+          for (int r = 0; r < 5; ++r) fetch8<true>(stage, (vi - 2 + r) * W + (ui - 2), lo[r], hi[r]);
+        } else {
+          const int c0 = (ui - 2) - wx_[k], r0 = (vi - 2) - wy_[k];
+          if (mode == kModeWindow && (unsigned)c0 <= 11u && (unsigned)r0 <= (unsigned)(kWinRows - 5)) {
+            const uint4* wp = win + r0 * S + slot;
+            const int kw = c0 >> 2;  // 0..2: the footprint row starts in word kw of the 16-byte window row
+            const unsigned sh = (unsigned)(c0 & 3) * 8u;
+#pragma unroll
+            for (int r = 0; r < 5; ++r) {
+              const uint4 q = wp[r * S];
+              const uint32_t w0 = kw == 0 ? q.x : kw == 1 ? q.y : q.z, w1 = kw == 0 ? q.y : kw == 1 ? q.z : q.w;
+              lo[r] = __funnelshift_r(w0, w1, sh);
+              hi[r] = w1 >> sh;
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < 5; ++r) fetch8<false>(cur_img, (vi - 2 + r) * W + (ui - 2), lo[r], hi[r]);
+          }
         }
         float c2 = 0.f, gx = 0.f, gy = 0.f;
         float q0[5], q1[5];
-        if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { tp2 = clock64() + (long long)(lo[4] & 0u); }
         q0[0] = byte_to_float<0>(lo[0]); q0[1] = byte_to_float<1>(lo[0]); q0[2] = byte_to_float<2>(lo[0]);
         q0[3] = byte_to_float<3>(lo[0]); q0[4] = byte_to_float<0>(hi[0]);
 #pragma unroll
@@ -544,16 +753,15 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
             const int p = yy * 4 + xx;
             const float I = bilin(wtl, wtr, wbl, wbr, q0[xx], q0[xx + 1], q1[xx], q1[xx + 1]);
             const float res = __fsub_rn(I, pat_ref[p * S + slot]);
-            const float2 g = pat_dxy[p * S + slot];
+            const float2 gr = pat_dxy[p * S + slot];
             c2 = fmaf(res, res, c2);  // chi2 += res*res*weight, weight == 1 (:222); order differs from the serial sum anyway
-            gx = fmaf(g.x, res, gx);
-            gy = fmaf(g.y, res, gy);
-            if (EVAL) P.residuals_out[(size_t)slot * kPatchArea + p] = res;
+            gx = fmaf(gr.x, res, gx);
+            gy = fmaf(gr.y, res, gy);
+            if (EVAL) P.residuals_out[(size_t)(fbase + slot) * kPatchArea + p] = res;
           }
 #pragma unroll
           for (int c = 0; c < 5; ++c) q0[c] = q1[c];
         }
-        if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { tp3 = clock64() + (long long)(__float_as_int(gx) & 0); s.tk[6] += tp1 - tp0; s.tk[7] += tp2 - tp1; s.tk[0] += 0; }
         const double zi = fzi_[k], X = x * zi, Y = y * zi, dgx = (double)gx, dgy = (double)gy;
         acc[0] = fma(-zi, dgx, acc[0]);
         acc[1] = fma(-zi, dgy, acc[1]);
@@ -562,35 +770,50 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         acc[4] = fma(-fma(X, X, 1.0), dgx, fma(-(X * Y), dgy, acc[4]));
         acc[5] = fma(Y, dgx, fma(-X, dgy, acc[5]));
         acc[6] += (double)c2;
-        if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { s.tkx[0] += tp3 - tp2; s.tkx[1] += clock64() - tp3 + (long long)(acc[5] != acc[5]); }
       }
-      int n_in, n_out;
-      long long ti1 = 0;
-      if ((SVO_SIA_DEBUG && P.debug) && tid == 0) ti1 = clock64();
-      block_sum8_to_warp0(acc, n_in_t, n_out_t, s, nwarps, n_in, n_out);  // first __syncthreads of the iteration
-      if (tid == 0) {
-        long long ti2 = 0;
-        if (SVO_SIA_DEBUG && P.debug) { ti2 = clock64(); s.tk[2] += ti1 - ti0; s.tk[3] += ti2 - ti1; }
-        for (int k = 0; k < 6; ++k) s.x[k] = -(s.sums[k] * jscale);  // Jres_ = -sum J r
-        s.keep_chi2 = s.sums[6];
-        s.keep_n_in = n_in;
-        s.slow = (EVAL || (n_out > 0 && n_in > 0)) ? 1 : 0;
-        if (!s.slow) {
-          if (n_in == 0) {  // H_ == 0 exactly: Eigen's LDLT yields x = 0
-            for (int k = 0; k < 36; ++k) s.Hs[k] = 0.0;
-            s.h_is_tot = 0;
-            gn_finish(s, P.eps, P.trace, P.trace_cap, nullptr, level, iter, s.sums[6], n_in);
-          } else {
-            s.h_is_tot = 1;
-            gn_finish(s, P.eps, P.trace, P.trace_cap, &s.sol_tot, level, iter, s.sums[6], n_in);
-          }
+      SIA_DBG(long long ti1 = 0;)
+      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) ti1 = clock64();)
+
+      // ---- pair-wide sums: per-warp transposed reduction, one shared-memory hop, ONE barrier; then every warp adds
+      //      the per-warp partials in the same order (bit-identical totals everywhere)
+      const unsigned buf = g & 1u;
+      warp_reduce_t<8>(acc);
+      const int w_in = __reduce_add_sync(0xffffffffu, n_in_t), w_out = __reduce_add_sync(0xffffffffu, n_out_t);
+      const int gw = (int)crank * nwarps + warp;  // warp index within the pair
+      if constexpr (CS == 1) {
+        if ((lane & 3) == 0) s.part[buf][gw][lane >> 2] = acc[0];
+        if (lane == 0) { s.cnt[buf][gw][0] = w_in; s.cnt[buf][gw][1] = w_out; }
+      } else {
+        // every CTA of the cluster receives every warp's partials (distributed shared memory stores)
+        if ((lane & 3) == 0) {
+#pragma unroll
+          for (int r = 0; r < CS; ++r) st_cluster_f64(&s.part[buf][gw][lane >> 2], (unsigned)r, acc[0]);
         }
-        if (SVO_SIA_DEBUG && P.debug) s.tk[4] += clock64() - ti2;
+        if (lane == 0) {
+#pragma unroll
+          for (int r = 0; r < CS; ++r) st_cluster_v2s32(&s.cnt[buf][gw][0], (unsigned)r, w_in, w_out);
+        }
       }
-      __syncthreads();
-      if (s.slow) {
-        // some visible patches fell outside the current image (or EVAL wants H): H_ = sum over the
-        // patches that contributed in this pass.
+      pair_sync<CS>();  // barrier A: every warp's partial sums are in place
+      const int nw_pair = nwarps * CS;
+      double tot[7];
+      int n_in = 0, n_out = 0, done = 0;
+      auto compute_totals = [&]() {
+        const int kk = lane & 7;
+        double a = 0.0;
+        for (int wv = lane >> 3; wv < nw_pair; wv += 4) a += s.part[buf][wv][kk];
+        a += __shfl_xor_sync(0xffffffffu, a, 8);
+        a += __shfl_xor_sync(0xffffffffu, a, 16);
+#pragma unroll
+        for (int e = 0; e < 7; ++e) tot[e] = __shfl_sync(0xffffffffu, a, e);
+        int ci = 0, co = 0;
+        for (int wv = lane; wv < nw_pair; wv += 32) { ci += s.cnt[buf][wv][0]; co += s.cnt[buf][wv][1]; }
+        n_in = __reduce_add_sync(0xffffffffu, ci);
+        n_out = __reduce_add_sync(0xffffffffu, co);
+      };
+      // some visible patches fell outside the current image (or EVAL wants H): H_ = sum over the patches that
+      // contributed in this pass ("slow path"; all threads, one block barrier inside)
+      auto slow_sum_h = [&]() {
         double q_sxx[FPT], q_sxy[FPT], q_syy[FPT];
 #pragma unroll
         for (int k = 0; k < FPT; ++k) {
@@ -599,84 +822,154 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           const int slot = tid + k * T;
 #pragma unroll
           for (int p = 0; p < kPatchArea; ++p) {
-            const float2 g = pat_dxy[p * S + slot];
-            const double dx = (double)g.x, dy = (double)g.y;
+            const float2 gr = pat_dxy[p * S + slot];
+            const double dx = (double)gr.x, dy = (double)gr.y;
             q_sxx[k] = fma(dx, dx, q_sxx[k]);
             q_sxy[k] = fma(dx, dy, q_sxy[k]);
             q_syy[k] = fma(dy, dy, q_syy[k]);
           }
         }
-        block_sum_h_to_warp0<FPT>(
+        pair_sum_h_to_warp0<FPT, CS, SH>(
             [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
               x = fx_[k]; y = fy_[k]; zi = fzi_[k]; sxx = q_sxx[k]; sxy = q_sxy[k]; syy = q_syy[k]; cnt = 0.0;
               asm volatile("" : "+d"(x), "+d"(y), "+d"(zi));  // see the per-level call: no hoisting into local memory
             },
             s, nwarps);
-        if (tid == 0) {
-          const double s2 = jscale * jscale;
-          int idx = 0;
-          s.h_is_tot = 0;
-          for (int r = 0; r < 6; ++r)
-            for (int c = r; c < 6; ++c, ++idx) {
-              const double v = s.sums[idx] * s2;
-              s.Hs[r * 6 + c] = v;
-              s.Hs[c * 6 + r] = v;
-            }
-          const double chi2_keep = s.keep_chi2;
-          const int n_in_keep = s.keep_n_in;
-          if (EVAL) {
-            for (int k = 0; k < 6; ++k) P.Jres_out[k] = s.x[k];
-            const float chi2f = (float)chi2_keep;
-            *P.chi2_out = (double)(chi2f / (float)(n_in_keep * kPatchArea));
-            *P.n_meas_out = (long long)n_in_keep * kPatchArea;
-            s.n_in_last = n_in_keep;
-            s.done = 1;
-          } else {
-            solver_factor(s.sol_cur, s.Hs);
-            gn_finish(s, P.eps, P.trace, P.trace_cap, &s.sol_cur, level, iter, chi2_keep, n_in_keep);
+      };
+      auto eval_outputs = [&]() {  // EVAL, leader: computeResiduals' scalar outputs
+        for (int k = 0; k < 6; ++k) P.Jres_out[k] = -(tot[k] * jscale);
+        const float chi2f = (float)tot[6];
+        *P.chi2_out = (double)(chi2f / (float)(n_in * kPatchArea));
+        *P.n_meas_out = (long long)n_in * kPatchArea;
+        s.n_in_last = n_in;
+      };
+      auto fast_path_solver = [&]() -> const Solver6* {  // every visible patch contributed: H_ is the level's H
+        if (n_in == 0) {  // H_ == 0 exactly: Eigen's LDLT yields x = 0
+          if (leader) {
+            for (int k = 0; k < 36; ++k) s.Hs[k] = 0.0;
+            s.h_is_tot = 0;
           }
+          return nullptr;
         }
-        __syncthreads();
+        if (leader) s.h_is_tot = 1;
+        return &s.sol_tot;
+      };
+      SIA_DBG(long long ti2 = 0;)
+      if constexpr (CS == 1) {
+        // One CTA per pair: warp 0 alone adds the per-warp partials and runs the Gauss-Newton tail, then publishes the
+        // new pose through shared memory (barrier B); the other warps would only replicate that work on the same SM.
+        bool slow = false;
+        if (warp == 0) {
+          compute_totals();
+      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { ti2 = clock64(); s.tk[1] += ti1 - ti0; s.tk[2] += ti2 - ti1; })
+          slow = EVAL || (n_out > 0 && n_in > 0);
+          if (!slow) {
+            const Solver6* S6 = fast_path_solver();
+            gn_tail(s, g, S6, tot, jscale, n_in, iter, level, P.eps, cta_leader, leader, P.trace, P.trace_cap, chi2_prev, stop,
+                    done, R, t);
+            if (lane == 0) {
+#pragma unroll
+              for (int k = 0; k < 9; ++k) s.pub[k] = R[k];
+              s.pub[9] = t[0]; s.pub[10] = t[1]; s.pub[11] = t[2];
+              s.pub_done = done;
+            }
+          }
+          if (lane == 0) s.pub_slow = slow ? 1 : 0;
+        }
+        __syncthreads();  // barrier B
+        if (s.pub_slow) {
+          slow_sum_h();
+          if (warp == 0) {
+            warp0_scale_and_factor(s, jscale * jscale, s.Hs, s.sol_cur);
+            if (leader) s.h_is_tot = 0;
+            if (EVAL) {
+              if (leader) eval_outputs();
+            } else {
+              gn_tail(s, g, &s.sol_cur, tot, jscale, n_in, iter, level, P.eps, cta_leader, leader, P.trace, P.trace_cap,
+                      chi2_prev, stop, done, R, t);
+              if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k) s.pub[k] = R[k];
+                s.pub[9] = t[0]; s.pub[10] = t[1]; s.pub[11] = t[2];
+                s.pub_done = done;
+              }
+            }
+          }
+          __syncthreads();  // barrier C
+        }
+        if (!EVAL) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) R[k] = s.pub[k];
+          t[0] = s.pub[9]; t[1] = s.pub[10]; t[2] = s.pub[11];
+          done = s.pub_done;
+        }
+      } else {
+        // Cluster per pair: every warp of every CTA adds the partials in the same order and runs the tail redundantly in
+        // registers (bit-identical everywhere), which saves a second cluster barrier + DSMEM broadcast per iteration.
+        compute_totals();
+      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { ti2 = clock64(); s.tk[1] += ti1 - ti0; s.tk[2] += ti2 - ti1; })
+        const Solver6* S6;
+        const bool slow = EVAL || (n_out > 0 && n_in > 0);
+        if (!slow) {
+          S6 = fast_path_solver();
+        } else {
+          slow_sum_h();
+          if (warp == 0) {
+            warp0_scale_and_factor(s, jscale * jscale, s.Hs, s.sol_cur);
+            if (leader) s.h_is_tot = 0;
+          }
+          if (EVAL && leader) eval_outputs();
+          __syncthreads();  // s.sol_cur is visible to every warp of this CTA (each CTA factorised its own copy)
+          S6 = &s.sol_cur;
+        }
+        if (!EVAL)
+          gn_tail(s, g, S6, tot, jscale, n_in, iter, level, P.eps, cta_leader, leader, P.trace, P.trace_cap, chi2_prev, stop,
+                  done, R, t);
       }
       if (EVAL) {
 #pragma unroll
         for (int k = 0; k < FPT; ++k) {
           const int i = tid + k * T;
-          if (i < N) {
-            P.in_image_out[i] = (in_mask >> k) & 1u;
+          if (i < n_loc) {
+            P.in_image_out[fbase + i] = (in_mask >> k) & 1u;
             if (!((vis_mask >> k) & 1u))
               for (int p = 0; p < kPatchArea; ++p)
-                P.residuals_out[(size_t)i * kPatchArea + p] = __int_as_float(0x7fc00000);
+                P.residuals_out[(size_t)(fbase + i) * kPatchArea + p] = __int_as_float(0x7fc00000);
             for (int p = 0; p < kPatchArea; ++p)
-              P.ref_patch_out[(size_t)i * kPatchArea + p] = pat_ref[p * S + i];
+              P.ref_patch_out[(size_t)(fbase + i) * kPatchArea + p] = pat_ref[p * S + i];
           }
         }
+        break;
       }
-      if (s.done) break;
+      ++g;
+      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) s.tk[3] += clock64() - ti2;)
+      if (done) break;
     }
-    __syncthreads();  // stage region / patches are rewritten by the next level
+    pair_sync<CS>();  // stage region / patches are rewritten by the next level; the leader's state writes are visible
   }
 
   // ---- outputs ---------------------------------------------------------------------------------
 #pragma unroll
   for (int k = 0; k < FPT; ++k) {
     const int i = tid + k * T;
-    if (i < N && P.visible_out) P.visible_out[job.feat_off + i] = (vis_mask >> k) & 1u;
+    if (i < n_loc && P.visible_out) P.visible_out[job.feat_off + fbase + i] = (vis_mask >> k) & 1u;
   }
-  if (tid == 0) {
-    if (P.T_out) pose_to_rt12(s.model, P.T_out + 12 * (size_t)blockIdx.x);
+  if (leader) {
+    if (P.T_out) pose_to_rt12(s.st[g & 1u].model, P.T_out + 12 * (size_t)pair);
     if (P.H_out)
-      for (int k = 0; k < 36; ++k) P.H_out[36 * (size_t)blockIdx.x + k] = s.h_is_tot ? s.Htot[k] : s.Hs[k];
+      for (int k = 0; k < 36; ++k) P.H_out[36 * (size_t)pair + k] = s.h_is_tot ? s.Htot[k] : s.Hs[k];
     if (P.stats) {
       svo_b200_sia_stats st;
       st.n_iters = s.n_iters; st.sum_visible = s.sum_vis; st.sum_in_image = s.sum_in;
       st.n_tracked = s.n_in_last;  // n_meas_/patch_area_ of the last pass (:74)
-      P.stats[blockIdx.x] = st;
+      P.stats[pair] = st;
     }
     if (P.n_trace) *P.n_trace = s.n_trace;
-    if (SVO_SIA_DEBUG && P.debug && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2 || blockIdx.x == gridDim.x - 1))
-      printf("[sia dbg] cta %d iters %d cycles: pre_par %lld pre_ser %lld pass %lld reduce %lld serial %lld total %lld | t0: geom %lld wts+ld %lld pix %lld acc %lld\n", blockIdx.x,
-             s.n_iters, s.tk[0], s.tk[1], s.tk[2], s.tk[3], s.tk[4], (long long)clock64() - s.tk[5], s.tk[6], s.tk[7], s.tkx[0], s.tkx[1]);
+#if SVO_SIA_DEBUG
+    if (SVO_SIA_DEBUG && P.debug && (pair == 0 || pair == (int)(gridDim.x / CS) / 2 || pair == (int)(gridDim.x / CS) - 1))
+      printf("[sia dbg] pair %d iters %d cycles: setup %lld pass %lld reduce %lld tail %lld (solve %lld update %lld) total %lld | setup parts: loads+patches %lld hsum %lld factor+wait %lld\n", pair, s.n_iters,
+             s.tk[0], s.tk[1], s.tk[2], s.tk[3], s.tk[5], s.tk[6], (long long)clock64() - s.tk[4], s.tk[7], s.tkx[0], s.tkx[1]);
+#endif
   }
 }
 
@@ -689,45 +982,104 @@ struct SiaBatchState {
   int max_feat = 0;
   SiaParams P;
   size_t in_bytes = 0;
-  // device output offsets inside ctx->d_out
+  // The batch API owns its staging buffers: stage / run / fetch may be interleaved with any other entry point of the
+  // context (align, pose optimizer, depth filter ... reuse the context's generic scratch) without clobbering a staged
+  // batch.
+  DevBuf d_in, d_out;
+  HostBuf h_in, h_out;
   size_t o_T = 0, o_H = 0, o_vis = 0, o_stats = 0, out_bytes = 0;
-  int threads = 0, fpt = 1;
+  int threads = 0, fpt = 1, cluster = 1;
   size_t smem = 0;
   bool staged = false;
 };
 
 void sia_batch_free(svo_b200_ctx* ctx) {
+  if (ctx->sia) {
+    if (ctx->sia->d_in.p) cudaFree(ctx->sia->d_in.p);
+    if (ctx->sia->d_out.p) cudaFree(ctx->sia->d_out.p);
+    if (ctx->sia->h_in.p) cudaFreeHost(ctx->sia->h_in.p);
+    if (ctx->sia->h_out.p) cudaFreeHost(ctx->sia->h_out.p);
+  }
   delete ctx->sia;
   ctx->sia = nullptr;
 }
 
-static int g_sia_spare = 0;     // env SVO_B200_SIA_SPARE=1 (experimental): 352-thread CTAs for <= 320 features, so that the last warp owns
-                                // no feature and the per-level LDL^T truly overlaps the first residual pass
-static int g_sia_minb = 2;      // tuning knobs (env SVO_B200_SIA_MINB / SVO_B200_SIA_STAGE_KB), read once
-static int g_sia_stage_kb = 20;
+// tuning knobs, read once from the environment (defaults are the measured best)
+static int g_sia_minb = 2;        // SVO_B200_SIA_MINB: resident CTAs per SM the <=320-feature kernel is compiled for
+static int g_sia_stage_kb = 20;   // SVO_B200_SIA_STAGE_KB: minimum staging region (holds level >= 2 of 640x480)
+static int g_sia_windows = 1;     // SVO_B200_SIA_WINDOWS=0: fine levels gather from global memory instead of cp.async windows
+static int g_sia_prefetch = 1;    // SVO_B200_SIA_PREFETCH=0: no bulk L2 prefetch of the next (coarse, TMA-staged) current image.
+                                  // (Per-feature L2 prefetches of the next level's footprints were measured and removed: the extra
+                                  // uncoalesced requests cost more L1 time than the DRAM latency they hide.)
+static int g_sia_cluster = -1;    // SVO_B200_SIA_CLUSTER: force the CTAs per pair (1, 2, 4, 8); -1 = by batch size
+static int g_sia_fpt2 = 1;        // SVO_B200_SIA_FPT2: <= 320 features per CTA as 160 threads x 2 features: 1 = three CTAs per SM (default,
+                                  // measured best for full batches), 2 = two CTAs per SM with windows, 0 = 320 threads x 1 feature
 
-static int pick_launch(svo_b200_ctx* ctx, int max_feat, int& threads, int& fpt, int& stage_cap, size_t& smem) {
+static void read_env_once() {
   static bool env_read = false;
-  if (!env_read) {
-    env_read = true;
-    if (const char* e = getenv("SVO_B200_SIA_MINB")) g_sia_minb = atoi(e) == 3 ? 3 : 2;
-    if (const char* e = getenv("SVO_B200_SIA_SPARE")) g_sia_spare = atoi(e) != 0;
-    if (const char* e = getenv("SVO_B200_SIA_STAGE_KB")) g_sia_stage_kb = atoi(e) > 0 ? atoi(e) : 20;
+  if (env_read) return;
+  env_read = true;
+  if (const char* e = getenv("SVO_B200_SIA_MINB")) g_sia_minb = atoi(e) == 3 ? 3 : 2;
+  if (const char* e = getenv("SVO_B200_SIA_STAGE_KB")) g_sia_stage_kb = atoi(e) > 0 ? atoi(e) : 20;
+  if (const char* e = getenv("SVO_B200_SIA_WINDOWS")) g_sia_windows = atoi(e) != 0;
+  if (const char* e = getenv("SVO_B200_SIA_PREFETCH")) g_sia_prefetch = atoi(e) != 0;
+  if (const char* e = getenv("SVO_B200_SIA_CLUSTER")) g_sia_cluster = atoi(e);
+  if (const char* e = getenv("SVO_B200_SIA_FPT2")) g_sia_fpt2 = atoi(e);
+}
+
+// Launch geometry for a batch of B pairs with at most max_feat features each.
+//   cluster == 1: one CTA per pair, 320 / 384 / 512 threads (one feature per thread up to 512, two up to 1024);
+//   cluster  > 1: (small batches) the pair's features are split over `cluster` CTAs of 96 threads.
+static size_t sia_shared_bytes(int threads, int cluster) {
+  if (cluster == 2) return sizeof(SiaSharedT<3, 2>);
+  if (cluster == 4) return sizeof(SiaSharedT<3, 4>);
+  if (cluster == 8) return sizeof(SiaSharedT<3, 8>);
+  if (threads == 160) return sizeof(SiaSharedT<5, 1>);
+  if (threads == 320) return sizeof(SiaSharedT<10, 1>);
+  if (threads == 384) return sizeof(SiaSharedT<12, 1>);
+  return sizeof(SiaSharedT<16, 1>);
+}
+
+static int pick_launch(svo_b200_ctx* ctx, int B, int max_feat, int& threads, int& fpt, int& cluster, int& stage_cap,
+                       size_t& smem) {
+  read_env_once();
+  if (max_feat > 1024)
+    return set_err(ctx, SVO_B200_ELIMIT, "sparse_img_align: %d features per pair > 1024 (shared-memory patch cache)", max_feat);
+  cluster = 1;
+  int want = ctx->sia_cluster >= 0 ? ctx->sia_cluster : g_sia_cluster;
+  // small batch (live streams, BASELINE configs[4]'s 32 pairs per GPU): spread each pair over 4 SMs while all clusters
+  // are resident at once (2 CTAs of 96 threads per SM)
+  if (want < 0) want = (B * 4 <= 2 * ctx->sm_count) ? 4 : 1;
+  // full batches (more pairs than 2 per SM): 160 threads x 2 features, three CTAs per SM; in between, 320 x 1 with windows
+  int fpt2 = ctx->sia_fpt > 0 ? (ctx->sia_fpt == 2 ? 1 : 0) : g_sia_fpt2;
+  if (ctx->sia_fpt == 0 && B <= 2 * ctx->sm_count) fpt2 = 0;
+  if (want > 1 && max_feat <= 96 * want && (want == 2 || want == 4 || want == 8)) cluster = want;
+  if (cluster > 1) {
+    fpt = 1;
+    threads = 96;
+  } else {
+    fpt = max_feat <= 512 ? 1 : 2;
+    threads = ((max_feat + fpt - 1) / fpt + 31) / 32 * 32;
+    // the kernels are instantiated for MAXT in {320, 384, 512}; launching exactly MAXT threads makes the
+    // slot count S = MAXT*FPT a compile-time constant (immediate shared-memory offsets)
+    threads = fpt == 1 ? (threads <= 320 ? 320 : threads <= 384 ? 384 : 512) : 512;
+    if (fpt2 && max_feat <= 320) { fpt = 2; threads = 160; }
   }
-  if (max_feat <= 512) fpt = 1;
-  else if (max_feat <= 1024) fpt = 2;
-  else if (max_feat <= 2048) fpt = 4;
-  else return set_err(ctx, SVO_B200_ELIMIT, "sparse_img_align: %d features per pair > 2048", max_feat);
-  threads = ((max_feat + fpt - 1) / fpt + 31) / 32 * 32;
-  // the kernels are instantiated for MAXT in {320, 384, 512}; launching exactly MAXT threads makes the
-  // slot count S = MAXT*FPT a compile-time constant (immediate shared-memory offsets)
-  threads = fpt == 1 ? (threads <= 320 ? (g_sia_spare ? 352 : 320) : threads <= 384 ? 384 : 512) : 512;
-  const size_t base = ((sizeof(SiaShared) + 15) & ~size_t(15)) + (size_t)3 * kPatchArea * threads * fpt * sizeof(float);
-  const size_t budget = (size_t)ctx->max_smem_optin;
+  const int slots = threads * fpt;
+  const size_t base = ((sia_shared_bytes(threads, cluster) + 15) & ~size_t(15)) + (size_t)3 * kPatchArea * slots * sizeof(float);
+  // shared memory one CTA may use so that the intended number of CTAs stays resident per SM (228 KB per SM, 1 KB
+  // reserved per CTA)
+  const int resident = cluster > 1 ? 2 : (threads == 160 ? (fpt2 == 2 ? 2 : 3) : threads <= 384 ? 2 : 1);
+  size_t budget = (size_t)ctx->max_smem_optin;
+  const size_t per_cta = (size_t)(228 * 1024) / resident - 1024;
+  if (per_cta < budget) budget = per_cta;
   if (base + 1024 > budget)
     return set_err(ctx, SVO_B200_ELIMIT, "sparse_img_align: %d features need %zu B of shared memory", max_feat, base);
-  // staging region for the coarse current-level images (TMA); default 20 KB holds level >= 2 of 640x480
+  // staging region: the coarse current-level images (TMA; 20 KB holds level >= 2 of 640x480) or, at the fine levels,
+  // one 96-byte window per feature slot
   size_t cap = (size_t)g_sia_stage_kb * 1024;
+  const size_t win = (size_t)kWinBytes * slots;
+  if (g_sia_windows && win > cap && base + win <= budget) cap = win;
   if (base + cap > budget) cap = (budget - base) & ~size_t(15);
   stage_cap = (int)cap;
   smem = base + cap;
@@ -735,27 +1087,41 @@ static int pick_launch(svo_b200_ctx* ctx, int max_feat, int& threads, int& fpt, 
 }
 
 template <bool EVAL>
-static int launch_sia(svo_b200_ctx* ctx, const SiaParams& P, int B, int threads, int fpt, size_t smem) {
+static int launch_sia(svo_b200_ctx* ctx, const SiaParams& P, int B, int threads, int fpt, int cluster, size_t smem) {
   auto go = [&](auto kern) -> int {
     SVO_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // ask for the full shared-memory carveout so that two CTAs of ~90 KB fit one SM
+    // ask for the full shared-memory carveout so that two CTAs of ~95 KB fit one SM
     SVO_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                              (int)cudaSharedmemCarveoutMaxShared));
-    kern<<<B, threads, smem, ctx->stream>>>(P);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(B * cluster));
+    cfg.blockDim = dim3((unsigned)threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = cluster > 1 ? 1 : 0;
+    SVO_CUDA_CHECK(ctx, cudaLaunchKernelEx(&cfg, kern, P));
     ctx->launches++;
     SVO_CUDA_CHECK(ctx, cudaGetLastError());
     return 0;
   };
+  if (cluster == 2) return go(sia_kernel<1, EVAL, 96, 2, 2>);
+  if (cluster == 4) return go(sia_kernel<1, EVAL, 96, 2, 4>);
+  if (cluster == 8) return go(sia_kernel<1, EVAL, 96, 2, 8>);
   // <= 384 threads: cap registers so that two CTAs are resident per SM
   if (fpt == 1) {
-    if (threads <= 320 && g_sia_minb == 3) return go(sia_kernel<1, EVAL, 320, 3>);
-    if (threads <= 320) return go(sia_kernel<1, EVAL, 320, 2>);
-    if (threads == 352) return go(sia_kernel<1, EVAL, 352, 2>);
-    if (threads <= 384) return go(sia_kernel<1, EVAL, 384, 2>);
-    return go(sia_kernel<1, EVAL, 512, 1>);
+    if (threads <= 320 && g_sia_minb == 3) return go(sia_kernel<1, EVAL, 320, 3, 1>);
+    if (threads <= 320) return go(sia_kernel<1, EVAL, 320, 2, 1>);
+    if (threads <= 384) return go(sia_kernel<1, EVAL, 384, 2, 1>);
+    return go(sia_kernel<1, EVAL, 512, 1, 1>);
   }
-  if (fpt == 2) return go(sia_kernel<2, EVAL, 512, 1>);
-  return go(sia_kernel<4, EVAL, 512, 1>);
+  if (threads == 160) return go(sia_kernel<2, EVAL, 160, 3, 1>);
+  return go(sia_kernel<2, EVAL, 512, 1, 1>);
 }
 
 static inline int pad16(int n) { return (n + 15) / 16 * 16; }
@@ -778,9 +1144,13 @@ static int fill_common(svo_b200_ctx* ctx, SiaParams& P, const svo_b200_frame* fr
     return set_err(ctx, SVO_B200_EINVAL, "sparse_img_align: levels [%d,%d] outside the pyramid (%d levels)",
                    opt->min_level, opt->max_level, fr->n_levels);
   for (int l = 0; l < fr->n_levels; ++l) { P.w[l] = fr->w[l]; P.h[l] = fr->h[l]; }
-  P.fx = cam->fx; P.fy = cam->fy; P.cx = cam->cx; P.cy = cam->cy;
+  int rc = cam_to_dev(ctx, cam, P.cam);
+  if (rc) return rc;
   P.max_level = opt->max_level; P.min_level = opt->min_level; P.n_iter = opt->n_iter; P.eps = opt->eps;
   P.debug = getenv("SVO_B200_SIA_DEBUG") ? 1 : 0;
+  read_env_once();
+  P.use_windows = g_sia_windows;
+  P.use_prefetch = g_sia_prefetch;
   return 0;
 }
 
@@ -789,6 +1159,16 @@ static int fill_common(svo_b200_ctx* ctx, SiaParams& P, const svo_b200_frame* fr
 using namespace svo;
 
 extern "C" {
+
+int svo_b200_sia_config(svo_b200_ctx* ctx, int ctas_per_pair, int features_per_thread) {
+  if (!ctx) return SVO_B200_EINVAL;
+  if (!(ctas_per_pair == -1 || ctas_per_pair == 1 || ctas_per_pair == 2 || ctas_per_pair == 4 || ctas_per_pair == 8) ||
+      features_per_thread < 0 || features_per_thread > 2)
+    return set_err(ctx, SVO_B200_EINVAL, "sia_config: ctas_per_pair must be -1, 1, 2, 4 or 8 and features_per_thread 0, 1 or 2");
+  ctx->sia_cluster = ctas_per_pair;
+  ctx->sia_fpt = features_per_thread;
+  return 0;
+}
 
 int svo_b200_sia_batch_stage(svo_b200_ctx* ctx, int B, const svo_b200_frame* const* ref,
                              const svo_b200_frame* const* cur, const svo_b200_camera* cam,
@@ -818,7 +1198,7 @@ int svo_b200_sia_batch_stage(svo_b200_ctx* ctx, int B, const svo_b200_frame* con
   int rc = fill_common(ctx, st.P, ref[0], cam, opt);
   if (rc) return rc;
   int stage_cap = 0;
-  rc = pick_launch(ctx, st.max_feat, st.threads, st.fpt, stage_cap, st.smem);
+  rc = pick_launch(ctx, B, st.max_feat, st.threads, st.fpt, st.cluster, stage_cap, st.smem);
   if (rc) return rc;
   st.P.stage_cap = stage_cap;
   st.P.slots = st.threads * st.fpt;
@@ -832,12 +1212,12 @@ int svo_b200_sia_batch_stage(svo_b200_ctx* ctx, int B, const svo_b200_frame* con
     o_blob[b] = cin.take((size_t)pad16(n) * 65 + 16, 128);
   }
   st.in_bytes = cin.off;
-  if ((rc = ensure_host(ctx, ctx->h_in, st.in_bytes))) return rc;
-  if ((rc = ensure_dev(ctx, ctx->d_in, st.in_bytes))) return rc;
+  if ((rc = ensure_host(ctx, st.h_in, st.in_bytes))) return rc;
+  if ((rc = ensure_dev(ctx, st.d_in, st.in_bytes))) return rc;
   // a previous async copy out of the pinned buffer must be finished before it is rewritten
   SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  uint8_t* hin = static_cast<uint8_t*>(ctx->h_in.p);
-  uint8_t* din = static_cast<uint8_t*>(ctx->d_in.p);
+  uint8_t* hin = static_cast<uint8_t*>(st.h_in.p);
+  uint8_t* din = static_cast<uint8_t*>(st.d_in.p);
   SiaJob* jobs = reinterpret_cast<SiaJob*>(hin + o_jobs);
   for (int b = 0; b < B; ++b) {
     SiaJob& j = jobs[b];
@@ -861,9 +1241,9 @@ int svo_b200_sia_batch_stage(svo_b200_ctx* ctx, int B, const svo_b200_frame* con
   st.o_stats = co.take(sizeof(svo_b200_sia_stats) * (size_t)B);
   st.o_vis = co.take((size_t)st.total_feat + 16);
   st.out_bytes = co.off;
-  if ((rc = ensure_dev(ctx, ctx->d_out, st.out_bytes))) return rc;
-  if ((rc = ensure_host(ctx, ctx->h_out, st.out_bytes))) return rc;
-  uint8_t* dout = static_cast<uint8_t*>(ctx->d_out.p);
+  if ((rc = ensure_dev(ctx, st.d_out, st.out_bytes))) return rc;
+  if ((rc = ensure_host(ctx, st.h_out, st.out_bytes))) return rc;
+  uint8_t* dout = static_cast<uint8_t*>(st.d_out.p);
   st.P.jobs = reinterpret_cast<const SiaJob*>(din + o_jobs);
   st.P.T_out = reinterpret_cast<double*>(dout + st.o_T);
   st.P.H_out = reinterpret_cast<double*>(dout + st.o_H);
@@ -877,7 +1257,7 @@ int svo_b200_sia_batch_run(svo_b200_ctx* ctx) {
   if (!ctx || !ctx->sia || !ctx->sia->staged) return set_err(ctx, SVO_B200_EINVAL, "sia_batch_run: nothing staged");
   cudaSetDevice(ctx->device);
   SiaBatchState& st = *ctx->sia;
-  return launch_sia<false>(ctx, st.P, st.B, st.threads, st.fpt, st.smem);
+  return launch_sia<false>(ctx, st.P, st.B, st.threads, st.fpt, st.cluster, st.smem);
 }
 
 int svo_b200_sia_batch_fetch(svo_b200_ctx* ctx, double* T_out, uint8_t* visible_out, double* H_out,
@@ -885,9 +1265,9 @@ int svo_b200_sia_batch_fetch(svo_b200_ctx* ctx, double* T_out, uint8_t* visible_
   if (!ctx || !ctx->sia || !ctx->sia->staged) return set_err(ctx, SVO_B200_EINVAL, "sia_batch_fetch: nothing staged");
   cudaSetDevice(ctx->device);
   SiaBatchState& st = *ctx->sia;
-  SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(ctx->h_out.p, ctx->d_out.p, st.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(st.h_out.p, st.d_out.p, st.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  const uint8_t* h = static_cast<const uint8_t*>(ctx->h_out.p);
+  const uint8_t* h = static_cast<const uint8_t*>(st.h_out.p);
   if (T_out) memcpy(T_out, h + st.o_T, sizeof(double) * 12 * (size_t)st.B);
   if (H_out) memcpy(H_out, h + st.o_H, sizeof(double) * 36 * (size_t)st.B);
   if (stats_out) memcpy(stats_out, h + st.o_stats, sizeof(svo_b200_sia_stats) * (size_t)st.B);
@@ -939,6 +1319,7 @@ int svo_b200_sparse_img_align(svo_b200_ctx* ctx, const svo_b200_frame* ref, cons
   }
   st.P.trace = nullptr;
   st.P.n_trace = nullptr;
+  st.staged = false;  // the single-pair call leaves nothing staged behind
   return 0;
 }
 
@@ -955,14 +1336,15 @@ int svo_b200_sparse_residuals(svo_b200_ctx* ctx, const svo_b200_frame* ref, cons
   int rc = svo_b200_sia_batch_stage(ctx, 1, &ref, &cur, cam, &opt, T, off, px, f, point_pos, has_point, ref_pos);
   if (rc) return rc;
   SiaBatchState& st = *ctx->sia;
+  const size_t nslots = (size_t)st.P.slots * (size_t)st.cluster;
   Carver c;
-  const size_t o_vin = c.take(N), o_rp = c.take(sizeof(float) * 16 * (size_t)st.P.slots),
-               o_res = c.take(sizeof(float) * 16 * (size_t)st.P.slots), o_in = c.take(N),
+  const size_t o_vin = c.take(N), o_rp = c.take(sizeof(float) * 16 * nslots),
+               o_res = c.take(sizeof(float) * 16 * nslots), o_in = c.take(N),
                o_j = c.take(sizeof(double) * 6), o_c = c.take(sizeof(double)), o_n = c.take(sizeof(long long));
   if ((rc = ensure_dev(ctx, ctx->d_scratch, c.off))) return rc;
   uint8_t* ds = static_cast<uint8_t*>(ctx->d_scratch.p);
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(ds + o_vin, visible_io, N, cudaMemcpyHostToDevice, ctx->stream));
-  SVO_CUDA_CHECK(ctx, cudaMemsetAsync(ds + o_res, 0xff, sizeof(float) * 16 * (size_t)st.P.slots, ctx->stream));
+  SVO_CUDA_CHECK(ctx, cudaMemsetAsync(ds + o_res, 0xff, sizeof(float) * 16 * nslots, ctx->stream));
   st.P.eval_level = level;
   st.P.visible_in = ds + o_vin;
   st.P.ref_patch_out = reinterpret_cast<float*>(ds + o_rp);
@@ -971,7 +1353,7 @@ int svo_b200_sparse_residuals(svo_b200_ctx* ctx, const svo_b200_frame* ref, cons
   st.P.Jres_out = reinterpret_cast<double*>(ds + o_j);
   st.P.chi2_out = reinterpret_cast<double*>(ds + o_c);
   st.P.n_meas_out = reinterpret_cast<long long*>(ds + o_n);
-  if ((rc = launch_sia<true>(ctx, st.P, 1, st.threads, st.fpt, st.smem))) return rc;
+  if ((rc = launch_sia<true>(ctx, st.P, 1, st.threads, st.fpt, st.cluster, st.smem))) return rc;
   double Tdummy[12];
   if ((rc = svo_b200_sia_batch_fetch(ctx, Tdummy, visible_io, H_out, nullptr))) return rc;
   if (ref_patch_out) SVO_CUDA_CHECK(ctx, cudaMemcpy(ref_patch_out, ds + o_rp, sizeof(float) * 16 * (size_t)N, cudaMemcpyDeviceToHost));

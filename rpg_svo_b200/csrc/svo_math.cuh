@@ -9,6 +9,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "../../include/svo_b200.h"
+
 namespace svo {
 
 struct Quat {
@@ -156,7 +158,7 @@ __device__ inline void pose_to_rt12(const Pose& P, double* T) {
 // 6x6 buffer `m` (lower triangle used) that may live in shared memory, plus a solve with the
 // pseudo-inverse of D.  One thread executes these; they run once per pyramid level.
 // ------------------------------------------------------------------------------------------
-__device__ inline void ldlt6_factor(double* m, int* tr) {
+static __device__ __noinline__ void ldlt6_factor(double* m, int* tr) {
   for (int k = 0; k < 6; ++k) {
     int big = k;
     double bigv = fabs(m[k * 6 + k]);
@@ -194,7 +196,7 @@ __device__ inline void ldlt6_factor(double* m, int* tr) {
   }
 }
 // x (in/out) holds b on entry.  x may be in shared memory (dynamic indexing).
-__device__ inline void ldlt6_solve(const double* m, const int* tr, double* x) {
+static __device__ __noinline__ void ldlt6_solve(const double* m, const int* tr, double* x) {
   for (int i = 0; i < 6; ++i) { const int j = tr[i]; double s = x[i]; x[i] = x[j]; x[j] = s; }
   for (int i = 1; i < 6; ++i) {
     double s = x[i];
@@ -219,6 +221,16 @@ __device__ inline void ldlt6_solve(const double* m, const int* tr, double* x) {
 // works while the CTA waits): explicit FMAs, no divisions, no sincos for small rotations.
 // Results agree with the plain versions to a few ulp.
 // ------------------------------------------------------------------------------------------
+static __device__ __noinline__ void se3_exp_coeffs_large(double th2, double& imag, double& real, double& a, double& b) {
+  const double th = sqrt(th2);
+  double sh, ch, s, c;
+  sincos(0.5 * th, &sh, &ch);
+  sincos(th, &s, &c);
+  real = ch;
+  imag = sh / th;
+  a = (1.0 - c) / th2;
+  b = (th - s) / (th2 * th);
+}
 __device__ __forceinline__ Pose se3_exp_fast(const double* u) {
   const double wx = u[3], wy = u[4], wz = u[5];
   const double th2 = fma(wx, wx, fma(wy, wy, wz * wz));
@@ -236,14 +248,7 @@ __device__ __forceinline__ Pose se3_exp_fast(const double* u) {
     b = fma(th2, fma(th2, fma(th2, fma(th2, fma(th2, fma(th2, fma(th2, -1.0 / 355687428096000.0, 1.0 / 1307674368000.0),
             -1.0 / 6227020800.0), 1.0 / 39916800.0), -1.0 / 362880.0), 1.0 / 5040.0), -1.0 / 120.0), 1.0 / 6.0);
   } else {
-    const double th = sqrt(th2);
-    double sh, ch, s, c;
-    sincos(0.5 * th, &sh, &ch);
-    sincos(th, &s, &c);
-    real = ch;
-    imag = sh / th;
-    a = (1.0 - c) / th2;
-    b = (th - s) / (th2 * th);
+    se3_exp_coeffs_large(th2, imag, real, a, b);  // |omega| >= 0.5 rad in one update: cold, kept out of line
   }
   Pose P;
   P.q.w = real; P.q.x = imag * wx; P.q.y = imag * wy; P.q.z = imag * wz;
@@ -278,6 +283,17 @@ __device__ __forceinline__ Pose pose_mul_fast(const Pose& A, const Pose& B) {
   return C;
 }
 
+// 1/z, correctly rounded for finite normal z: f32 reciprocal seed, two f64 Newton steps, residual correction.
+__device__ __forceinline__ double rcp_rn(double z) {
+  double r = (double)__frcp_rn((float)z);
+  double e = fma(-z, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-z, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-z, r, 1.0);
+  return fma(r, e, r);
+}
+
 // Unpivoted LDL^T of a symmetric positive definite 6x6, fully unrolled in registers.
 // L: strict lower triangle row-major (15), dinv: 1/d.  Returns false when a pivot is not safely
 // positive (caller falls back to the pivoted Eigen-like routine above).
@@ -285,7 +301,7 @@ struct Fact6 {
   double L[15];
   double dinv[6];
 };
-__device__ __forceinline__ int tri(int i, int j) { return i * (i - 1) / 2 + j; }  // i > j
+__device__ __forceinline__ constexpr int tri(int i, int j) { return i * (i - 1) / 2 + j; }  // i > j
 __device__ __forceinline__ bool fact6_compute(const double* H /*36 row-major*/, Fact6& F) {
   double d[6];
   double maxdiag = 0.0;
@@ -304,6 +320,36 @@ __device__ __forceinline__ bool fact6_compute(const double* H /*36 row-major*/, 
 #pragma unroll
     for (int i = j + 1; i < 6; ++i) {
       double v = H[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) v = fma(-(F.L[tri(i, k)] * F.L[tri(j, k)]), d[k], v);
+      F.L[tri(i, j)] = v * inv;
+    }
+  }
+  return ok;
+}
+// same, from the 21 upper-triangle entries (row-major: (0,0..5), (1,1..5), ...) held in registers
+__device__ __forceinline__ constexpr int upper_idx(int r, int c) {  // r <= c
+  return r * 6 - r * (r - 1) / 2 + (c - r);
+}
+__device__ __forceinline__ bool fact6_compute_upper(const double (&h)[21], Fact6& F) {
+  double d[6];
+  double maxdiag = 0.0;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) maxdiag = fmax(maxdiag, fabs(h[upper_idx(j, j)]));
+  bool ok = maxdiag > 0.0 && maxdiag < 1e300;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    double dj = h[upper_idx(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; ++k) dj = fma(-(F.L[tri(j, k)] * F.L[tri(j, k)]), d[k], dj);
+    d[j] = dj;
+    ok = ok && (dj > 1e-13 * maxdiag);
+    const double adj = fabs(dj);
+    const double inv = (adj > 1e-30 && adj < 1e30) ? rcp_rn(dj) : 1.0 / dj;  // correctly rounded reciprocal without the IEEE-division slow path
+    F.dinv[j] = inv;
+#pragma unroll
+    for (int i = j + 1; i < 6; ++i) {
+      double v = h[upper_idx(j, i)];
 #pragma unroll
       for (int k = 0; k < j; ++k) v = fma(-(F.L[tri(i, k)] * F.L[tri(j, k)]), d[k], v);
       F.L[tri(i, j)] = v * inv;
@@ -395,6 +441,76 @@ __device__ __forceinline__ double fast_rcp(double z) {
   return fma(r, e, r);
 }
 
+// x / z given rz ~ 1/z (relative error << 2^-53, e.g. from fast_rcp): one residual correction turns the product
+// x*rz into the correctly rounded quotient (Markstein's division step; the same sequence the compiler's own f64
+// division ends with).  The reference divides (Eigen's project2d = head<2>() / z), so this keeps the f32-cast pixel
+// coordinate on the reference's side of every rounding boundary.
+__device__ __forceinline__ double div_rn(double x, double z, double rz) {
+  const double q = x * rz;
+  const double r = fma(-z, q, x);
+  return fma(r, rz, q);
+}
+
+// ------------------------------------------------------------------------------------------
+// [EXT] vk::AbstractCamera models, restated from the published rpg_vikit sources (pinhole_camera.cpp,
+// atan_camera.cpp); `c` is the CamDev of ctx.h (kernel parameter, read through the constant bank).
+//   world2cam(uv): unit-plane point -> pixel.      cam2world(px): pixel -> UNIT bearing vector.
+// ------------------------------------------------------------------------------------------
+template <class Cam>
+__device__ __forceinline__ void cam_world2cam(const Cam& c, double x, double y, double& u, double& v) {
+  if (!c.distorted) {  // px = fx*uv + cx  (both models without distortion)
+    u = fma(c.fx, x, c.cx);
+    v = fma(c.fy, y, c.cy);
+  } else if (c.model == SVO_B200_CAM_PINHOLE) {  // vk::PinholeCamera::world2cam(const Vector2d&), radial-tangential
+    const double r2 = fma(x, x, y * y), r4 = r2 * r2, r6 = r4 * r2;
+    const double a1 = 2.0 * x * y, a2 = fma(2.0 * x, x, r2), a3 = fma(2.0 * y, y, r2);
+    const double cdist = fma(c.d[4], r6, fma(c.d[1], r4, fma(c.d[0], r2, 1.0)));
+    const double xd = fma(c.d[3], a2, fma(c.d[2], a1, x * cdist));
+    const double yd = fma(c.d[3], a1, fma(c.d[2], a3, y * cdist));
+    u = fma(xd, c.fx, c.cx);
+    v = fma(yd, c.fy, c.cy);
+  } else {  // vk::ATANCamera::world2cam: factor = rtrans_factor(|uv|) = atan(r * tans) / (s * r)
+    const double r = sqrt(fma(x, x, y * y));
+    const double factor = r < 0.001 ? 1.0 : c.s_inv * atan(r * c.tans) / r;
+    u = fma(c.fx * factor, x, c.cx);
+    v = fma(c.fy * factor, y, c.cy);
+  }
+}
+template <class Cam>
+__device__ __forceinline__ void cam_cam2world(const Cam& c, double u, double v, double (&f)[3]) {
+  double x, y;
+  if (c.model == SVO_B200_CAM_PINHOLE) {
+    if (!c.distorted) {
+      x = (u - c.cx) / c.fx;
+      y = (v - c.cy) / c.fy;
+    } else {
+      // cv::undistortPoints on ONE CV_32FC2 point [EXT OpenCV]: float in, 5 fixed-point iterations in double, float out
+      const double uf = (double)(float)u, vf = (double)(float)v;
+      const double x0 = (uf - c.cx) * c.fx_inv, y0 = (vf - c.cy) * c.fy_inv;
+      x = x0; y = y0;
+      for (int j = 0; j < 5; ++j) {
+        const double r2 = x * x + y * y;
+        const double icdist = 1.0 / (1.0 + ((c.d[4] * r2 + c.d[1]) * r2 + c.d[0]) * r2);
+        const double dX = 2.0 * c.d[2] * x * y + c.d[3] * (r2 + 2.0 * x * x);
+        const double dY = c.d[2] * (r2 + 2.0 * y * y) + 2.0 * c.d[3] * x * y;
+        x = (x0 - dX) * icdist;
+        y = (y0 - dY) * icdist;
+      }
+      x = (double)(float)x;
+      y = (double)(float)y;
+    }
+  } else {  // vk::ATANCamera::cam2world
+    const double dx = (u - c.cx) * c.fx_inv, dy = (v - c.cy) * c.fy_inv;
+    const double dist_r = sqrt(dx * dx + dy * dy);
+    const double r = c.distorted ? tan(dist_r * c.d[0]) * c.tans_inv : dist_r;  // invrtrans
+    const double d_factor = dist_r > 0.01 ? r / dist_r : 1.0;
+    x = d_factor * dx;
+    y = d_factor * dy;
+  }
+  const double n = sqrt(x * x + y * y + 1.0);
+  f[0] = x / n; f[1] = y / n; f[2] = 1.0 / n;
+}
+
 // byte k of w -> float, exactly: PRMT builds the float 2^23 + byte, one FADD removes the 2^23.
 template <int KB>
 __device__ __forceinline__ float byte_to_float(uint32_t w) {
@@ -453,6 +569,9 @@ __device__ __forceinline__ void fence_proxy_async() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
                                              uint64_t* bar) {

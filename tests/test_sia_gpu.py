@@ -13,6 +13,20 @@ pytestmark = pytest.mark.gpu
 POSE_TOL = 1e-4
 RES_TOL = 1e-4
 
+# Launch geometries of the alignment kernel (svo_b200_sia_config): every parity test of this file runs on each.
+#   auto        the library's choice (a 4-CTA cluster per pair for these small batches)
+#   cta-1fpt    one CTA per pair, one feature per thread (320 / 384 / 512 threads)
+#   cta-2fpt    one CTA per pair, two features per thread (160 threads for <= 320 features: the full-batch kernel)
+#   cluster-4/8 the pair's features split over a thread-block cluster, partial sums exchanged through DSMEM
+GEOMETRIES = {"auto": (-1, 0), "cta-1fpt": (1, 1), "cta-2fpt": (1, 2), "cluster-4": (4, 0), "cluster-8": (8, 0)}
+
+
+@pytest.fixture(params=list(GEOMETRIES), autouse=True)
+def geometry(request, ctx):
+    ctx.sia_config(*GEOMETRIES[request.param])
+    yield request.param
+    ctx.sia_config(-1, 0)
+
 
 def _run_both(ctx, oracle, d, max_level, min_level, n_iter=30, T0=None, trace=True):
     T0 = synth.se3_identity() if T0 is None else T0
