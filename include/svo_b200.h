@@ -79,9 +79,20 @@ const char* svo_b200_version(void);
  * (width >> l, height >> l) (integer division, svo/src/frame.cpp:162). */
 int svo_b200_frame_create(svo_b200_ctx* ctx, int width, int height, int n_levels,
                           svo_b200_frame** frame_out);
+/* Rounding of the device-side pyramid build (vk::halfSample [EXT], called by frame_utils::createImgPyramid,
+ * svo/src/frame.cpp:156-165).  vikit has two branches that round differently:
+ *   SVO_B200_PYR_X86 (default)  what the reference computes on its own platform (x86): the SSE2 branch
+ *       avg(avg(top, bottom)) of adjacent columns, round-half-up twice (_mm_avg_epu8, _mm_avg_epu16), whenever the
+ *       source level's width is a multiple of 16 (cv::Mat buffers are 16-byte aligned), else the scalar branch;
+ *   SVO_B200_PYR_SCALAR         (a+b+c+d)/4 with integer division at every level (non-SIMD builds).
+ * 640, 752 and 1920 are multiples of 16, so on x86 at least the first level always takes the SSE2 branch. */
+#define SVO_B200_PYR_X86 0
+#define SVO_B200_PYR_SCALAR 1
+int svo_b200_set_pyramid_rule(svo_b200_ctx* ctx, int rule);
+
 /* Upload n_given >= 1 levels from host memory (levels[l] has pitch == width>>l).  Levels
- * n_given..n_levels-1 are built on the device with the scalar vk::halfSample rule
- * (a+b+c+d)/4.  The copy is asynchronous on the context stream when host memory is pinned. */
+ * n_given..n_levels-1 are built on the device with vk::halfSample's rule (svo_b200_set_pyramid_rule).
+ * The copy is asynchronous on the context stream when host memory is pinned. */
 int svo_b200_frame_upload(svo_b200_ctx* ctx, svo_b200_frame* frame, const uint8_t* const* levels,
                           int n_given);
 /* Device-to-device variant: level 0 already on this GPU. */

@@ -185,9 +185,13 @@ def sparse_residuals(ref_img, cur_img, level, cam, T, px, f, pos, has_point, ref
                 H=H.reshape(6, 6), Jres=Jres, chi2=chi2.value, n_meas=nm.value)
 
 
-def half_sample(img):
+PYR_SCALAR, PYR_X86 = 0, 1
+
+
+def half_sample(img, rule=PYR_X86):
+    """[EXT] vk::halfSample: rule PYR_X86 = the reference's x86 build (SSE2 branch for widths % 16 == 0), PYR_SCALAR."""
     out = np.zeros((img.shape[0] // 2, img.shape[1] // 2), np.uint8)
-    lib().orc_half_sample(_p(np.ascontiguousarray(img)), img.shape[1], img.shape[0], _p(out))
+    lib().orc_half_sample_rule(_p(np.ascontiguousarray(img)), img.shape[1], img.shape[0], _p(out), int(rule))
     return out
 
 
@@ -393,6 +397,20 @@ def ref_sparse_img_align(ref_l0, cur_l0, n_levels, cam, T_ref_w, T_cur_w, px, f,
                                          _p(_cam4(cam)), _p(c64(T_ref_w).reshape(12)), _p(T), _p(px), _p(f), _p(pos), _p(hp),
                                          n, max_level, min_level, n_iter, _p(vis), _p(H), _p(cache))
     return dict(T_cur_w=T.reshape(3, 4), n_tracked=int(ret), visible=vis, H=H.reshape(6, 6), ref_patch=cache)
+
+
+def ref_image_pyramid(img, n_levels):
+    """frame_utils::createImgPyramid of the compiled reference (svo/src/frame.cpp:156-165 over the shim's vk::halfSample,
+    real SSE2 intrinsics on this x86 host)."""
+    h, w = img.shape
+    sizes = [((h >> l), (w >> l)) for l in range(n_levels)]
+    out = np.zeros(sum(a * b for a, b in sizes), np.uint8)
+    ref_lib().ref_image_pyramid(_p(np.ascontiguousarray(img, np.uint8)), w, h, n_levels, _p(out))
+    pyr, o = [], 0
+    for a, b in sizes:
+        pyr.append(out[o:o + a * b].reshape(a, b).copy())
+        o += a * b
+    return pyr
 
 
 def ref_pose_optimize(reproj_thresh, n_iter, cam, T_f_w, f, pos, level, has_point):

@@ -17,6 +17,7 @@
 #include <vikit/abstract_camera.h>
 
 #include <chrono>
+#include <cstring>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -43,7 +44,10 @@ struct SIA : public SparseImgAlign {
 FramePtr make_frame(vk::AbstractCamera* cam, const uint8_t* img, int w, int h, int n_levels, const double* T_f_w) {
   Config::nPyrLevels() = 1;
   Config::kltMaxLevel() = n_levels - 1;  // Frame::initFrame builds max(nPyrLevels, kltMaxLevel+1) levels (frame.cpp:58)
-  cv::Mat m(h, w, const_cast<uint8_t*>(img), (size_t)w);
+  // the image goes into an aligned cv::Mat of its own, as the reference's callers hand it over (cv::imread /
+  // cv_bridge buffers are 16-byte aligned): vk::halfSample's SSE2 branch tests the alignment of level 0
+  cv::Mat m(h, w, CV_8U);
+  std::memcpy(m.data, img, (size_t)w * h);
   FramePtr f(new Frame(cam, m, 0.0));
   f->T_f_w_ = se3_from12(T_f_w);
   return f;
@@ -81,6 +85,20 @@ float shiTomasiScore(const cv::Mat& img, int u, int v) { return fast_ext::shiTom
 }
 
 extern "C" {
+
+// frame_utils::createImgPyramid of the reference's frame.cpp (through Frame::initFrame): levels 0..n_levels-1 written
+// back to back into `out` (level l has (w >> l) x (h >> l) pixels).
+void ref_image_pyramid(const uint8_t* img, int w, int h, int n_levels, uint8_t* out) {
+  vk::PinholeCamera cam(w, h, 300.0, 300.0, w / 2.0, h / 2.0);
+  const double T[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  FramePtr f = make_frame(&cam, img, w, h, n_levels, T);
+  size_t o = 0;
+  for (int l = 0; l < n_levels; ++l) {
+    const cv::Mat& m = f->img_pyr_[l];
+    for (int y = 0; y < m.rows; ++y) std::memcpy(out + o + (size_t)y * m.cols, m.data + (size_t)y * m.step.p[0], m.cols);
+    o += (size_t)m.rows * m.cols;
+  }
+}
 
 // svo::SparseImgAlign::run on two frames built from level-0 images (pyramids by the reference's createImgPyramid).
 long long ref_sparse_img_align(const uint8_t* ref_l0, const uint8_t* cur_l0, int w, int h, int n_levels, const double* cam4,

@@ -7,6 +7,7 @@
 #include <string>
 #define CV_8U 0
 #define CV_8UC1 0
+#include <cstdlib>
 #define CV_32F 5
 #define CV_WINDOW_AUTOSIZE 1
 namespace cv {
@@ -26,7 +27,9 @@ struct Mat {
     rows = r; cols = c; type_ = type;
     const size_t es = (type == CV_32F) ? 4 : 1;
     step.p[0] = es * c; step.p[1] = es;
-    own.reset(new unsigned char[es * (size_t)r * c + 64], std::default_delete<unsigned char[]>());
+    // 64-byte aligned like OpenCV's fastMalloc (vk::halfSample's SSE2 branch tests 16-byte alignment)
+    const size_t bytes = (es * (size_t)r * c + 64 + 63) & ~size_t(63);
+    own.reset(static_cast<unsigned char*>(std::aligned_alloc(64, bytes)), [](unsigned char* q) { std::free(q); });
     data = own.get();
     std::memset(data, 0, es * (size_t)r * c);
   }

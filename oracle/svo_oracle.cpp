@@ -488,17 +488,29 @@ int orc_sparse_residuals(const uint8_t* ref_img, const uint8_t* cur_img, int col
   return 0;
 }
 
-// [EXT] vk::halfSample, scalar path (rpg_vikit vision.cpp): (tl + tr + bl + br) / 4, integer
-// division; called from svo/src/frame.cpp:156-165 (createImgPyramid; rows/2, cols/2).
-void orc_half_sample(const uint8_t* in, int in_cols, int in_rows, uint8_t* out) {
+// [EXT] vk::halfSample (rpg_vikit vision.cpp); called from svo/src/frame.cpp:156-165 (createImgPyramid; rows/2, cols/2).
+//   rule 0 (SCALAR): (tl + tr + bl + br) / 4, integer division -- the non-SIMD branch.
+//   rule 1 (X86):    what an x86 build of the reference computes: when in_cols % 16 == 0 (the buffers are 16-byte
+//                    aligned cv::Mat allocations) the SSE2 branch runs -- vertical rounded average (a+c+1)>>1 of
+//                    _mm_avg_epu8, then rounded average of horizontally adjacent results (_mm_avg_epu16) -- else rule 0.
+void orc_half_sample_rule(const uint8_t* in, int in_cols, int in_rows, uint8_t* out, int rule) {
   const int oc = in_cols / 2, orows = in_rows / 2;
+  const bool sse2 = rule == 1 && (in_cols % 16) == 0;
   for (int y = 0; y < orows; ++y) {
     const uint8_t* top = in + size_t(2 * y) * in_cols;
     const uint8_t* bot = top + in_cols;
-    for (int x = 0; x < oc; ++x)
-      out[size_t(y) * oc + x] =
-          uint8_t((uint16_t(top[2 * x]) + top[2 * x + 1] + bot[2 * x] + bot[2 * x + 1]) / 4);
+    for (int x = 0; x < oc; ++x) {
+      if (sse2) {
+        const unsigned v0 = (unsigned(top[2 * x]) + bot[2 * x] + 1u) >> 1, v1 = (unsigned(top[2 * x + 1]) + bot[2 * x + 1] + 1u) >> 1;
+        out[size_t(y) * oc + x] = uint8_t((v0 + v1 + 1u) >> 1);
+      } else {
+        out[size_t(y) * oc + x] = uint8_t((uint16_t(top[2 * x]) + top[2 * x + 1] + bot[2 * x] + bot[2 * x + 1]) / 4);
+      }
+    }
   }
+}
+void orc_half_sample(const uint8_t* in, int in_cols, int in_rows, uint8_t* out) {
+  orc_half_sample_rule(in, in_cols, in_rows, out, 0);
 }
 
 void orc_se3_exp(const double* x6, double* T12_out) { se3_to_rt12(se3_exp(x6), T12_out); }

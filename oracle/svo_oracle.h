@@ -77,6 +77,8 @@ int orc_sparse_residuals(
 
 /* [EXT] vk::halfSample scalar path: out = (a+b+c+d)/4 (integer division). */
 void orc_half_sample(const uint8_t* in, int in_cols, int in_rows, uint8_t* out);
+/* rule 0 = scalar, 1 = x86 (vikit's SSE2 avg(avg) branch when in_cols % 16 == 0, scalar otherwise). */
+void orc_half_sample_rule(const uint8_t* in, int in_cols, int in_rows, uint8_t* out, int rule);
 
 /* Sophus helpers exposed for the pinning tests. */
 void orc_se3_exp(const double* x6, double* T12_out);

@@ -269,6 +269,10 @@ class Context:
         self._check(self.lib.svo_b200_sia_batch_stage(self.h, B, ra, ca, C.byref(cs), C.byref(opt), _p(T),
                                                       _p(fo), _p(px), _p(f), _p(pos), _p(hp), _p(rpos)))
 
+    def set_pyramid_rule(self, rule: int):
+        """0 = PYR_X86 (vikit's SSE2 rounding where an x86 build of the reference takes it; default), 1 = PYR_SCALAR."""
+        self._check(self.lib.svo_b200_set_pyramid_rule(self.h, int(rule)))
+
     def sia_config(self, ctas_per_pair=-1, features_per_thread=0):
         """Launch geometry of the alignment kernel (svo_b200_sia_config): -1 / 0 = automatic."""
         self._check(self.lib.svo_b200_sia_config(self.h, int(ctas_per_pair), int(features_per_thread)))

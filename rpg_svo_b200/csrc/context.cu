@@ -73,11 +73,30 @@ int ensure_host(svo_b200_ctx* ctx, HostBuf& b, size_t bytes) {
   return 0;
 }
 
-// [EXT] vk::halfSample scalar rule: out = (a + b + c + d) / 4 with integer division, rows/2 x cols/2
-// (svo/src/frame.cpp:156-165).  HBM-bound byte kernel: each thread produces 4 output pixels from two
-// 8-byte row segments (coalesced 64-bit loads, one 32-bit store).
+// [EXT] vk::halfSample (svo/src/frame.cpp:156-165), both branches of rpg_vikit's vision.cpp:
+//   scalar: out = (a + b + c + d) / 4, integer division;
+//   SSE2 (what an x86 build runs when in_w % 16 == 0): vertical _mm_avg_epu8, then _mm_avg_epu16 of adjacent columns,
+//          i.e. avg(avg(a, c), avg(b, d)) with round-half-up at both steps.
+// Packed forms on 32-bit words holding four consecutive pixels of the top / bottom row: the two results come back in
+// bytes 0 and 2.
+__device__ __forceinline__ uint32_t half2_scalar(uint32_t top, uint32_t bot) {
+  const uint32_t s = (top & 0x00ff00ffu) + ((top >> 8) & 0x00ff00ffu) + (bot & 0x00ff00ffu) + ((bot >> 8) & 0x00ff00ffu);
+  return (s >> 2) & 0x00ff00ffu;
+}
+__device__ __forceinline__ uint32_t half2_avg(uint32_t top, uint32_t bot) {
+  const uint32_t v = __vavgu4(top, bot);          // per byte (a + c + 1) >> 1
+  return __vavgu4(v, v >> 8) & 0x00ff00ffu;       // bytes 0, 2: (v0 + v1 + 1) >> 1, (v2 + v3 + 1) >> 1
+}
+__device__ __forceinline__ uint32_t half2(uint32_t top, uint32_t bot, bool avg) {
+  return avg ? half2_avg(top, bot) : half2_scalar(top, bot);
+}
+__device__ __forceinline__ uint32_t half1(uint32_t a, uint32_t b, uint32_t c, uint32_t d, bool avg) {  // one output pixel
+  return avg ? ((((a + c + 1u) >> 1) + ((b + d + 1u) >> 1) + 1u) >> 1) : ((a + b + c + d) >> 2);
+}
+// HBM-bound byte kernel: each thread produces 4 output pixels from two 8-byte row segments (coalesced 64-bit loads,
+// one 32-bit store).  `avg` selects the SSE2 rounding.
 __global__ void half_sample_kernel(const uint8_t* __restrict__ in, int in_w, int in_h,
-                                   uint8_t* __restrict__ out, int out_w, int out_h) {
+                                   uint8_t* __restrict__ out, int out_w, int out_h, int avg) {
   const int quads = (out_w + 3) / 4;
   const int total = quads * out_h;
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
@@ -88,20 +107,12 @@ __global__ void half_sample_kernel(const uint8_t* __restrict__ in, int in_w, int
     if (x0 + 4 <= out_w && ((in_w & 7) == 0)) {
       const uint2 t = *reinterpret_cast<const uint2*>(top);
       const uint2 b = *reinterpret_cast<const uint2*>(bot);
-      uint32_t r = 0;
-      const uint32_t tw[2] = {t.x, t.y}, bw[2] = {b.x, b.y};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t tt = tw[k >> 1] >> ((k & 1) * 16), bb = bw[k >> 1] >> ((k & 1) * 16);
-        const uint32_t s = (tt & 0xff) + ((tt >> 8) & 0xff) + (bb & 0xff) + ((bb >> 8) & 0xff);
-        r |= (s >> 2) << (8 * k);
-      }
+      const uint32_t q0 = half2(t.x, b.x, avg != 0), q1 = half2(t.y, b.y, avg != 0);
+      const uint32_t r = (q0 & 0xffu) | ((q0 >> 8) & 0xff00u) | ((q1 & 0xffu) << 16) | ((q1 << 8) & 0xff000000u);
       *reinterpret_cast<uint32_t*>(out + (size_t)y * out_w + x0) = r;
     } else {
-      for (int k = 0; k < 4 && x0 + k < out_w; ++k) {
-        const uint32_t s = (uint32_t)top[2 * k] + top[2 * k + 1] + bot[2 * k] + bot[2 * k + 1];
-        out[(size_t)y * out_w + x0 + k] = (uint8_t)(s >> 2);
-      }
+      for (int k = 0; k < 4 && x0 + k < out_w; ++k)
+        out[(size_t)y * out_w + x0 + k] = (uint8_t)half1(top[2 * k], top[2 * k + 1], bot[2 * k], bot[2 * k + 1], avg != 0);
     }
   }
 }
@@ -117,6 +128,7 @@ struct PyrGeom {
   unsigned long long stride[SVO_B200_MAX_LEVELS];
   int n_levels;
   int tiles_x;
+  unsigned avg_mask;  // bit l: level l is produced with the SSE2 rounding (avg of avg) instead of (a+b+c+d)/4
 };
 __global__ void __launch_bounds__(128) pyramid_fused_kernel(int first, PyrGeom g) {
   __shared__ __align__(16) uint8_t t0[16][128];
@@ -149,13 +161,9 @@ __global__ void __launch_bounds__(128) pyramid_fused_kernel(int first, PyrGeom g
     const int r = t >> 4, c = (t & 15) * 4;
     const uint2 a = *reinterpret_cast<const uint2*>(&t0[2 * r][2 * c]);
     const uint2 b = *reinterpret_cast<const uint2*>(&t0[2 * r + 1][2 * c]);
-    const uint32_t aw[2] = {a.x, a.y}, bw[2] = {b.x, b.y};
-    uint32_t o = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t tt = aw[k >> 1] >> ((k & 1) * 16), bb = bw[k >> 1] >> ((k & 1) * 16);
-      o |= (((tt & 0xff) + ((tt >> 8) & 0xff) + (bb & 0xff) + ((bb >> 8) & 0xff)) >> 2) << (8 * k);
-    }
+    const bool avg = (g.avg_mask >> 1) & 1u;
+    const uint32_t q0 = half2(a.x, b.x, avg), q1 = half2(a.y, b.y, avg);
+    const uint32_t o = (q0 & 0xffu) | ((q0 >> 8) & 0xff00u) | ((q1 & 0xffu) << 16) | ((q1 << 8) & 0xff000000u);
     *reinterpret_cast<uint32_t*>(&t1[r][c]) = o;
     const int y = ty * 8 + r, x = tx * 64 + c, W1 = g.w[1];
     if (y < g.h[1]) {
@@ -169,8 +177,8 @@ __global__ void __launch_bounds__(128) pyramid_fused_kernel(int first, PyrGeom g
   __syncthreads();
   if (g.n_levels > 2) {  // level 2: 4 x 32
     const int r = t >> 5, c = t & 31;
-    const uint32_t sum = (uint32_t)t1[2 * r][2 * c] + t1[2 * r][2 * c + 1] + t1[2 * r + 1][2 * c] + t1[2 * r + 1][2 * c + 1];
-    const uint8_t o = (uint8_t)(sum >> 2);
+    const uint8_t o = (uint8_t)half1(t1[2 * r][2 * c], t1[2 * r][2 * c + 1], t1[2 * r + 1][2 * c], t1[2 * r + 1][2 * c + 1],
+                                     (g.avg_mask >> 2) & 1u);
     t2[r][c] = o;
     const int y = ty * 4 + r, x = tx * 32 + c;
     if (y < g.h[2] && x < g.w[2]) g.slab[2][fi * g.stride[2] + (size_t)y * g.w[2] + x] = o;
@@ -178,17 +186,18 @@ __global__ void __launch_bounds__(128) pyramid_fused_kernel(int first, PyrGeom g
   __syncthreads();
   if (g.n_levels > 3 && t < 32) {  // level 3: 2 x 16
     const int r = t >> 4, c = t & 15;
-    const uint32_t sum = (uint32_t)t2[2 * r][2 * c] + t2[2 * r][2 * c + 1] + t2[2 * r + 1][2 * c] + t2[2 * r + 1][2 * c + 1];
-    const uint8_t o = (uint8_t)(sum >> 2);
+    const uint8_t o = (uint8_t)half1(t2[2 * r][2 * c], t2[2 * r][2 * c + 1], t2[2 * r + 1][2 * c], t2[2 * r + 1][2 * c + 1],
+                                     (g.avg_mask >> 3) & 1u);
     t3[r][c] = o;
     const int y = ty * 2 + r, x = tx * 16 + c;
     if (y < g.h[3] && x < g.w[3]) g.slab[3][fi * g.stride[3] + (size_t)y * g.w[3] + x] = o;
   }
   __syncthreads();
   if (g.n_levels > 4 && t < 8) {  // level 4: 1 x 8
-    const uint32_t sum = (uint32_t)t3[0][2 * t] + t3[0][2 * t + 1] + t3[1][2 * t] + t3[1][2 * t + 1];
     const int y = ty, x = tx * 8 + t;
-    if (y < g.h[4] && x < g.w[4]) g.slab[4][fi * g.stride[4] + (size_t)y * g.w[4] + x] = (uint8_t)(sum >> 2);
+    if (y < g.h[4] && x < g.w[4])
+      g.slab[4][fi * g.stride[4] + (size_t)y * g.w[4] + x] =
+          (uint8_t)half1(t3[0][2 * t], t3[0][2 * t + 1], t3[1][2 * t], t3[1][2 * t + 1], (g.avg_mask >> 4) & 1u);
   }
 }
 
@@ -196,10 +205,11 @@ __global__ void __launch_bounds__(128) pyramid_fused_kernel(int first, PyrGeom g
 // Level 0 -> level 1 for a batch of frames as a pure streaming kernel: 94 % of the pyramid's bytes move
 // here, so it is written against the HBM roofline -- a persistent grid (a few CTAs per SM), each work
 // item = 16 level-0 pixels of two consecutive rows (2 x 128-bit loads) -> 8 level-1 pixels (one 64-bit
-// store); the 2x2 sums are formed SIMD-in-register (two 16-bit lanes per word).  Requires W0 % 16 == 0.
+// store); the 2x2 reductions are formed SIMD-in-register (scalar rule: two 16-bit lanes per word; SSE2 rule: two
+// __vavgu4).  Requires W0 % 16 == 0.
 __global__ void __launch_bounds__(256) pyramid_l0_l1_stream_kernel(const uint8_t* __restrict__ l0, size_t stride0,
                                                                    uint8_t* __restrict__ l1, size_t stride1, int first,
-                                                                   int count, int W0, int H1) {
+                                                                   int count, int W0, int H1, int avg) {
   const int items_x = W0 >> 4, W1 = W0 >> 1;
   const long long per_frame = (long long)items_x * H1, total = per_frame * count;
   for (long long it = (long long)blockIdx.x * blockDim.x + threadIdx.x; it < total; it += (long long)gridDim.x * blockDim.x) {
@@ -213,14 +223,18 @@ __global__ void __launch_bounds__(256) pyramid_l0_l1_stream_kernel(const uint8_t
     uint32_t o[2] = {0u, 0u};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      // horizontal pair sums of both rows in two 16-bit lanes, then the vertical add and the /4
-      const uint32_t s = (aw[k] & 0x00ff00ffu) + ((aw[k] >> 8) & 0x00ff00ffu) + (bw[k] & 0x00ff00ffu) + ((bw[k] >> 8) & 0x00ff00ffu);
-      const uint32_t q = (s >> 2) & 0x00ff00ffu;             // two results, bytes 0 and 2
+      const uint32_t q = half2(aw[k], bw[k], avg != 0);        // two results, bytes 0 and 2
       const uint32_t two = (q & 0xffu) | ((q >> 8) & 0xff00u);  // packed into the low 16 bits
       o[k >> 1] |= two << (16 * (k & 1));
     }
     *reinterpret_cast<uint2*>(l1 + (size_t)(first + fr) * stride1 + (size_t)y * W1 + 8 * ix) = make_uint2(o[0], o[1]);
   }
+}
+
+// does producing a level from a source level of width `src_w` use vikit's SSE2 rounding?  (x86 rule: width % 16 == 0;
+// cv::Mat buffers are always 16-byte aligned)
+static inline int pyr_avg(const svo_b200_ctx* ctx, int src_w) {
+  return ctx->pyramid_rule == SVO_B200_PYR_X86 && (src_w % 16) == 0;
 }
 
 static int build_levels(svo_b200_ctx* ctx, svo_b200_frame* fr, int from_level) {
@@ -231,7 +245,7 @@ static int build_levels(svo_b200_ctx* ctx, svo_b200_frame* fr, int from_level) {
     int blocks = (total + threads - 1) / threads;
     if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
     half_sample_kernel<<<blocks, threads, 0, ctx->stream>>>(fr->lvl(l - 1), fr->w[l - 1], fr->h[l - 1],
-                                                            fr->lvl(l), fr->w[l], fr->h[l]);
+                                                            fr->lvl(l), fr->w[l], fr->h[l], pyr_avg(ctx, fr->w[l - 1]));
     ctx->launches++;
   }
   SVO_CUDA_CHECK(ctx, cudaGetLastError());
@@ -243,6 +257,13 @@ static int build_levels(svo_b200_ctx* ctx, svo_b200_frame* fr, int from_level) {
 using namespace svo;
 
 extern "C" {
+
+int svo_b200_set_pyramid_rule(svo_b200_ctx* ctx, int rule) {
+  if (!ctx) return SVO_B200_EINVAL;
+  if (rule != SVO_B200_PYR_X86 && rule != SVO_B200_PYR_SCALAR) return set_err(ctx, SVO_B200_EINVAL, "set_pyramid_rule: unknown rule %d", rule);
+  ctx->pyramid_rule = rule;
+  return 0;
+}
 
 const char* svo_b200_version(void) { return "svo_b200 0.1 (sm_100a)"; }
 
@@ -433,7 +454,8 @@ int svo_b200_frame_pool_upload(svo_b200_ctx* ctx, svo_b200_frame_pool* pool, int
     if (stream01) {
       const int blocks = ctx->sm_count * 8;
       pyramid_l0_l1_stream_kernel<<<blocks, 256, 0, ctx->stream>>>(pool->slab[0], pool->stride[0], pool->slab[1],
-                                                                   pool->stride[1], first, count, f0.w[0], f0.h[1]);
+                                                                   pool->stride[1], first, count, f0.w[0], f0.h[1],
+                                                                   pyr_avg(ctx, f0.w[0]));
       ctx->launches++;
     }
     const int n_sub = f0.n_levels - base;  // levels seen by the fused kernel, its level 0 = our level `base`
@@ -444,6 +466,8 @@ int svo_b200_frame_pool_upload(svo_b200_ctx* ctx, svo_b200_frame_pool* pool, int
       for (int l = 0; l < n_sub; ++l) {
         g.w[l] = f0.w[base + l]; g.h[l] = f0.h[base + l]; g.slab[l] = pool->slab[base + l]; g.stride[l] = pool->stride[base + l];
       }
+      for (int l = 1; l < g.n_levels; ++l)
+        if (pyr_avg(ctx, g.w[l - 1])) g.avg_mask |= 1u << l;
       g.tiles_x = (g.w[0] + 127) / 128;
       const int tiles_y = (g.h[0] + 15) / 16;
       for (int done = 0; done < count; done += 32768) {  // gridDim.y limit 65535

@@ -56,6 +56,7 @@ struct svo_b200_ctx {
   DevBuf d_in, d_out, d_scratch;
   HostBuf h_in, h_out;
   svo::SiaBatchState* sia = nullptr;
+  int pyramid_rule = SVO_B200_PYR_X86;  // svo_b200_set_pyramid_rule
   int sia_cluster = -1;  // svo_b200_sia_config: CTAs per pair (-1 = by batch size)
   int sia_fpt = 0;       //                      features per thread (0 = automatic)
 };

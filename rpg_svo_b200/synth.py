@@ -180,17 +180,25 @@ def render(cam: Camera, T_f_w: np.ndarray, plane: Plane, tex: np.ndarray) -> np.
     return np.clip(np.rint(val), 0, 255).astype(np.uint8).reshape(cam.height, cam.width)
 
 
-def half_sample(img: np.ndarray) -> np.ndarray:
-    """[EXT] vk::halfSample scalar rule (a+b+c+d)/4, integer division (svo/src/frame.cpp:156-165)."""
+PYR_SCALAR, PYR_X86 = 0, 1
+
+
+def half_sample(img: np.ndarray, rule: int = PYR_X86) -> np.ndarray:
+    """[EXT] vk::halfSample (svo/src/frame.cpp:156-165).  PYR_X86 (default) = what the reference's x86 build computes:
+    vikit's SSE2 branch -- rounded vertical average, then rounded average of adjacent columns -- when the input width is
+    a multiple of 16, else the scalar rule (a+b+c+d)/4 with integer division; PYR_SCALAR = the scalar rule always."""
     h, w = img.shape[0] // 2, img.shape[1] // 2
     i = img[: 2 * h, : 2 * w].astype(np.uint16)
+    if rule == PYR_X86 and img.shape[1] % 16 == 0:
+        v = (i[0::2, :] + i[1::2, :] + 1) >> 1
+        return ((v[:, 0::2] + v[:, 1::2] + 1) >> 1).astype(np.uint8)
     return ((i[0::2, 0::2] + i[0::2, 1::2] + i[1::2, 0::2] + i[1::2, 1::2]) // 4).astype(np.uint8)
 
 
-def build_pyramid(img: np.ndarray, n_levels: int) -> list[np.ndarray]:
+def build_pyramid(img: np.ndarray, n_levels: int, rule: int = PYR_X86) -> list[np.ndarray]:
     pyr = [np.ascontiguousarray(img)]
     for _ in range(1, n_levels):
-        pyr.append(np.ascontiguousarray(half_sample(pyr[-1])))
+        pyr.append(np.ascontiguousarray(half_sample(pyr[-1], rule)))
     return pyr
 
 

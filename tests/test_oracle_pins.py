@@ -488,3 +488,28 @@ def test_oracle_matcher_wide_baseline_equals_reference_source_compiled_here(orac
             assert np.allclose(r["px_cur"], o["px_cur"], rtol=0, atol=1e-9), i
         levels.append(o["search_level"])
     assert len(set(levels)) > 1
+
+
+# ---- vk::halfSample / createImgPyramid: the rounding rule the reference's x86 build applies -------------------------------
+@pytest.mark.parametrize("size,levels", [((640, 480), 5), ((752, 480), 5), ((1920, 1080), 6), ((656, 490), 5), ((70, 50), 3)])
+def test_pyramid_rule_reference_source_compiled_here(oracle, size, levels):
+    """oracle/_ref = the reference's own frame.cpp (createImgPyramid) over the restated vk::halfSample with REAL SSE2
+    intrinsics (the branch vikit takes when cols % 16 == 0 and the buffers are 16-byte aligned).  The oracle's plain-C
+    restatement of that rule (PYR_X86) and the numpy one must equal it bit for bit at every level; the scalar rule must
+    NOT wherever the SSE2 branch is taken."""
+    if oracle.ref_lib() is None:
+        pytest.skip("oracle/_ref not built (no /root/reference on this box)")
+    from rpg_svo_b200 import synth
+
+    w, h = size
+    img = np.random.default_rng(w + 3 * h).integers(0, 256, (h, w), dtype=np.uint8)
+    ref = oracle.ref_image_pyramid(img, levels)
+    cur = img
+    for l in range(levels):
+        assert np.array_equal(ref[l], cur), f"level {l}"
+        if l + 1 < levels:
+            nxt = oracle.half_sample(cur, oracle.PYR_X86)
+            assert np.array_equal(nxt, synth.half_sample(cur, synth.PYR_X86))
+            if cur.shape[1] % 16 == 0:
+                assert not np.array_equal(nxt, oracle.half_sample(cur, oracle.PYR_SCALAR))
+            cur = nxt
