@@ -9,7 +9,7 @@
  *   svo_b200_find_match_direct      <- Matcher::findMatchDirect               svo/include/svo/matcher.h:109-112
  *   svo_b200_reproject_map          <- Reprojector::reprojectMap              svo/include/svo/reprojector.h:58-62, svo/src/reprojector.cpp:64-217
  *   svo_b200_fast_detect            <- feature_detection::FastDetector::detect svo/include/svo/feature_detection.h:107-122, svo/src/feature_detection.cpp:66-115
- *   svo_b200_pose_optimize          <- pose_optimizer::optimizeGaussNewton    svo/include/svo/pose_optimizer.h:37-45
+ *   svo_b200_pose_optimize(_batch)  <- pose_optimizer::optimizeGaussNewton    svo/include/svo/pose_optimizer.h:37-45
  *   svo_b200_point_optimize_batch   <- Point::optimize                        svo/include/svo/point.h:86, svo/src/point.cpp:119-177
  *   svo_b200_depth_filter_update    <- DepthFilter::updateSeeds               svo/include/svo/depth_filter.h:155
  *                                      (Matcher::findEpipolarMatchDirect, updateSeed, computeTau inside)
@@ -86,8 +86,8 @@ int svo_b200_frame_create(svo_b200_ctx* ctx, int width, int height, int n_levels
  *       source level's width is a multiple of 16 (cv::Mat buffers are 16-byte aligned), else the scalar branch;
  *   SVO_B200_PYR_SCALAR         (a+b+c+d)/4 with integer division at every level (non-SIMD builds).
  * 640, 752 and 1920 are multiples of 16, so on x86 at least the first level always takes the SSE2 branch. */
-#define SVO_B200_PYR_X86 0
-#define SVO_B200_PYR_SCALAR 1
+#define SVO_B200_PYR_SCALAR 0
+#define SVO_B200_PYR_X86 1
 int svo_b200_set_pyramid_rule(svo_b200_ctx* ctx, int rule);
 
 /* Upload n_given >= 1 levels from host memory (levels[l] has pitch == width>>l).  Levels
@@ -222,6 +222,13 @@ int svo_b200_pose_optimize(svo_b200_ctx* ctx, double reproj_thresh, int n_iter,
                            double fx /*cam->errorMultiplier2()*/, double* T_f_w_io, const double* f,
                            const double* point_pos, const int* level, uint8_t* has_point_io, int N,
                            svo_b200_pose_opt_result* out);
+
+/* B frames in one launch (one CTA per frame): frame b owns observations [obs_offset[b], obs_offset[b+1]) of the
+ * concatenated arrays; fx[b] = that frame's cam->errorMultiplier2().  Same results as B single calls. */
+int svo_b200_pose_optimize_batch(svo_b200_ctx* ctx, int B, double reproj_thresh, int n_iter, const double* fx /*B*/,
+                                 double* T_f_w_io /*B*12*/, const int* obs_offset /*B+1*/, const double* f,
+                                 const double* point_pos, const int* level, uint8_t* has_point_io,
+                                 svo_b200_pose_opt_result* out /*B*/);
 
 /* Point::optimize (svo/src/point.cpp:119-177) for P independent points ("next" row f3: structure
  * refinement after the pose optimizer, frame_handler_base.cpp:178-196).  Point p owns observations

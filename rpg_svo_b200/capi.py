@@ -270,7 +270,7 @@ class Context:
                                                       _p(fo), _p(px), _p(f), _p(pos), _p(hp), _p(rpos)))
 
     def set_pyramid_rule(self, rule: int):
-        """0 = PYR_X86 (vikit's SSE2 rounding where an x86 build of the reference takes it; default), 1 = PYR_SCALAR."""
+        """1 = PYR_X86 (vikit's SSE2 rounding where an x86 build of the reference takes it; default), 0 = PYR_SCALAR."""
         self._check(self.lib.svo_b200_set_pyramid_rule(self.h, int(rule)))
 
     def sia_config(self, ctas_per_pair=-1, features_per_thread=0):
@@ -383,6 +383,25 @@ def _pose_optimize(self, reproj_thresh, n_iter, fx, T_f_w, f, pos, level, has_po
                 cov=np.array(out.cov[:]).reshape(6, 6))
 
 
+def _pose_optimize_batch(self, reproj_thresh, n_iter, fx, T_f_w, obs_offset, f, pos, level, has_point):
+    """B frames in one launch (svo_b200_pose_optimize_batch); returns a list of dicts like pose_optimize."""
+    off = _i32(obs_offset)
+    B = len(off) - 1
+    T = c64(T_f_w).copy().reshape(B, 12)
+    hp = _u8(has_point).copy()
+    out = (PoseOptResult * B)()
+    fxa = c64(np.broadcast_to(np.asarray(fx, np.float64), (B,)))
+    self._check(self.lib.svo_b200_pose_optimize_batch(self.h, B, C.c_double(reproj_thresh), int(n_iter), _p(fxa), _p(T), _p(off),
+                                                      _p(c64(f)), _p(c64(pos)), _p(_i32(level)), _p(hp), out))
+    res = []
+    for b in range(B):
+        o = out[b]
+        res.append(dict(T=T[b].reshape(3, 4), has_point=hp[off[b]:off[b + 1]], estimated_scale=o.estimated_scale,
+                        error_init=o.error_init, error_final=o.error_final, num_obs=o.num_obs, n_iter_done=o.n_iter_done,
+                        cov=np.array(o.cov[:]).reshape(6, 6)))
+    return res
+
+
 def _depth_filter_update(self, ref_frames, ref_T_f_w, cur: Frame, cur_T_f_w, cam, ref_index, ftr_px, ftr_f, ftr_level,
                          ftr_type, ftr_grad, batch_id, batch_counter, seeds, max_n_kfs=3, sigma2_thresh=200.0,
                          max_search_level=2, align_max_iter=10, max_epi_search_steps=1000):
@@ -411,6 +430,7 @@ Context.align2d_batch = _align2d_batch
 Context.align1d_batch = _align1d_batch
 Context.find_match_direct = _find_match_direct
 Context.pose_optimize = _pose_optimize
+Context.pose_optimize_batch = _pose_optimize_batch
 Context.depth_filter_update = _depth_filter_update
 
 

@@ -2,14 +2,22 @@
 //
 // Replaces svo/src/pose_optimizer.cpp:28-161: robust (Tukey weights, MAD scale) Gauss-Newton on the
 // unit-plane reprojection error of one frame, outlier culling, covariance and the median error
-// statistics.  One CTA runs the whole optimisation on the device (<= n_iter iterations without a host
-// round trip): threads stride over the features, every iteration ends in a 28-value block reduction
-// (21 unique A entries, 6 b entries, chi2), thread 0 factorises the 6x6 system, applies
-// T <- exp(dT) * T and the accept / rollback rule, and broadcasts the pose.  The three medians
-// ([EXT] vk::getMedian = nth_element at floor(n/2)) are exact order statistics obtained by an
-// 8-pass radix select on order-preserving keys in shared memory.  All arithmetic is f64 except the f32 error vector / Tukey weight, as
-// in the reference.
+// statistics.  One CTA per frame runs the whole optimisation on the device (<= n_iter iterations without a
+// host round trip); a batch of frames is one launch (grid = #frames).
+//   * the per-observation constants -- point position, project2d(f), 1/(1<<level) -- are computed once and
+//     kept in shared memory (SoA, conflict free): an iteration re-reads 48 B per observation from shared
+//     memory instead of 52 B from global memory and performs no division but the two of project2d(xyz),
+//     which are a Newton reciprocal + one correction step (correctly rounded, like the reference's `/`);
+//   * every iteration ends in a 28-value block reduction (21 unique A entries, 6 b entries, chi2: transposed
+//     warp shuffles, one shared-memory hop, ONE barrier), after which warp 0 alone -- all lanes redundantly, in
+//     registers -- factorises the 6x6 system, applies T <- exp(dT) * T and the accept / rollback rule and
+//     publishes the pose (second barrier);
+//   * the three medians ([EXT] vk::getMedian = nth_element at floor(n/2)) are exact order statistics by an
+//     MSB-first radix select on order-preserving keys that stops as soon as one candidate is left (3-4 passes of
+//     8 bits instead of 8); error_init and error_final are selected in the same passes.
+// All arithmetic is f64 except the f32 error vector / Tukey weight, as in the reference.
 #include <cstring>
+#include <vector>
 
 #include "ctx.h"
 #include "svo_math.cuh"
@@ -21,15 +29,16 @@ constexpr int kPoWarps = kPoThreads / 32;
 constexpr int kPoK = 28;
 
 struct PoseOptParams {
-  const double* f;
+  const double* f;      // all frames' observations, concatenated
   const double* pos;
   const int* level;
-  uint8_t* has_point;  // in/out
-  int N;
+  uint8_t* has_point;   // in/out
+  const int* obs_offset;  // B+1
+  const double* fx;       // B: cam->errorMultiplier2()
   int n_iter;
-  double fx, reproj_thresh;
-  double* T_io;  // 12
-  svo_b200_pose_opt_result* out;
+  double reproj_thresh;
+  double* T_io;  // B*12
+  svo_b200_pose_opt_result* out;  // B
 };
 
 struct PoseOptShared {
@@ -37,14 +46,14 @@ struct PoseOptShared {
   double sums[kPoK];
   double R[9], t[3];
   double A[36];
-  double x[8];
-  double med;
-  Pose T, T_old;
+  double med[2];
+  Pose T, T_old;   // frame->T_f_w_ and the roll-back copy (warp 0)
+  double chi2;
   Solver6 sol;
-  double chi2, scale;
-  int done, num_obs, iters, n_deleted;
-  unsigned hist[256];
-  int sel_bin, sel_k;
+  double x[8];
+  int done, iters;
+  unsigned hist[2][256];
+  int sel_bin[2], sel_k[2], sel_cnt[2];
 };
 
 // [EXT] vk::robust_cost::TukeyWeightFunction::value, b = 4.6851f
@@ -58,8 +67,10 @@ __device__ __forceinline__ float tukey_weight(float x) {
   return 0.0f;
 }
 
+// Per-warp partial sums of K values into s.part, then ONE barrier.  Afterwards po_total(k) (any thread) adds the
+// per-warp partials of value k in warp order.
 template <int K>
-__device__ __forceinline__ void po_block_sum(double (&v)[K], PoseOptShared& s) {
+__device__ __forceinline__ void po_partials(double (&v)[K], PoseOptShared& s) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (K == kPoK) {  // 28 = 16 + 8 (transposed reductions) + 4 (tree)
     double a16[16], a8[8], a4[4];
@@ -86,165 +97,209 @@ __device__ __forceinline__ void po_block_sum(double (&v)[K], PoseOptShared& s) {
     }
   }
   __syncthreads();
-  if (warp == 0) {
-    if (lane < K) {
-      double acc = 0.0;
-      for (int w = 0; w < kPoWarps; ++w) acc += s.part[w * kPoK + lane];
-      s.sums[lane] = acc;
-    }
-    __syncwarp();
-  }
-  __syncthreads();
+}
+__device__ __forceinline__ double po_total(const PoseOptShared& s, int k) {
+  double acc = 0.0;
+#pragma unroll
+  for (int w = 0; w < kPoWarps; ++w) acc += s.part[w * kPoK + k];
+  return acc;
 }
 
-// k-th smallest (0-based) of the entries of v[0..N) whose valid flag is set: exact order statistic by
-// MSB-first radix select on order-preserving 64-bit keys (8 passes of 8 bits; shared-memory histogram,
-// warp-parallel bin scan).  Result in s.med (NaN if there are no more than k valid entries).
+// k-th smallest (0-based) of the valid entries of NA arrays at once (same validity flags, same k): exact order
+// statistics by MSB-first radix select on order-preserving 64-bit keys, 8 bits per pass, shared-memory histograms,
+// warp-parallel bin scan.  An array drops out as soon as its selected bin holds a single candidate (that element is
+// then found in the next sweep).  Results in s.med[a] (NaN if there are no more than k valid entries).
 __device__ __forceinline__ unsigned long long order_key(double d) {
   const unsigned long long u = (unsigned long long)__double_as_longlong(d);
   return (u >> 63) ? ~u : (u | 0x8000000000000000ULL);
 }
-__device__ void block_kth(const double* v, const uint8_t* valid, int N, int k, PoseOptShared& s) {
-  unsigned long long prefix = 0, mask = 0;
-  int kk = k;
-  for (int pass = 7; pass >= 0; --pass) {
+template <int NA>
+__device__ void block_kth(const double* const (&v)[NA], const uint8_t* valid, int N, int k, PoseOptShared& s) {
+  unsigned long long prefix[NA], mask[NA];
+  int kk[NA], state[NA];  // state: 0 = selecting, 1 = one candidate left (pick it up in the next sweep), 2 = done
+#pragma unroll
+  for (int a = 0; a < NA; ++a) { prefix[a] = 0; mask[a] = 0; kk[a] = k; state[a] = 0; }
+  for (int pass = 7; pass >= -1; --pass) {
+    bool any = false;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) any = any || state[a] != 2;
+    if (!any) break;
     const int shift = pass * 8;
-    for (int b = threadIdx.x; b < 256; b += blockDim.x) s.hist[b] = 0;
+    for (int b = threadIdx.x; b < 256 * NA; b += blockDim.x) (&s.hist[0][0])[b] = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < N; i += blockDim.x) {
       if (!valid[i]) continue;
-      const unsigned long long key = order_key(v[i]);
-      if ((key & mask) == prefix) atomicAdd(&s.hist[(unsigned)(key >> shift) & 255u], 1u);
+#pragma unroll
+      for (int a = 0; a < NA; ++a) {
+        if (state[a] == 2) continue;
+        const unsigned long long key = order_key(v[a][i]);
+        if ((key & mask[a]) != prefix[a]) continue;
+        if (state[a] == 1 || pass < 0) s.med[a] = v[a][i];  // the single remaining candidate (ties: identical values)
+        else atomicAdd(&s.hist[a][(unsigned)(key >> shift) & 255u], 1u);
+      }
     }
     __syncthreads();
-    if (threadIdx.x < 32) {  // warp 0: lane l owns bins [8l, 8l+8)
-      const int lane = threadIdx.x;
-      unsigned loc[8], sum = 0;
+    if (threadIdx.x < 32 * NA) {  // warp a scans array a: lane l owns bins [8l, 8l+8)
+      const int a = threadIdx.x >> 5, lane = threadIdx.x & 31;
+      const int st_a = (NA == 1 || a == 0) ? state[0] : state[NA - 1];
+      const int kk_a = (NA == 1 || a == 0) ? kk[0] : kk[NA - 1];
+      if (st_a == 0 && pass >= 0) {
+        unsigned loc[8], sum = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { loc[j] = s.hist[8 * lane + j]; sum += loc[j]; }
-      unsigned inc = sum;
+        for (int j = 0; j < 8; ++j) { loc[j] = s.hist[a][8 * lane + j]; sum += loc[j]; }
+        unsigned inc = sum;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-      }
-      const unsigned exc = inc - sum;
-      const unsigned hit = __ballot_sync(0xffffffffu, inc > (unsigned)kk);
-      if (hit == 0) {
-        if (lane == 0) { s.sel_bin = -1; }
-      } else if (lane == __ffs(hit) - 1) {
-        unsigned cum = exc;
-        int bin = 8 * lane;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          if (cum + loc[j] > (unsigned)kk) { bin = 8 * lane + j; break; }
-          cum += loc[j];
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned t = __shfl_up_sync(0xffffffffu, inc, o);
+          if (lane >= o) inc += t;
         }
-        s.sel_bin = bin;
-        s.sel_k = kk - (int)cum;
+        const unsigned exc = inc - sum;
+        const int target = kk_a;
+        const unsigned hit = __ballot_sync(0xffffffffu, inc > (unsigned)target);
+        if (hit == 0) {
+          if (lane == 0) s.sel_bin[a] = -1;
+        } else if (lane == __ffs(hit) - 1) {
+          unsigned cum = exc;
+          int bin = 8 * lane;
+          unsigned cnt = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (cum + loc[j] > (unsigned)target) { bin = 8 * lane + j; cnt = loc[j]; break; }
+            cum += loc[j];
+          }
+          s.sel_bin[a] = bin;
+          s.sel_k[a] = target - (int)cum;
+          s.sel_cnt[a] = (int)cnt;
+        }
       }
     }
     __syncthreads();
-    if (s.sel_bin < 0) {  // fewer than k+1 valid entries
-      if (threadIdx.x == 0) s.med = __longlong_as_double(0x7ff8000000000000LL);
-      __syncthreads();
-      return;
+#pragma unroll
+    for (int a = 0; a < NA; ++a) {
+      if (state[a] == 1 || (state[a] == 0 && pass < 0)) { state[a] = 2; continue; }
+      if (state[a] != 0) continue;
+      if (s.sel_bin[a] < 0) {  // fewer than k+1 valid entries
+        if (threadIdx.x == 0) s.med[a] = __longlong_as_double(0x7ff8000000000000LL);
+        state[a] = 2;
+        continue;
+      }
+      prefix[a] |= (unsigned long long)s.sel_bin[a] << shift;
+      mask[a] |= 0xffULL << shift;
+      kk[a] = s.sel_k[a];
+      if (s.sel_cnt[a] == 1 || pass == 0) state[a] = 1;  // unique candidate, or all 64 bits fixed: equal values
     }
-    prefix |= (unsigned long long)s.sel_bin << shift;
-    mask |= 0xffULL << shift;
-    kk = s.sel_k;
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    const unsigned long long u = (prefix >> 63) ? (prefix & 0x7fffffffffffffffULL) : ~prefix;
-    s.med = __longlong_as_double((long long)u);
   }
   __syncthreads();
 }
 
-__device__ __forceinline__ void reproj_error(const PoseOptParams& P, int i, const double* R, const double* t,
-                                             double& ex, double& ey, double* xyz_f) {
-  const double px = P.pos[3 * i], py = P.pos[3 * i + 1], pz = P.pos[3 * i + 2];
-  // xyz_f = T_f_w * pos
-  xyz_f[0] = R[0] * px + R[1] * py + R[2] * pz + t[0];
-  xyz_f[1] = R[3] * px + R[4] * py + R[5] * pz + t[1];
-  xyz_f[2] = R[6] * px + R[7] * py + R[8] * pz + t[2];
-  const double fxn = P.f[3 * i] / P.f[3 * i + 2], fyn = P.f[3 * i + 1] / P.f[3 * i + 2];  // project2d(f)
-  const double sic = 1.0 / (double)(1 << P.level[i]);
-  ex = (fxn - xyz_f[0] / xyz_f[2]) * sic;
-  ey = (fyn - xyz_f[1] / xyz_f[2]) * sic;
+// SoA view of one frame's observations in shared memory
+struct PoObs {
+  double *px, *py, *pz, *fxn, *fyn, *sic, *work, *init;
+  uint8_t* valid;
+};
+
+// e = (project2d(f) - project2d(T_f_w * pos)) / (1 << level)  (:52-54, :82-85, :135-137); xyz_f out
+__device__ __forceinline__ void reproj_error(const PoObs& o, int i, const double (&R)[9], const double (&t)[3], double& ex,
+                                             double& ey, double (&p)[3], double& z_inv) {
+  const double X = o.px[i], Y = o.py[i], Z = o.pz[i];
+  p[0] = R[0] * X + R[1] * Y + R[2] * Z + t[0];
+  p[1] = R[3] * X + R[4] * Y + R[5] * Z + t[1];
+  p[2] = R[6] * X + R[7] * Y + R[8] * Z + t[2];
+  z_inv = rcp_rn(p[2]);
+  const double sic = o.sic[i];
+  ex = (o.fxn[i] - div_rn(p[0], p[2], z_inv)) * sic;
+  ey = (o.fyn[i] - div_rn(p[1], p[2], z_inv)) * sic;
 }
 
 __global__ void __launch_bounds__(kPoThreads) pose_opt_kernel(PoseOptParams P) {
   extern __shared__ __align__(16) unsigned char po_smem[];
   PoseOptShared& s = *reinterpret_cast<PoseOptShared*>(po_smem);
-  double* work = reinterpret_cast<double*>(po_smem + ((sizeof(PoseOptShared) + 15) & ~size_t(15)));
-  double* init = work + P.N;
-  const int tid = threadIdx.x, N = P.N;
+  const int fr = blockIdx.x;
+  const int o0 = P.obs_offset[fr], N = P.obs_offset[fr + 1] - o0;
+  const int Np = (N + 1) & ~1;
+  PoObs o;
+  o.px = reinterpret_cast<double*>(po_smem + ((sizeof(PoseOptShared) + 15) & ~size_t(15)));
+  o.py = o.px + Np; o.pz = o.py + Np; o.fxn = o.pz + Np; o.fyn = o.fxn + Np; o.sic = o.fyn + Np;
+  o.work = o.sic + Np; o.init = o.work + Np;
+  o.valid = reinterpret_cast<uint8_t*>(o.init + Np);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const double fx = P.fx[fr];
+  uint8_t* has_point = P.has_point + o0;
 
+  // ---- per-observation constants, once ------------------------------------------------------------
+  double cnt[1] = {0.0};
+  for (int i = tid; i < N; i += kPoThreads) {
+    const uint8_t hp = has_point[i];
+    o.valid[i] = hp;
+    if (!hp) continue;
+    const size_t g = (size_t)(o0 + i);
+    o.px[i] = P.pos[3 * g]; o.py[i] = P.pos[3 * g + 1]; o.pz[i] = P.pos[3 * g + 2];
+    const double f2 = P.f[3 * g + 2];
+    o.fxn[i] = P.f[3 * g] / f2;  // vk::project2d(f)
+    o.fyn[i] = P.f[3 * g + 1] / f2;
+    o.sic[i] = 1.0 / (double)(1 << P.level[g]);
+    cnt[0] += 1.0;
+  }
+  // pose: every thread derives R, t from the input itself (same arithmetic everywhere)
+  double R[9], t[3];
+  {
+    const Pose T0 = pose_from_rt12(P.T_io + 12 * (size_t)fr);
+    qmatrix(T0.q, R);
+    t[0] = T0.t[0]; t[1] = T0.t[1]; t[2] = T0.t[2];
+    if (tid == 0) { s.T = T0; s.T_old = T0; s.chi2 = 0.0; }
+  }
   if (tid == 0) {
-    s.T = pose_from_rt12(P.T_io);
-    s.T_old = s.T;
-    qmatrix(s.T.q, s.R);
-    s.t[0] = s.T.t[0]; s.t[1] = s.T.t[1]; s.t[2] = s.T.t[2];
-    s.chi2 = 0.0; s.done = 0; s.iters = 0; s.n_deleted = 0;
+    s.done = 0; s.iters = 0;
     for (int k = 0; k < 36; ++k) s.A[k] = 0.0;
   }
-  __syncthreads();
-
-  // ---- scale of the error for robust estimation (:47-60) ------------------------------------
-  double cnt[1] = {0.0};
-  {
-    double R[9], t[3];
-    for (int k = 0; k < 9; ++k) R[k] = s.R[k];
-    for (int k = 0; k < 3; ++k) t[k] = s.t[k];
-    for (int i = tid; i < N; i += kPoThreads) {
-      if (!P.has_point[i]) continue;
-      double ex, ey, xyz[3];
-      reproj_error(P, i, R, t, ex, ey, xyz);
-      work[i] = (double)(float)sqrt(ex * ex + ey * ey);  // errors.push_back(e.norm()) -> float
-      cnt[0] += 1.0;
-    }
-  }
-  po_block_sum<1>(cnt, s);
-  const int num_obs = (int)s.sums[0];
+  po_partials<1>(cnt, s);
+  const int num_obs = (int)po_total(s, 0);
   if (num_obs == 0) {  // errors.empty() -> return (:57-58)
     if (tid == 0) {
       svo_b200_pose_opt_result r;
       memset(&r, 0, sizeof(r));
-      *P.out = r;
+      P.out[fr] = r;
     }
     return;
   }
-  block_kth(work, P.has_point, N, num_obs / 2, s);
+  // ---- scale of the error for robust estimation (:47-60) ------------------------------------
+  for (int i = tid; i < N; i += kPoThreads) {
+    if (!o.valid[i]) continue;
+    double ex, ey, p[3], zi;
+    reproj_error(o, i, R, t, ex, ey, p, zi);
+    o.work[i] = (double)(float)sqrt(ex * ex + ey * ey);  // errors.push_back(e.norm()) -> float
+  }
+  __syncthreads();
+  {
+    const double* const arr[1] = {o.work};
+    block_kth<1>(arr, o.valid, N, num_obs / 2, s);
+  }
   // [EXT] MADScaleEstimator: 1.48f * median (float arithmetic)
-  const double estimated_scale = (double)__fmul_rn(1.48f, (float)s.med);
+  const double estimated_scale = (double)__fmul_rn(1.48f, (float)s.med[0]);
   double scale = estimated_scale;
 
   // ---- Gauss-Newton (:63-121) -------------------------------------------------------------------
   for (int iter = 0; iter < P.n_iter; ++iter) {
-    if (iter == 5) scale = 0.85 / P.fx;  // (:69-70)
-    double R[9], t[3];
-    for (int k = 0; k < 9; ++k) R[k] = s.R[k];
-    for (int k = 0; k < 3; ++k) t[k] = s.t[k];
+    if (iter == 5) scale = 0.85 / fx;  // (:69-70)
+    const double scale_rcp = rcp_rn(scale);
     double acc[kPoK];
 #pragma unroll
     for (int k = 0; k < kPoK; ++k) acc[k] = 0.0;
     for (int i = tid; i < N; i += kPoThreads) {
-      if (!P.has_point[i]) continue;
-      double ex, ey, p[3];
-      reproj_error(P, i, R, t, ex, ey, p);
-      const double sic = 1.0 / (double)(1 << P.level[i]);
+      if (!o.valid[i]) continue;
+      double ex, ey, p[3], z_inv;
+      reproj_error(o, i, R, t, ex, ey, p, z_inv);
+      const double sic = o.sic[i];
       // Frame::jacobian_xyz2uv (frame.h:116-138), then J *= sqrt_inv_cov
-      const double x = p[0], y = p[1], z_inv = 1. / p[2], z_inv_2 = z_inv * z_inv;
+      const double x = p[0], y = p[1], z_inv_2 = z_inv * z_inv;
       double J0[6], J1[6];
       J0[0] = -z_inv; J0[1] = 0.0; J0[2] = x * z_inv_2; J0[3] = y * J0[2]; J0[4] = -(1.0 + x * J0[2]); J0[5] = y * z_inv;
       J1[0] = 0.0; J1[1] = -z_inv; J1[2] = y * z_inv_2; J1[3] = 1.0 + y * J1[2]; J1[4] = -J0[3]; J1[5] = -x * z_inv;
 #pragma unroll
       for (int k = 0; k < 6; ++k) { J0[k] *= sic; J1[k] *= sic; }
       const double e_sq = ex * ex + ey * ey;
-      if (iter == 0) init[i] = e_sq;  // chi2_vec_init (:87-88)
-      const double w = (double)tukey_weight((float)(sqrt(e_sq) / scale));
+      if (iter == 0) o.init[i] = e_sq;  // chi2_vec_init (:87-88)
+      const double w = (double)tukey_weight((float)div_rn(sqrt(e_sq), scale, scale_rcp));  // e.norm() / scale, correctly rounded
       int idx = 0;
 #pragma unroll
       for (int r = 0; r < 6; ++r)
@@ -254,76 +309,101 @@ __global__ void __launch_bounds__(kPoThreads) pose_opt_kernel(PoseOptParams P) {
       for (int r = 0; r < 6; ++r) acc[21 + r] -= (J0[r] * ex + J1[r] * ey) * w;
       acc[27] += e_sq * w;
     }
-    po_block_sum<kPoK>(acc, s);
-    if (tid == 0) {
-      int idx = 0;
-      for (int r = 0; r < 6; ++r)
-        for (int c = r; c < 6; ++c, ++idx) { s.A[r * 6 + c] = s.sums[idx]; s.A[c * 6 + r] = s.sums[idx]; }
+    po_partials<kPoK>(acc, s);  // barrier A
+    if (warp == 0) {
+      // warp 0: totals (lane k adds value k over the warps), then every lane runs the 6x6 solve and the update
+      // redundantly in registers; lane 0 publishes
+      if (lane < kPoK) s.sums[lane] = po_total(s, lane);
+      __syncwarp();
+      double h[21], b[6];
+#pragma unroll
+      for (int k = 0; k < 21; ++k) h[k] = s.sums[k];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) b[k] = s.sums[21 + k];
       const double new_chi2 = s.sums[27];
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int c = r; c < 6; ++c) { s.A[r * 6 + c] = h[upper_idx(r, c)]; s.A[c * 6 + r] = h[upper_idx(r, c)]; }
+      }
       double dT[6];
-      solver_factor(s.sol, s.A);
-      if (!s.sol.pivoted) {
-        double b[6];
-        for (int k = 0; k < 6; ++k) b[k] = s.sums[21 + k];
-        fact6_solve(s.sol.F, b, dT);
-      } else {
-        for (int k = 0; k < 6; ++k) s.x[k] = s.sums[21 + k];
-        ldlt6_solve(s.sol.ldl, s.sol.tr, s.x);
+      Fact6 F;
+      if (fact6_compute_upper(h, F)) {
+        fact6_solve(F, b, dT);
+      } else {  // degenerate A: the pivoted Eigen-like LDL^T, through shared memory
+        __syncwarp();
+        if (lane == 0) {
+          for (int k = 0; k < 36; ++k) s.sol.ldl[k] = s.A[k];
+          ldlt6_factor(s.sol.ldl, s.sol.tr);
+          for (int k = 0; k < 6; ++k) s.x[k] = b[k];
+          ldlt6_solve(s.sol.ldl, s.sol.tr, s.x);
+        }
+        __syncwarp();
+#pragma unroll
         for (int k = 0; k < 6; ++k) dT[k] = s.x[k];
       }
-      s.iters++;
+      int done = 0;
+      Pose T = s.T;
+      __syncwarp();
       if ((iter > 0 && new_chi2 > s.chi2) || isnan(dT[0])) {
-        s.T = s.T_old;  // roll-back (:100-107)
-        s.done = 1;
+        T = s.T_old;  // roll-back (:100-107)
+        done = 1;
+        __syncwarp();
+        if (lane == 0) s.T = T;
       } else {
-        const Pose Tn = pose_mul_fast(se3_exp_fast(dT), s.T);  // exp(dT) * T  (:110)
-        s.T_old = s.T;
-        s.T = Tn;
-        s.chi2 = new_chi2;
+        const Pose Tn = pose_mul_fast(se3_exp_fast(dT), T);  // exp(dT) * T  (:110)
         double m = 0;
+#pragma unroll
         for (int k = 0; k < 6; ++k) m = fmax(m, fabs(dT[k]));
-        if (m <= 0.0000000001) s.done = 1;  // EPS (global.h:77)
+        if (m <= 0.0000000001) done = 1;  // EPS (global.h:77)
+        __syncwarp();
+        if (lane == 0) { s.T_old = T; s.T = Tn; s.chi2 = new_chi2; }
+        T = Tn;
       }
-      qmatrix(s.T.q, s.R);
-      s.t[0] = s.T.t[0]; s.t[1] = s.T.t[1]; s.t[2] = s.T.t[2];
+      if (lane == 0) {
+        qmatrix(T.q, s.R);
+        s.t[0] = T.t[0]; s.t[1] = T.t[1]; s.t[2] = T.t[2];
+        s.done = done;
+        s.iters++;
+      }
     }
-    __syncthreads();
+    __syncthreads();  // barrier B
+#pragma unroll
+    for (int k = 0; k < 9; ++k) R[k] = s.R[k];
+    t[0] = s.t[0]; t[1] = s.t[1]; t[2] = s.t[2];
     if (s.done) break;
   }
 
   // ---- remove measurements with too large reprojection error (:129-145) ------------------------
-  const double thresh = P.reproj_thresh / P.fx;
+  const double thresh = P.reproj_thresh / fx;
   double del[1] = {0.0};
-  {
-    double R[9], t[3];
-    for (int k = 0; k < 9; ++k) R[k] = s.R[k];
-    for (int k = 0; k < 3; ++k) t[k] = s.t[k];
-    for (int i = tid; i < N; i += kPoThreads) {
-      if (!P.has_point[i]) continue;
-      double ex, ey, xyz[3];
-      reproj_error(P, i, R, t, ex, ey, xyz);
-      const double e_sq = ex * ex + ey * ey;
-      work[i] = e_sq;  // chi2_vec_final
-      if (sqrt(e_sq) > thresh) del[0] += 1.0;
-    }
+  for (int i = tid; i < N; i += kPoThreads) {
+    if (!o.valid[i]) continue;
+    double ex, ey, p[3], zi;
+    reproj_error(o, i, R, t, ex, ey, p, zi);
+    const double e_sq = ex * ex + ey * ey;
+    o.work[i] = e_sq;  // chi2_vec_final
+    if (sqrt(e_sq) > thresh) del[0] += 1.0;
   }
+  po_partials<1>(del, s);
+  const int n_deleted = (int)po_total(s, 0);
   // medians use the pre-culling validity flags: both vectors hold one entry per original observation
-  block_kth(init, P.has_point, N, num_obs / 2, s);
-  const double med_init = (P.n_iter > 0) ? s.med : 0.0;
-  __syncthreads();
-  block_kth(work, P.has_point, N, num_obs / 2, s);
-  const double med_final = s.med;
-  __syncthreads();
+  {
+    const double* const arr[2] = {o.init, o.work};
+    block_kth<2>(arr, o.valid, N, num_obs / 2, s);
+  }
+  const double med_init = (P.n_iter > 0) ? s.med[0] : 0.0;
+  const double med_final = s.med[1];
   for (int i = tid; i < N; i += kPoThreads)
-    if (P.has_point[i] && sqrt(work[i]) > thresh) P.has_point[i] = 0;  // point = NULL
-  po_block_sum<1>(del, s);
+    if (o.valid[i] && sqrt(o.work[i]) > thresh) has_point[i] = 0;  // point = NULL
 
   if (tid == 0) {
     svo_b200_pose_opt_result r;
     memset(&r, 0, sizeof(r));
     // Cov_ = (A * fx^2)^-1  (:125-126), Gauss-Jordan with partial pivoting on [A|I]
     double M[6][12];
-    const double f2 = P.fx * P.fx;
+    const double f2 = fx * fx;
     for (int a = 0; a < 6; ++a)
       for (int b = 0; b < 6; ++b) { M[a][b] = s.A[a * 6 + b] * f2; M[a][6 + b] = (a == b) ? 1.0 : 0.0; }
     for (int c = 0; c < 6; ++c) {
@@ -342,13 +422,13 @@ __global__ void __launch_bounds__(kPoThreads) pose_opt_kernel(PoseOptParams P) {
     }
     for (int a = 0; a < 6; ++a)
       for (int b = 0; b < 6; ++b) r.cov[a * 6 + b] = M[a][6 + b];
-    r.estimated_scale = estimated_scale * P.fx;
-    r.error_init = sqrt(med_init) * P.fx;
-    r.error_final = sqrt(med_final) * P.fx;
-    r.num_obs = (long long)num_obs - (long long)s.sums[0];
+    r.estimated_scale = estimated_scale * fx;
+    r.error_init = sqrt(med_init) * fx;
+    r.error_final = sqrt(med_final) * fx;
+    r.num_obs = (long long)num_obs - (long long)n_deleted;
     r.n_iter_done = s.iters;
-    *P.out = r;
-    pose_to_rt12(s.T, P.T_io);
+    P.out[fr] = r;
+    pose_to_rt12(s.T, P.T_io + 12 * (size_t)fr);
   }
 }
 
@@ -356,55 +436,78 @@ __global__ void __launch_bounds__(kPoThreads) pose_opt_kernel(PoseOptParams P) {
 
 using namespace svo;
 
-extern "C" int svo_b200_pose_optimize(svo_b200_ctx* ctx, double reproj_thresh, int n_iter, double fx,
-                                      double* T_f_w_io, const double* f, const double* point_pos, const int* level,
-                                      uint8_t* has_point_io, int N, svo_b200_pose_opt_result* out) {
-  if (!ctx || !T_f_w_io || !out || N < 0 || n_iter < 0 || (N > 0 && (!f || !point_pos || !level || !has_point_io)))
-    return set_err(ctx, SVO_B200_EINVAL, "pose_optimize: bad arguments");
-  memset(out, 0, sizeof(*out));
-  if (N == 0) return 0;  // errors.empty() -> return
+extern "C" int svo_b200_pose_optimize_batch(svo_b200_ctx* ctx, int B, double reproj_thresh, int n_iter, const double* fx,
+                                            double* T_f_w_io, const int* obs_offset, const double* f,
+                                            const double* point_pos, const int* level, uint8_t* has_point_io,
+                                            svo_b200_pose_opt_result* out) {
+  if (!ctx || B < 0 || n_iter < 0 || (B > 0 && (!fx || !T_f_w_io || !obs_offset || !out)))
+    return set_err(ctx, SVO_B200_EINVAL, "pose_optimize_batch: bad arguments");
+  if (B == 0) return 0;
+  memset(out, 0, sizeof(*out) * (size_t)B);
+  const int base = obs_offset[0], total = obs_offset[B] - base;
+  int max_n = 0;
+  for (int b = 0; b < B; ++b) {
+    const int n = obs_offset[b + 1] - obs_offset[b];
+    if (n < 0) return set_err(ctx, SVO_B200_EINVAL, "pose_optimize_batch: obs_offset not monotone");
+    if (n > max_n) max_n = n;
+  }
+  if (total == 0) return 0;  // errors.empty() -> return, for every frame
+  if (!f || !point_pos || !level || !has_point_io) return set_err(ctx, SVO_B200_EINVAL, "pose_optimize_batch: NULL observation arrays");
   cudaSetDevice(ctx->device);
-  const size_t smem = ((sizeof(PoseOptShared) + 15) & ~size_t(15)) + sizeof(double) * 2 * (size_t)N;
+  const size_t smem = ((sizeof(PoseOptShared) + 15) & ~size_t(15)) + (sizeof(double) * 8 + 1) * (size_t)((max_n + 1) & ~1) + 16;
   if (smem > (size_t)ctx->max_smem_optin)
-    return set_err(ctx, SVO_B200_ELIMIT, "pose_optimize: %d features need %zu B of shared memory", N, smem);
+    return set_err(ctx, SVO_B200_ELIMIT, "pose_optimize: %d observations in one frame need %zu B of shared memory", max_n, smem);
   Carver c;
-  const size_t o_T = c.take(sizeof(double) * 12), o_hp = c.take(N), o_out = c.take(sizeof(svo_b200_pose_opt_result));
+  const size_t o_T = c.take(sizeof(double) * 12 * B), o_hp = c.take(total), o_out = c.take(sizeof(svo_b200_pose_opt_result) * B);
   const size_t io_end = c.off;
-  const size_t o_f = c.take(sizeof(double) * 3 * N), o_pos = c.take(sizeof(double) * 3 * N), o_lv = c.take(sizeof(int) * N);
+  const size_t o_f = c.take(sizeof(double) * 3 * total), o_pos = c.take(sizeof(double) * 3 * total),
+               o_lv = c.take(sizeof(int) * total), o_off = c.take(sizeof(int) * (B + 1)), o_fx = c.take(sizeof(double) * B);
   int rc;
   if ((rc = ensure_host(ctx, ctx->h_in, c.off))) return rc;
   if ((rc = ensure_dev(ctx, ctx->d_in, c.off))) return rc;
   SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
   uint8_t* h = static_cast<uint8_t*>(ctx->h_in.p);
   uint8_t* d = static_cast<uint8_t*>(ctx->d_in.p);
-  memcpy(h + o_T, T_f_w_io, sizeof(double) * 12);
-  memcpy(h + o_hp, has_point_io, N);
-  memset(h + o_out, 0, sizeof(svo_b200_pose_opt_result));
-  memcpy(h + o_f, f, sizeof(double) * 3 * N);
-  memcpy(h + o_pos, point_pos, sizeof(double) * 3 * N);
-  memcpy(h + o_lv, level, sizeof(int) * N);
+  memcpy(h + o_T, T_f_w_io, sizeof(double) * 12 * B);
+  memcpy(h + o_hp, has_point_io + base, total);
+  memset(h + o_out, 0, sizeof(svo_b200_pose_opt_result) * B);
+  memcpy(h + o_f, f + 3 * (size_t)base, sizeof(double) * 3 * total);
+  memcpy(h + o_pos, point_pos + 3 * (size_t)base, sizeof(double) * 3 * total);
+  memcpy(h + o_lv, level + base, sizeof(int) * total);
+  int* off = reinterpret_cast<int*>(h + o_off);
+  for (int b = 0; b <= B; ++b) off[b] = obs_offset[b] - base;
+  memcpy(h + o_fx, fx, sizeof(double) * B);
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(d, h, c.off, cudaMemcpyHostToDevice, ctx->stream));
   PoseOptParams P;
   P.f = reinterpret_cast<const double*>(d + o_f);
   P.pos = reinterpret_cast<const double*>(d + o_pos);
   P.level = reinterpret_cast<const int*>(d + o_lv);
   P.has_point = d + o_hp;
-  P.N = N;
+  P.obs_offset = reinterpret_cast<const int*>(d + o_off);
+  P.fx = reinterpret_cast<const double*>(d + o_fx);
   P.n_iter = n_iter;
-  P.fx = fx;
   P.reproj_thresh = reproj_thresh;
   P.T_io = reinterpret_cast<double*>(d + o_T);
   P.out = reinterpret_cast<svo_b200_pose_opt_result*>(d + o_out);
   SVO_CUDA_CHECK(ctx, cudaFuncSetAttribute(pose_opt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  pose_opt_kernel<<<1, kPoThreads, smem, ctx->stream>>>(P);
+  pose_opt_kernel<<<B, kPoThreads, smem, ctx->stream>>>(P);
   ctx->launches++;
   SVO_CUDA_CHECK(ctx, cudaGetLastError());
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(h, d, io_end, cudaMemcpyDeviceToHost, ctx->stream));
   SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
-  memcpy(T_f_w_io, h + o_T, sizeof(double) * 12);
-  memcpy(has_point_io, h + o_hp, N);
-  memcpy(out, h + o_out, sizeof(*out));
+  memcpy(T_f_w_io, h + o_T, sizeof(double) * 12 * B);
+  memcpy(has_point_io + base, h + o_hp, total);
+  memcpy(out, h + o_out, sizeof(*out) * (size_t)B);
   return 0;
+}
+
+extern "C" int svo_b200_pose_optimize(svo_b200_ctx* ctx, double reproj_thresh, int n_iter, double fx,
+                                      double* T_f_w_io, const double* f, const double* point_pos, const int* level,
+                                      uint8_t* has_point_io, int N, svo_b200_pose_opt_result* out) {
+  if (!ctx || !T_f_w_io || !out || N < 0 || n_iter < 0 || (N > 0 && (!f || !point_pos || !level || !has_point_io)))
+    return set_err(ctx, SVO_B200_EINVAL, "pose_optimize: bad arguments");
+  const int off[2] = {0, N};
+  return svo_b200_pose_optimize_batch(ctx, 1, reproj_thresh, n_iter, &fx, T_f_w_io, off, f, point_pos, level, has_point_io, out);
 }
 
 // ================================================================================================

@@ -1047,9 +1047,9 @@ static int pick_launch(svo_b200_ctx* ctx, int B, int max_feat, int& threads, int
     return set_err(ctx, SVO_B200_ELIMIT, "sparse_img_align: %d features per pair > 1024 (shared-memory patch cache)", max_feat);
   cluster = 1;
   int want = ctx->sia_cluster >= 0 ? ctx->sia_cluster : g_sia_cluster;
-  // small batch (live streams, BASELINE configs[4]'s 32 pairs per GPU): spread each pair over 4 SMs while all clusters
-  // are resident at once (2 CTAs of 96 threads per SM)
-  if (want < 0) want = (B * 4 <= 2 * ctx->sm_count) ? 4 : 1;
+  // small batch (live streams, BASELINE configs[4]'s 32 pairs per GPU): spread each pair over 4 SMs while every CTA
+  // still has an SM of its own (measured: 4*B = 296 CTAs, two per SM, is already slower than one 320-thread CTA per pair)
+  if (want < 0) want = (B * 4 <= ctx->sm_count) ? 4 : 1;
   // full batches (more pairs than 2 per SM): 160 threads x 2 features, three CTAs per SM; in between, 320 x 1 with windows
   int fpt2 = ctx->sia_fpt > 0 ? (ctx->sia_fpt == 2 ? 1 : 0) : g_sia_fpt2;
   if (ctx->sia_fpt == 0 && B <= 2 * ctx->sm_count) fpt2 = 0;

@@ -23,6 +23,40 @@ def test_pose_optimize_matches_oracle(ctx, oracle, n, size):
         assert synth.pose_error(g["T"], c["T_true"])[0] < 5e-3  # the optimiser recovers the pose
 
 
+def test_pose_optimize_batch_equals_single_calls(ctx, oracle):
+    """svo_b200_pose_optimize_batch: frames of different sizes (one without observations) in one launch give exactly
+    what single calls give, and match the oracle."""
+    cases = [synth.make_pose_opt_case(40 + k, n, *size) for k, (n, size) in
+             enumerate([(1000, (1920, 1080)), (120, (752, 480)), (9, (640, 480)), (300, (640, 480))])]
+    cases[2]["has_point"][:] = 0
+    off = np.concatenate([[0], np.cumsum([len(c["level"]) for c in cases])]).astype(np.int32)
+    cat = lambda k: np.concatenate([c[k] for c in cases])
+    res = ctx.pose_optimize_batch(2.0, 10, [c["cam"].fx for c in cases], np.stack([c["T_init"] for c in cases]), off,
+                                  cat("f"), cat("pos"), cat("level"), cat("has_point"))
+    for c, r in zip(cases, res):
+        g = ctx.pose_optimize(2.0, 10, c["cam"].fx, c["T_init"], c["f"], c["pos"], c["level"], c["has_point"])
+        assert np.array_equal(r["T"], g["T"]) and np.array_equal(r["has_point"], g["has_point"])
+        assert (r["num_obs"], r["n_iter_done"], r["error_final"]) == (g["num_obs"], g["n_iter_done"], g["error_final"])
+        o = oracle.pose_optimize(2.0, 10, c["cam"].fx, c["T_init"], c["f"], c["pos"], c["level"], c["has_point"])
+        assert np.array_equal(r["has_point"], o["has_point"]) and r["num_obs"] == o["num_obs"]
+        dt, dr = synth.pose_error(r["T"], o["T"])
+        assert dt < 1e-8 and dr < 1e-8
+
+
+def test_pose_optimize_ties_and_tiny_sets(ctx, oracle):
+    """The median select with repeated values (identical observations) and with 1..3 observations."""
+    c = synth.make_pose_opt_case(77, 64, 752, 480)
+    for k in ("f", "pos", "level"):
+        c[k][32:] = c[k][:32]  # every observation twice: the order statistics see ties everywhere
+    for n in (64, 3, 2, 1):
+        hp = c["has_point"].copy(); hp[:] = 0; hp[:n] = 1
+        g = ctx.pose_optimize(2.0, 10, c["cam"].fx, c["T_init"], c["f"], c["pos"], c["level"], hp)
+        o = oracle.pose_optimize(2.0, 10, c["cam"].fx, c["T_init"], c["f"], c["pos"], c["level"], hp)
+        assert g["num_obs"] == o["num_obs"] and np.array_equal(g["has_point"], o["has_point"]), n
+        for key in ("estimated_scale", "error_init", "error_final"):
+            assert abs(g[key] - o[key]) <= 1e-9 * max(1.0, abs(o[key])), (n, key)
+
+
 def test_pose_optimize_no_observations(ctx):
     c = synth.make_pose_opt_case(3, 16, 640, 480)
     hp = np.zeros(16, np.uint8)
