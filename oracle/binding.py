@@ -38,7 +38,7 @@ def build(force: bool = False) -> str:
 
 class Camera(C.Structure):
     _fields_ = [("fx", C.c_double), ("fy", C.c_double), ("cx", C.c_double), ("cy", C.c_double),
-                ("width", C.c_int), ("height", C.c_int)]
+                ("width", C.c_int), ("height", C.c_int), ("model", C.c_int), ("reserved_", C.c_int), ("d", C.c_double * 5)]
 
 
 class SiaIter(C.Structure):
@@ -85,7 +85,8 @@ def _p(a):
 
 
 def cam_struct(cam) -> Camera:
-    return Camera(cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height)
+    d = (C.c_double * 5)(*([float(x) for x in getattr(cam, "d", ())] + [0.0] * 5)[:5])
+    return Camera(cam.fx, cam.fy, cam.cx, cam.cy, cam.width, cam.height, int(getattr(cam, "model", 0)), 0, d)
 
 
 def _level_ptrs(pyr):
@@ -183,6 +184,22 @@ def sparse_residuals(ref_img, cur_img, level, cam, T, px, f, pos, has_point, ref
                            _p(res), _p(inimg), _p(H), _p(Jres), C.byref(chi2), C.byref(nm))
     return dict(visible=vis, ref_patch=ref_patch, jac=jac, residuals=res, in_image=inimg,
                 H=H.reshape(6, 6), Jres=Jres, chi2=chi2.value, n_meas=nm.value)
+
+
+def camera_world2cam(cam, xyz):
+    xyz = c64(xyz).reshape(-1, 3)
+    out = np.zeros((len(xyz), 2))
+    cs = cam_struct(cam)
+    lib().orc_camera_world2cam(C.byref(cs), _p(xyz), len(xyz), _p(out))
+    return out
+
+
+def camera_cam2world(cam, px):
+    px = c64(px).reshape(-1, 2)
+    out = np.zeros((len(px), 3))
+    cs = cam_struct(cam)
+    lib().orc_camera_cam2world(C.byref(cs), _p(px), len(px), _p(out))
+    return out
 
 
 PYR_SCALAR, PYR_X86 = 0, 1
@@ -378,7 +395,9 @@ def ref_lib():
 
 
 def _cam4(cam):
-    return c64([cam.fx, cam.fy, cam.cx, cam.cy])
+    """[fx fy cx cy model d0..d4] for the ref_* wrappers (oracle/ref_wrap.cpp: make_camera)."""
+    d = ([float(x) for x in getattr(cam, "d", ())] + [0.0] * 5)[:5]
+    return c64([cam.fx, cam.fy, cam.cx, cam.cy, float(getattr(cam, "model", 0))] + d)
 
 
 def ref_sparse_img_align(ref_l0, cur_l0, n_levels, cam, T_ref_w, T_cur_w, px, f, pos, has_point, max_level, min_level,

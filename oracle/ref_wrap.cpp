@@ -24,6 +24,14 @@
 
 using namespace svo;
 
+// camera from the flat parameter block of oracle/binding.py (_cam4): [fx fy cx cy model d0..d4]; model 0 =
+// vk::PinholeCamera(w, h, fx, fy, cx, cy, d0..d4), model 1 = vk::ATANCamera with the pixel parameters converted back to
+// the normalised ones its constructor expects
+vk::AbstractCamera* ref_make_camera(int w, int h, const double* c) {
+  if ((int)c[4] == 1) return new vk::ATANCamera(w, h, c[0] / w, c[1] / h, (c[2] + 0.5) / w, (c[3] + 0.5) / h, c[5]);
+  return new vk::PinholeCamera(w, h, c[0], c[1], c[2], c[3], c[5], c[6], c[7], c[8], c[9]);
+}
+
 namespace {
 SE3 se3_from12(const double* T) {
   Matrix3d R;
@@ -105,7 +113,8 @@ long long ref_sparse_img_align(const uint8_t* ref_l0, const uint8_t* cur_l0, int
                                const double* T_ref_w, double* T_cur_w_io, const double* px, const double* f, const double* pos,
                                const uint8_t* has_point, int N, int max_level, int min_level, int n_iter,
                                uint8_t* visible_out, double* H_out, float* patch_cache_out) {
-  vk::PinholeCamera cam(w, h, cam4[0], cam4[1], cam4[2], cam4[3]);
+  std::unique_ptr<vk::AbstractCamera> cam_owner(ref_make_camera(w, h, cam4));
+  vk::AbstractCamera& cam = *cam_owner;
   FramePtr ref = make_frame(&cam, ref_l0, w, h, n_levels, T_ref_w);
   FramePtr cur = make_frame(&cam, cur_l0, w, h, n_levels, T_cur_w_io);
   std::vector<std::unique_ptr<Point>> pts;
@@ -126,7 +135,7 @@ long long ref_sparse_img_align(const uint8_t* ref_l0, const uint8_t* cur_l0, int
 // ---- a stream of frame pairs kept alive between calls, for timing svo::SparseImgAlign::run alone (bench.py's
 // --impl reference arm and cpu_baseline leg): pair k = (frame k, frame k+1); pyramids are built at create time.
 struct RefStream {
-  std::unique_ptr<vk::PinholeCamera> cam;
+  std::unique_ptr<vk::AbstractCamera> cam;
   std::vector<FramePtr> ref, cur;  // separate objects: run() writes cur->T_f_w_
   std::vector<std::unique_ptr<Point>> pts;
 };
@@ -134,7 +143,7 @@ void* ref_stream_create(const uint8_t* level0s /*(B+1) images*/, int B, int w, i
                         const double* T_f_w /*(B+1)x12*/, const int* feat_offset, const double* px, const double* f,
                         const double* pos, const uint8_t* has_point) {
   RefStream* s = new RefStream;
-  s->cam.reset(new vk::PinholeCamera(w, h, cam4[0], cam4[1], cam4[2], cam4[3]));
+  s->cam.reset(ref_make_camera(w, h, cam4));
   for (int k = 0; k < B; ++k) {
     FramePtr ref = make_frame(s->cam.get(), level0s + (size_t)k * w * h, w, h, n_levels, T_f_w + 12 * k);
     for (int i = feat_offset[k]; i < feat_offset[k + 1]; ++i) {
@@ -182,7 +191,8 @@ void ref_stream_destroy(void* handle) { delete (RefStream*)handle; }
 void ref_pose_optimize(double reproj_thresh, int n_iter, const double* cam4, int w, int h, double* T_f_w_io, const double* f,
                        const double* pos, const int* level, uint8_t* has_point_io, int N, double* scalars4 /*scale,init,final,num_obs*/,
                        double* cov36) {
-  vk::PinholeCamera cam(w, h, cam4[0], cam4[1], cam4[2], cam4[3]);
+  std::unique_ptr<vk::AbstractCamera> cam_owner(ref_make_camera(w, h, cam4));
+  vk::AbstractCamera& cam = *cam_owner;
   std::vector<uint8_t> img((size_t)w * h, 0);
   FramePtr fr = make_frame(&cam, img.data(), w, h, 1, T_f_w_io);
   std::vector<std::unique_ptr<Point>> pts;
@@ -223,7 +233,8 @@ void ref_matcher(int mode /*0 direct, 1 epipolar*/, const uint8_t* ref_l0, const
                  const double* cam4, const double* T_ref_w, const double* T_cur_w, const double* ref_px, const double* ref_f,
                  int ref_level, int ftr_type, const double* ref_grad, const double* point_pos, const double* px_cur_in,
                  double d_est, double d_min, double d_max, int n_pyr_levels, ref_match_out* out) {
-  vk::PinholeCamera cam(w, h, cam4[0], cam4[1], cam4[2], cam4[3]);
+  std::unique_ptr<vk::AbstractCamera> cam_owner(ref_make_camera(w, h, cam4));
+  vk::AbstractCamera& cam = *cam_owner;
   FramePtr ref = make_frame(&cam, ref_l0, w, h, n_levels, T_ref_w);
   FramePtr cur = make_frame(&cam, cur_l0, w, h, n_levels, T_cur_w);
   Config::nPyrLevels() = n_pyr_levels;  // max search level = nPyrLevels()-1 (matcher.cpp:153,214)
@@ -282,7 +293,8 @@ void ref_depth_filter_update(const uint8_t* ref_l0s /*n_ref images*/, const doub
                              const double* ftr_px, const double* ftr_f, const int* ftr_level, const int* ftr_type,
                              const double* ftr_grad, const int* batch_id, int batch_counter, int n_pyr_levels, float* a, float* b,
                              float* mu, float* z_range, float* sigma2, uint8_t* status_out, double* xyz_world_out) {
-  vk::PinholeCamera cam(w, h, cam4[0], cam4[1], cam4[2], cam4[3]);
+  std::unique_ptr<vk::AbstractCamera> cam_owner(ref_make_camera(w, h, cam4));
+  vk::AbstractCamera& cam = *cam_owner;
   std::vector<FramePtr> refs;
   for (int r = 0; r < n_ref; ++r) refs.push_back(make_frame(&cam, ref_l0s + (size_t)r * w * h, w, h, n_levels, ref_T_f_w + 12 * r));
   FramePtr cur = make_frame(&cam, cur_l0, w, h, n_levels, cur_T_f_w);

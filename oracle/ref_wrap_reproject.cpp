@@ -19,6 +19,8 @@
 
 #include "svo_oracle.h"
 
+vk::AbstractCamera* ref_make_camera(int w, int h, const double* c);  // oracle/ref_wrap.cpp
+
 using namespace svo;
 
 namespace {
@@ -42,7 +44,8 @@ extern "C" void ref_reproject_map(const orc_map_view* m, const uint8_t* kf_l0s /
                                   const int* cell_order, int* pt_type_io, int* pt_n_failed_io, int* pt_n_succeeded_io,
                                   uint8_t* pt_action_out, int* overlap_kf_out, int64_t* overlap_count_out, int* new_point,
                                   double* new_px, int* new_level, int* new_type, double* new_grad, orc_reproject_stats* st) {
-  vk::PinholeCamera cam(w, h, cam4[0], cam4[1], cam4[2], cam4[3]);
+  std::unique_ptr<vk::AbstractCamera> cam_owner(ref_make_camera(w, h, cam4));
+  vk::AbstractCamera& cam = *cam_owner;
   std::vector<FramePtr> kfs;
   for (int k = 0; k < m->n_kfs; ++k) kfs.push_back(make_frame(&cam, kf_l0s + (size_t)k * w * h, w, h, n_levels, m->kf_T_f_w + 12 * k));
   FramePtr cur = make_frame(&cam, cur_l0, w, h, n_levels, cur_T_f_w);

@@ -29,18 +29,72 @@ using namespace orc;
 namespace {
 
 // ------------------------------------------------------------------------------------------
-// [EXT] vk::PinholeCamera without distortion (rpg_vikit, not vendored, no version pinned).
+// [EXT] vk::AbstractCamera models (rpg_vikit, not vendored, no version pinned), restated from the published
+// pinhole_camera.cpp / atan_camera.cpp:
+//   model 0  vk::PinholeCamera(width, height, fx, fy, cx, cy, d0..d4): radial-tangential distortion when
+//            fabs(d0) > 1e-7; cam2world then goes through cv::undistortPoints on ONE CV_32FC2 point [EXT OpenCV]
+//            (float in, 5 fixed-point iterations in double, float out);
+//   model 1  vk::ATANCamera (PTAM's FOV model), d0 = s; fx, fy, cx, cy are the pixel values its constructor derives.
+// Explicit fma() spells the contraction GCC applies to the reference build (px = fx*u + cx).
 // ------------------------------------------------------------------------------------------
 struct Cam {
   double fx, fy, cx, cy;
   int width, height;
-  // world2cam(uv on unit plane): px = fx*u + cx
-  V2 world2cam_uv(V2 uv) const { return {std::fma(fx, uv.x, cx), std::fma(fy, uv.y, cy)}; }
+  int model;
+  double d[5];
+  bool distorted;
+  double s_inv, tans, tans_inv;
+  // world2cam(uv on unit plane)
+  V2 world2cam_uv(V2 uv) const {
+    const double x = uv.x, y = uv.y;
+    if (!distorted) return {std::fma(fx, x, cx), std::fma(fy, y, cy)};
+    if (model == 0) {
+      const double r2 = std::fma(x, x, y * y), r4 = r2 * r2, r6 = r4 * r2;
+      const double a1 = 2.0 * x * y, a2 = std::fma(2.0 * x, x, r2), a3 = std::fma(2.0 * y, y, r2);
+      const double cdist = std::fma(d[4], r6, std::fma(d[1], r4, std::fma(d[0], r2, 1.0)));
+      const double xd = std::fma(d[3], a2, std::fma(d[2], a1, x * cdist));
+      const double yd = std::fma(d[3], a1, std::fma(d[2], a3, y * cdist));
+      return {std::fma(xd, fx, cx), std::fma(yd, fy, cy)};
+    }
+    const double r = std::sqrt(std::fma(x, x, y * y));
+    const double factor = r < 0.001 ? 1.0 : s_inv * std::atan(r * tans) / r;  // rtrans_factor
+    return {std::fma(fx * factor, x, cx), std::fma(fy * factor, y, cy)};
+  }
   // world2cam(xyz) = world2cam(project2d(xyz)), project2d = xyz.head2 / z
   V2 world2cam(V3 p) const { return world2cam_uv(V2{p.x / p.z, p.y / p.z}); }
   // cam2world(u,v): normalised bearing vector
   V3 cam2world(double u, double v) const {
-    return normalized(V3{(u - cx) / fx, (v - cy) / fy, 1.0});
+    double x, y;
+    if (model == 0) {
+      if (!distorted) {
+        x = (u - cx) / fx;
+        y = (v - cy) / fy;
+      } else {
+        const double uf = double(float(u)), vf = double(float(v));
+        const double ifx = 1.0 / fx, ify = 1.0 / fy;
+        const double x0 = (uf - cx) * ifx, y0 = (vf - cy) * ify;
+        x = x0; y = y0;
+        for (int j = 0; j < 5; ++j) {
+          const double r2 = x * x + y * y;
+          const double icdist = 1.0 / (1.0 + ((d[4] * r2 + d[1]) * r2 + d[0]) * r2);
+          const double dX = 2.0 * d[2] * x * y + d[3] * (r2 + 2.0 * x * x);
+          const double dY = d[2] * (r2 + 2.0 * y * y) + 2.0 * d[3] * x * y;
+          x = (x0 - dX) * icdist;
+          y = (y0 - dY) * icdist;
+        }
+        x = double(float(x));
+        y = double(float(y));
+      }
+    } else {
+      const double ifx = 1.0 / fx, ify = 1.0 / fy;
+      const double dx = (u - cx) * ifx, dy = (v - cy) * ify;
+      const double dist_r = std::sqrt(dx * dx + dy * dy);
+      const double r = distorted ? std::tan(dist_r * d[0]) * tans_inv : dist_r;  // invrtrans
+      const double d_factor = dist_r > 0.01 ? r / dist_r : 1.0;
+      x = d_factor * dx;
+      y = d_factor * dy;
+    }
+    return normalized(V3{x, y, 1.0});
   }
   double errorMultiplier2() const { return std::fabs(fx); }
   bool isInFrame(int x, int y, int boundary) const {
@@ -52,7 +106,19 @@ struct Cam {
   }
 };
 inline Cam make_cam(const orc_camera* c) {
-  return Cam{c->fx, c->fy, c->cx, c->cy, c->width, c->height};
+  Cam k{};
+  k.fx = c->fx; k.fy = c->fy; k.cx = c->cx; k.cy = c->cy; k.width = c->width; k.height = c->height;
+  k.model = c->model;
+  for (int i = 0; i < 5; ++i) k.d[i] = c->d[i];
+  if (c->model == 0) {
+    k.distorted = std::fabs(c->d[0]) > 0.0000001;
+  } else if (c->d[0] != 0.0) {
+    k.tans = 2.0 * std::tan(c->d[0] / 2.0);
+    k.tans_inv = 1.0 / k.tans;
+    k.s_inv = 1.0 / c->d[0];
+    k.distorted = true;
+  }
+  return k;
 }
 
 struct Img {
@@ -511,6 +577,22 @@ void orc_half_sample_rule(const uint8_t* in, int in_cols, int in_rows, uint8_t* 
 }
 void orc_half_sample(const uint8_t* in, int in_cols, int in_rows, uint8_t* out) {
   orc_half_sample_rule(in, in_cols, in_rows, out, 0);
+}
+
+// [EXT] camera models, exposed for the tests: n points, xyz (n*3) -> px (n*2) and px (n*2) -> unit bearing (n*3)
+void orc_camera_world2cam(const orc_camera* cam, const double* xyz, int n, double* px_out) {
+  const Cam c = make_cam(cam);
+  for (int i = 0; i < n; ++i) {
+    const V2 p = c.world2cam(V3{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]});
+    px_out[2 * i] = p.x; px_out[2 * i + 1] = p.y;
+  }
+}
+void orc_camera_cam2world(const orc_camera* cam, const double* px, int n, double* f_out) {
+  const Cam c = make_cam(cam);
+  for (int i = 0; i < n; ++i) {
+    const V3 f = c.cam2world(px[2 * i], px[2 * i + 1]);
+    f_out[3 * i] = f.x; f_out[3 * i + 1] = f.y; f_out[3 * i + 2] = f.z;
+  }
 }
 
 void orc_se3_exp(const double* x6, double* T12_out) { se3_to_rt12(se3_exp(x6), T12_out); }

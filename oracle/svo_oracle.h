@@ -27,8 +27,11 @@ extern "C" {
 #define ORC_MAX_LEVELS 8
 
 typedef struct {
-  double fx, fy, cx, cy; /* [EXT] vk::PinholeCamera without distortion */
+  double fx, fy, cx, cy; /* [EXT] vk::PinholeCamera / vk::ATANCamera pixel parameters */
   int width, height;
+  int model;             /* 0 = pinhole (d = k1 k2 p1 p2 k3, all 0 = undistorted), 1 = ATAN (d[0] = s) */
+  int reserved_;
+  double d[5];
 } orc_camera;
 
 /* One Gauss-Newton iteration of vk::NLLSSolver::optimizeGaussNewton as driven by
@@ -77,6 +80,9 @@ int orc_sparse_residuals(
 
 /* [EXT] vk::halfSample scalar path: out = (a+b+c+d)/4 (integer division). */
 void orc_half_sample(const uint8_t* in, int in_cols, int in_rows, uint8_t* out);
+/* [EXT] vk::AbstractCamera::world2cam(xyz) / cam2world(px) of the restated models, n points each. */
+void orc_camera_world2cam(const orc_camera* cam, const double* xyz, int n, double* px_out);
+void orc_camera_cam2world(const orc_camera* cam, const double* px, int n, double* f_out);
 /* rule 0 = scalar, 1 = x86 (vikit's SSE2 avg(avg) branch when in_cols % 16 == 0, scalar otherwise). */
 void orc_half_sample_rule(const uint8_t* in, int in_cols, int in_rows, uint8_t* out, int rule);
 

@@ -210,7 +210,8 @@ int svo_b200_find_match_direct(svo_b200_ctx* ctx, const svo_b200_frame* const* r
                 reinterpret_cast<const FrameDesc*>(d + o_fr)};
   MatchOut out = {reinterpret_cast<double*>(d + o_pc), d + o_su, reinterpret_cast<int*>(d + o_sl),
                   reinterpret_cast<double*>(d + o_A), reinterpret_cast<double*>(d + o_h)};
-  Cam cm = {cam->fx, cam->fy, cam->cx, cam->cy, cam->width, cam->height};
+  Cam cm;
+  { const int rc_cam = cam_to_dev(ctx, cam, cm); if (rc_cam) return rc_cam; }
   const int blocks = (M + kWarpsPerCta - 1) / kWarpsPerCta;
   find_match_direct_kernel<<<blocks, kWarpsPerCta * 32, 0, ctx->stream>>>(
       make_desc(cur), cm, M, in, out, opt->max_search_level, opt->align_max_iter, reinterpret_cast<const double*>(d + o_cT));

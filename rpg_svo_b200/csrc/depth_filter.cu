@@ -186,8 +186,9 @@ __global__ void __launch_bounds__(kDfWarps * 32) depth_filter_kernel(const Depth
     }
     if (!reject) {
       const int L = best_search_level(Aff, P.max_search_level);
-      const double pAu = fma(cam.fx, Ax, cam.cx), pAv = fma(cam.fy, Ay, cam.cy);
-      const double pBu = fma(cam.fx, Bx, cam.cx), pBv = fma(cam.fy, By, cam.cy);
+      double pAu, pAv, pBu, pBv;
+      cam_world2cam(cam, Ax, Ay, pAu, pAv);  // cam_->world2cam(A), world2cam(B)  (:217-218)
+      cam_world2cam(cam, Bx, By, pBu, pBv);
       const double ddx = pAu - pBu, ddy = pAv - pBv;
       const double epi_length = sqrt(ddx * ddx + ddy * ddy) / (double)(1 << L);
       const FrameDesc& rf = P.ref_frames[r];
@@ -219,12 +220,15 @@ __global__ void __launch_bounds__(kDfWarps * 32) depth_filter_kernel(const Depth
           for (int k = lane; k < n_steps; k += 32) {
             // uv_k = (B - step) + k*step  (the reference accumulates uv += step; same value to ~1 ulp)
             const double uk = fma((double)k, step_x, u0), vk = fma((double)k, step_y, v0);
-            const int qx = (int)(fma(cam.fx, uk, cam.cx) / sc + 0.5), qy = (int)(fma(cam.fy, vk, cam.cy) / sc + 0.5);
+            double wu, wv;
+            cam_world2cam(cam, uk, vk, wu, wv);  // cam_->world2cam(uv)  (:272)
+            const int qx = (int)(wu / sc + 0.5), qy = (int)(wv / sc + 0.5);
             int px_prev = 0, py_prev = 0;  // last_checked_pxi starts at (0,0)
             if (k > 0) {
               const double up = fma((double)(k - 1), step_x, u0), vp = fma((double)(k - 1), step_y, v0);
-              px_prev = (int)(fma(cam.fx, up, cam.cx) / sc + 0.5);
-              py_prev = (int)(fma(cam.fy, vp, cam.cy) / sc + 0.5);
+              cam_world2cam(cam, up, vp, wu, wv);
+              px_prev = (int)(wu / sc + 0.5);
+              py_prev = (int)(wv / sc + 0.5);
             }
             if (qx == px_prev && qy == py_prev) continue;                 // :273-275
             if (!(qx >= 8 && qx < lim_x && qy >= 8 && qy < lim_y)) continue;  // isInFrame(pxi, 8, level)
@@ -242,8 +246,7 @@ __global__ void __launch_bounds__(kDfWarps * 32) depth_filter_kernel(const Depth
           if (best_key < (long long)(2000 * 64) * 4294967296LL) {
             const int kb = (int)(best_key & 0xffffffffLL);
             const double ub = fma((double)kb, step_x, u0), vb = fma((double)kb, step_y, v0);
-            start_u = fma(cam.fx, ub, cam.cx);
-            start_v = fma(cam.fy, vb, cam.cy);
+            cam_world2cam(cam, ub, vb, start_u, start_v);  // px_cur_ = world2cam(uv_best)  (:299)
             have_start = true;
           }
         }
@@ -355,7 +358,7 @@ extern "C" int svo_b200_depth_filter_update(svo_b200_ctx* ctx, const svo_b200_fr
   P.ref_T_f_w = reinterpret_cast<const double*>(d + o_rT);
   P.cur = make_desc(cur);
   memcpy(P.cur_T_f_w, cur_T_f_w, sizeof(double) * 12);
-  P.cam = Cam{cam->fx, cam->fy, cam->cx, cam->cy, cam->width, cam->height};
+  if ((rc = cam_to_dev(ctx, cam, P.cam))) return rc;
   P.M = M;
   P.ref_index = reinterpret_cast<const int*>(d + o_ri);
   P.ftr_px = reinterpret_cast<const double*>(d + o_px);

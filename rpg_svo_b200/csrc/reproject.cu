@@ -167,6 +167,8 @@ extern "C" int svo_b200_reproject_map(svo_b200_ctx* ctx, const svo_b200_map_view
   for (int p = 0; p < m->n_points; ++p) pt_action_out[p] = SVO_B200_PT_NONE;
   // initializeGrid (:47-58)
   const int cell_size = opt->grid_size;
+  Cam cm;
+  { const int rc_cam = cam_to_dev(ctx, cam, cm); if (rc_cam) return rc_cam; }
   const int grid_n_cols = (int)std::ceil((double)cam->width / cell_size);
   const int grid_n_rows = (int)std::ceil((double)cam->height / cell_size);
   const size_t n_cells = (size_t)grid_n_cols * grid_n_rows;
@@ -184,7 +186,8 @@ extern "C" int svo_b200_reproject_map(svo_b200_ctx* ctx, const svo_b200_map_view
       const double y = Tc[4] * kp[0] + Tc[5] * kp[1] + Tc[6] * kp[2] + Tc[7];
       const double z = Tc[8] * kp[0] + Tc[9] * kp[1] + Tc[10] * kp[2] + Tc[11];
       if (z < 0.0) continue;
-      const double u = cam->fx * (x / z) + cam->cx, v = cam->fy * (y / z) + cam->cy;
+      double u, v;
+      cam_world2cam(cm, x / z, y / z, u, v);  // Frame::w2c
       if (u >= 0.0 && v >= 0.0 && u < cam->width && v < cam->height) {
         const double* Tk = m->kf_T_f_w + 12 * (size_t)k;
         const double dx = Tc[3] - Tk[3], dy = Tc[7] - Tk[7], dz = Tc[11] - Tk[11];
@@ -262,7 +265,6 @@ extern "C" int svo_b200_reproject_map(svo_b200_ctx* ctx, const svo_b200_map_view
   ReprojOut out = {reinterpret_cast<double*>(d + o_px), d + o_in, reinterpret_cast<int*>(d + o_cell), d + o_su,
                    reinterpret_cast<double*>(d + o_pm), reinterpret_cast<int*>(d + o_sl), reinterpret_cast<double*>(d + o_A),
                    reinterpret_cast<int*>(d + o_rf)};
-  Cam cm = {cam->fx, cam->fy, cam->cx, cam->cy, cam->width, cam->height};
   const int blocks = (E + kRpWarps - 1) / kRpWarps;
   reproject_match_kernel<<<blocks, kRpWarps * 32, sizeof(double) * 3 * m->n_kfs, ctx->stream>>>(
       make_desc(cur), cm, E, m->n_kfs, in, out, reinterpret_cast<const double*>(d + o_cT), cell_size, grid_n_cols,

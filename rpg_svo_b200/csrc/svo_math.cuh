@@ -457,7 +457,7 @@ __device__ __forceinline__ double div_rn(double x, double z, double rz) {
 //   world2cam(uv): unit-plane point -> pixel.      cam2world(px): pixel -> UNIT bearing vector.
 // ------------------------------------------------------------------------------------------
 template <class Cam>
-__device__ __forceinline__ void cam_world2cam(const Cam& c, double x, double y, double& u, double& v) {
+__host__ __device__ __forceinline__ void cam_world2cam(const Cam& c, double x, double y, double& u, double& v) {
   if (!c.distorted) {  // px = fx*uv + cx  (both models without distortion)
     u = fma(c.fx, x, c.cx);
     v = fma(c.fy, y, c.cy);
@@ -477,7 +477,7 @@ __device__ __forceinline__ void cam_world2cam(const Cam& c, double x, double y, 
   }
 }
 template <class Cam>
-__device__ __forceinline__ void cam_cam2world(const Cam& c, double u, double v, double (&f)[3]) {
+__host__ __device__ __forceinline__ void cam_cam2world(const Cam& c, double u, double v, double (&f)[3]) {
   double x, y;
   if (c.model == SVO_B200_CAM_PINHOLE) {
     if (!c.distorted) {

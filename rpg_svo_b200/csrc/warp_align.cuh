@@ -39,10 +39,7 @@ struct ImgView {
   int cols, rows;  // row pitch == cols
 };
 
-struct Cam {
-  double fx, fy, cx, cy;
-  int width, height;
-};
+using Cam = CamDev;  // [EXT] vk::AbstractCamera: pinhole (+ radial-tangential distortion) or ATAN, see ctx.h / svo_math.cuh
 
 struct __align__(16) WarpAlignScratch {  // one per warp, shared memory
   float dx[64];
@@ -228,13 +225,12 @@ __device__ inline bool warp_align1d(const ImgView& img, WarpAlignScratch& S, flo
 
 // ------------------------------------------------------------------------------------------ geometry
 __device__ __forceinline__ void cam2world(const Cam& c, double u, double v, double* out) {  // [EXT] normalised bearing
-  const double x = (u - c.cx) / c.fx, y = (v - c.cy) / c.fy;
-  const double n = sqrt(x * x + y * y + 1.0);
-  out[0] = x / n; out[1] = y / n; out[2] = 1.0 / n;
+  double f[3];
+  cam_cam2world(c, u, v, f);
+  out[0] = f[0]; out[1] = f[1]; out[2] = f[2];
 }
-__device__ __forceinline__ void world2cam(const Cam& c, const double* p, double& u, double& v) {  // [EXT]
-  u = fma(c.fx, p[0] / p[2], c.cx);
-  v = fma(c.fy, p[1] / p[2], c.cy);
+__device__ __forceinline__ void world2cam(const Cam& c, const double* p, double& u, double& v) {  // [EXT] world2cam(project2d(xyz))
+  cam_world2cam(c, p[0] / p[2], p[1] / p[2], u, v);
 }
 __device__ __forceinline__ void pose_apply(const Pose& T, const double* p, double* out) {
   qrotate(T.q, p, out);

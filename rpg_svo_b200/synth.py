@@ -18,7 +18,9 @@ import numpy as np
 
 @dataclass(frozen=True)
 class Camera:
-    """[EXT] vk::PinholeCamera without distortion."""
+    """[EXT] vk::AbstractCamera: model 0 = vk::PinholeCamera (d = k1 k2 p1 p2 k3, radial-tangential; all zero = no
+    distortion), model 1 = vk::ATANCamera (d[0] = s; fx.. are the pixel values the vikit constructor derives).
+    numpy restatement used to manufacture test data (features, renders)."""
 
     fx: float
     fy: float
@@ -26,18 +28,90 @@ class Camera:
     cy: float
     width: int
     height: int
+    model: int = 0
+    d: tuple = (0.0, 0.0, 0.0, 0.0, 0.0)
+
+    @property
+    def distorted(self) -> bool:
+        return abs(self.d[0]) > 1e-7 if self.model == 0 else self.d[0] != 0.0
 
     def cam2world(self, px: np.ndarray) -> np.ndarray:
         """Pixel -> unit bearing vector (normalised), rows of px are (u, v)."""
         px = np.asarray(px, dtype=np.float64)
-        xyz = np.stack([(px[..., 0] - self.cx) / self.fx, (px[..., 1] - self.cy) / self.fy,
-                        np.ones(px.shape[:-1])], axis=-1)
+        u, v = px[..., 0], px[..., 1]
+        if self.model == 0 and not self.distorted:
+            x, y = (u - self.cx) / self.fx, (v - self.cy) / self.fy
+        elif self.model == 0:  # cv::undistortPoints on a CV_32FC2 point: float in, 5 iterations, float out
+            k = self.d
+            uf, vf = u.astype(np.float32).astype(np.float64), v.astype(np.float32).astype(np.float64)
+            x0, y0 = (uf - self.cx) * (1.0 / self.fx), (vf - self.cy) * (1.0 / self.fy)
+            x, y = x0.copy(), y0.copy()
+            for _ in range(5):
+                r2 = x * x + y * y
+                icdist = 1.0 / (1.0 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2)
+                dX = 2.0 * k[2] * x * y + k[3] * (r2 + 2.0 * x * x)
+                dY = k[2] * (r2 + 2.0 * y * y) + 2.0 * k[3] * x * y
+                x, y = (x0 - dX) * icdist, (y0 - dY) * icdist
+            x, y = x.astype(np.float32).astype(np.float64), y.astype(np.float32).astype(np.float64)
+        else:
+            dx, dy = (u - self.cx) * (1.0 / self.fx), (v - self.cy) * (1.0 / self.fy)
+            dist_r = np.sqrt(dx * dx + dy * dy)
+            s = self.d[0]
+            r = np.tan(dist_r * s) / (2.0 * np.tan(s / 2.0)) if s != 0.0 else dist_r
+            fac = np.where(dist_r > 0.01, r / np.where(dist_r > 0, dist_r, 1.0), 1.0)
+            x, y = fac * dx, fac * dy
+        xyz = np.stack([x, y, np.ones(px.shape[:-1])], axis=-1)
+        return xyz / np.linalg.norm(xyz, axis=-1, keepdims=True)
+
+    def cam2world_exact(self, px: np.ndarray) -> np.ndarray:
+        """True inverse of world2cam (for rendering): the radial-tangential model's fixed-point iteration run to
+        convergence in double (vikit's cam2world stops after OpenCV's 5 iterations and rounds to float)."""
+        if not (self.model == 0 and self.distorted):
+            return self.cam2world(px)
+        px = np.asarray(px, dtype=np.float64)
+        k = self.d
+        x0, y0 = (px[..., 0] - self.cx) / self.fx, (px[..., 1] - self.cy) / self.fy
+        x, y = x0.copy(), y0.copy()
+        for _ in range(60):
+            r2 = x * x + y * y
+            icdist = 1.0 / (1.0 + ((k[4] * r2 + k[1]) * r2 + k[0]) * r2)
+            dX = 2.0 * k[2] * x * y + k[3] * (r2 + 2.0 * x * x)
+            dY = k[2] * (r2 + 2.0 * y * y) + 2.0 * k[3] * x * y
+            x, y = (x0 - dX) * icdist, (y0 - dY) * icdist
+        xyz = np.stack([x, y, np.ones(px.shape[:-1])], axis=-1)
         return xyz / np.linalg.norm(xyz, axis=-1, keepdims=True)
 
     def world2cam(self, xyz: np.ndarray) -> np.ndarray:
         xyz = np.asarray(xyz, dtype=np.float64)
-        return np.stack([self.fx * xyz[..., 0] / xyz[..., 2] + self.cx,
-                         self.fy * xyz[..., 1] / xyz[..., 2] + self.cy], axis=-1)
+        x, y = xyz[..., 0] / xyz[..., 2], xyz[..., 1] / xyz[..., 2]
+        if not self.distorted:
+            return np.stack([self.fx * x + self.cx, self.fy * y + self.cy], axis=-1)
+        if self.model == 0:
+            k = self.d
+            r2 = x * x + y * y
+            cdist = 1 + k[0] * r2 + k[1] * r2 * r2 + k[4] * r2 ** 3
+            xd = x * cdist + k[2] * 2 * x * y + k[3] * (r2 + 2 * x * x)
+            yd = y * cdist + k[2] * (r2 + 2 * y * y) + k[3] * 2 * x * y
+            return np.stack([xd * self.fx + self.cx, yd * self.fy + self.cy], axis=-1)
+        s = self.d[0]
+        r = np.sqrt(x * x + y * y)
+        fac = np.where(r < 0.001, 1.0, np.arctan(r * 2.0 * np.tan(s / 2.0)) / (s * np.where(r > 0, r, 1.0)))
+        return np.stack([self.cx + self.fx * fac * x, self.cy + self.fy * fac * y], axis=-1)
+
+
+def atan_camera(width: int, height: int, fx: float, fy: float, cx: float, cy: float, s: float) -> Camera:
+    """vk::ATANCamera(width, height, fx, fy, cx, cy, s): the constructor's pixel parameters (fx_ = width*fx,
+    cx_ = cx*width - 0.5, ...)."""
+    return Camera(width * fx, height * fy, cx * width - 0.5, cy * height - 0.5, width, height, 1, (s, 0.0, 0.0, 0.0, 0.0))
+
+
+def reference_param_camera(kind: str) -> Camera:
+    """The two cameras the reference ships parameter files for (svo_ros/param/camera_atan.yaml, camera_pinhole.yaml)."""
+    if kind == "atan":
+        return atan_camera(752, 480, 0.509326, 0.796651, 0.45905, 0.510056, 0.9320)
+    if kind == "pinhole_radtan":
+        return Camera(414.536145, 414.284429, 348.804988, 240.076451, 752, 480, 0, (-0.283076, 0.066674, 0.000896, 0.000778, 0.0))
+    raise ValueError(kind)
 
 
 def camera_for(width: int, height: int) -> Camera:
@@ -161,8 +235,10 @@ def intersect(plane: Plane, T_f_w: np.ndarray, bearing: np.ndarray) -> np.ndarra
 def render(cam: Camera, T_f_w: np.ndarray, plane: Plane, tex: np.ndarray) -> np.ndarray:
     """Exact plane render (bilinear texture lookup, rounded to u8)."""
     u, v = np.meshgrid(np.arange(cam.width, dtype=np.float64), np.arange(cam.height, dtype=np.float64))
-    rays = np.stack([(u.ravel() - cam.cx) / cam.fx, (v.ravel() - cam.cy) / cam.fy,
-                     np.ones(u.size)], axis=1)
+    if cam.distorted:  # exact inverse projection of every pixel centre through the camera model
+        rays = cam.cam2world_exact(np.stack([u.ravel(), v.ravel()], axis=1))
+    else:
+        rays = np.stack([(u.ravel() - cam.cx) / cam.fx, (v.ravel() - cam.cy) / cam.fy, np.ones(u.size)], axis=1)
     X = intersect(plane, T_f_w, rays)
     s = (X @ plane.e1) * TEXELS_PER_M + TEX_SIZE / 2
     t = (X @ plane.e2) * TEXELS_PER_M + TEX_SIZE / 2
@@ -241,10 +317,10 @@ def features_for(rng, cam: Camera, T_f_w: np.ndarray, plane: Plane, n: int, max_
 
 def make_frame_pair(seed: int, width: int = 640, height: int = 480, n_feat: int = 300,
                     n_levels: int = 5, trans: float = 0.03, rot_deg: float = 0.5,
-                    tex_seed: int = 7) -> dict:
+                    tex_seed: int = 7, cam: Camera | None = None) -> dict:
     """One (ref, cur) pair of SURVEY.md 8d: GT motion uniform in +-trans m, +-rot_deg degrees."""
     rng = np.random.default_rng(seed)
-    cam = camera_for(width, height)
+    cam = camera_for(width, height) if cam is None else cam
     plane = Plane.tilted()
     tex = make_texture(tex_seed)
     T_ref_w = se3_mul(se3_exp(np.concatenate([rng.uniform(-0.2, 0.2, 3), rng.uniform(-0.03, 0.03, 3)])),
@@ -384,10 +460,10 @@ def make_align_case(seed: int, m: int, width: int = 640, height: int = 480, n_le
 
 
 def make_two_view(seed: int, width: int = 752, height: int = 480, n_levels: int = 5, baseline: float = 0.3,
-                  rot_deg: float = 2.0) -> dict:
+                  rot_deg: float = 2.0, cam: Camera | None = None) -> dict:
     """Reference keyframe + current frame with a real baseline (geometry of svo/test/test_matcher.cpp:52-57)."""
     rng = np.random.default_rng(seed)
-    cam = camera_for(width, height)
+    cam = camera_for(width, height) if cam is None else cam
     plane, tex = Plane.tilted(), make_texture(7)
     T_ref_w = base_pose()
     d = rng.normal(size=3); d[2] *= 0.2; d *= baseline / np.linalg.norm(d)
@@ -468,14 +544,14 @@ def make_pose_opt_case(seed: int, n: int = 1000, width: int = 1920, height: int 
 
 
 def make_map_case(seed: int, n_kfs: int = 8, n_points: int = 700, width: int = 752, height: int = 480, n_levels: int = 5,
-                  n_candidates: int = 80, spread: float = 0.5, bad_frac: float = 0.2) -> dict:
+                  n_candidates: int = 80, spread: float = 0.5, bad_frac: float = 0.2, cam: Camera | None = None) -> dict:
     """A small map for Reprojector::reprojectMap (svo/src/reprojector.cpp:64-217): n_kfs keyframes on a trajectory above
     the textured plane, world points on the plane observed by 1..n_kfs keyframes (one Feature per observation, detected
     on the integer grid of its level), point types / reprojection counters near the reference's thresholds, converged-
     seed candidates whose single observation is not in its keyframe's fts_ list, five key points per keyframe, a current
     frame close to the last keyframes, and a shuffled cell order.  Everything is flat arrays (the `map view`)."""
     rng = np.random.default_rng(seed)
-    cam = camera_for(width, height)
+    cam = camera_for(width, height) if cam is None else cam
     plane, tex = Plane.tilted(), make_texture(7)
     kf_T = []
     for k in range(n_kfs):
