@@ -11,6 +11,7 @@
  *   svo_b200_fast_detect            <- feature_detection::FastDetector::detect svo/include/svo/feature_detection.h:107-122, svo/src/feature_detection.cpp:66-115
  *   svo_b200_pose_optimize(_batch)  <- pose_optimizer::optimizeGaussNewton    svo/include/svo/pose_optimizer.h:37-45
  *   svo_b200_point_optimize_batch   <- Point::optimize                        svo/include/svo/point.h:86, svo/src/point.cpp:119-177
+ *   svo_b200_find_epipolar_match_direct <- Matcher::findEpipolarMatchDirect   svo/include/svo/matcher.h:114-121
  *   svo_b200_depth_filter_update    <- DepthFilter::updateSeeds               svo/include/svo/depth_filter.h:155
  *                                      (Matcher::findEpipolarMatchDirect, updateSeed, computeTau inside)
  *   svo_b200_frame_*                <- svo::Frame image pyramid               svo/include/svo/frame.h:52, svo/src/frame.cpp:156-165
@@ -344,6 +345,22 @@ int svo_b200_depth_filter_update(svo_b200_ctx* ctx, const svo_b200_frame* const*
                                  int batch_counter, float* a, float* b, float* mu, float* z_range,
                                  float* sigma2, uint8_t* status_out, double* px_cur_out,
                                  double* z_out, int* n_zmssd_out);
+
+/* M independent Matcher::findEpipolarMatchDirect calls (svo/include/svo/matcher.h:114-121, svo/src/matcher.cpp:179-321):
+ * candidate m is reference feature (ref_index, px, f, level, type, grad) searched in `cur` along the epipolar segment of
+ * depths [d_min, d_max] around d_estimate.  Outputs = the return value, `depth`, and the Matcher's public scratch
+ * members callers read afterwards (px_cur_, search_level_, epi_length_, reject_, A_cur_ref_); each may be NULL except
+ * success_out.  n_zmssd_out: ZMSSD evaluations along the line (instrumentation). */
+int svo_b200_find_epipolar_match_direct(svo_b200_ctx* ctx, const svo_b200_frame* const* ref_frames,
+                                        const double* ref_T_f_w, int n_ref, const svo_b200_frame* cur,
+                                        const double* cur_T_f_w, const svo_b200_camera* cam,
+                                        const svo_b200_depth_options* opt, int M, const int* ref_index,
+                                        const double* ftr_px, const double* ftr_f, const int* ftr_level,
+                                        const int* ftr_type, const double* ftr_grad, const double* d_estimate,
+                                        const double* d_min, const double* d_max, uint8_t* success_out,
+                                        double* depth_out, double* px_cur_out /*M*2*/, int* search_level_out,
+                                        double* epi_length_out, uint8_t* reject_out, double* A_cur_ref_out /*M*4*/,
+                                        int* n_zmssd_out);
 
 #ifdef __cplusplus
 }

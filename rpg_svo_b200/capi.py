@@ -426,6 +426,28 @@ def _depth_filter_update(self, ref_frames, ref_T_f_w, cur: Frame, cur_T_f_w, cam
     return out
 
 
+def _find_epipolar_match_direct(self, ref_frames, ref_T_f_w, cur: Frame, cur_T_f_w, cam, ref_index, ftr_px, ftr_f, ftr_level,
+                                ftr_type, ftr_grad, d_est, d_min, d_max, max_search_level=2, align_max_iter=10,
+                                max_epi_search_steps=1000):
+    """Matcher::findEpipolarMatchDirect for M candidates (svo_b200_find_epipolar_match_direct)."""
+    M = len(ref_index)
+    ra = _frame_array(ref_frames)
+    refT = c64(np.asarray(ref_T_f_w)).reshape(-1)
+    succ, rej = np.zeros(max(M, 1), np.uint8), np.zeros(max(M, 1), np.uint8)
+    depth, epi = np.zeros(max(M, 1)), np.zeros(max(M, 1))
+    pxc, A = np.zeros((max(M, 1), 2)), np.zeros((max(M, 1), 4))
+    sl, nz = np.zeros(max(M, 1), np.int32), np.zeros(max(M, 1), np.int32)
+    cs = cam_struct(cam)
+    opt = DepthOptions(3, 200.0, max_search_level, align_max_iter, max_epi_search_steps)
+    self._check(self.lib.svo_b200_find_epipolar_match_direct(
+        self.h, ra, _p(refT), len(ref_frames), cur.h, _p(c64(cur_T_f_w).reshape(12)), C.byref(cs), C.byref(opt), M,
+        _p(_i32(ref_index)), _p(c64(ftr_px)), _p(c64(ftr_f)), _p(_i32(ftr_level)), _p(_i32(ftr_type)), _p(c64(ftr_grad)),
+        _p(c64(d_est)), _p(c64(d_min)), _p(c64(d_max)), _p(succ), _p(depth), _p(pxc), _p(sl), _p(epi), _p(rej), _p(A), _p(nz)))
+    return dict(success=succ[:M].astype(bool), depth=depth[:M], px_cur=pxc[:M], search_level=sl[:M], epi_length=epi[:M],
+                reject=rej[:M].astype(bool), A_cur_ref=A[:M].reshape(M, 2, 2), n_zmssd=nz[:M])
+
+
+Context.find_epipolar_match_direct = _find_epipolar_match_direct
 Context.align2d_batch = _align2d_batch
 Context.align1d_batch = _align1d_batch
 Context.find_match_direct = _find_match_direct

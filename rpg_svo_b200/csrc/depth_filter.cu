@@ -43,6 +43,14 @@ struct DepthParams {
   double* px_cur;
   double* z;
   int* n_zmssd;
+  // standalone Matcher::findEpipolarMatchDirect (svo_b200_find_epipolar_match_direct): explicit depth range per
+  // candidate instead of seeds, no Bayesian update, the Matcher's public scratch members as outputs
+  int match_only;
+  const double *d_est, *d_min, *d_max;
+  int* search_level_out;
+  double* epi_length_out;
+  uint8_t* reject_out;
+  double* A_out;
 };
 
 // [EXT] vk::patch_score::ZMSSD<4>::computeScore on the 8x8 block whose top-left pixel is at byte
@@ -130,18 +138,20 @@ __global__ void __launch_bounds__(kDfWarps * 32) depth_filter_kernel(const Depth
 
   int status = 0, n_zm = 0;
   double out_pu = 0, out_pv = 0, out_z = 0;
-  float sa = P.a[i], sb = P.b[i], smu = P.mu[i], ssig = P.sigma2[i];
-  const float szr = P.z_range[i];
+  float sa = 0.f, sb = 0.f, smu = 1.f, ssig = 0.f, szr = 1.f;
+  if (!P.match_only) { sa = P.a[i]; sb = P.b[i]; smu = P.mu[i]; ssig = P.sigma2[i]; szr = P.z_range[i]; }
   const Cam& cam = P.cam;
 
   do {
-    if ((P.batch_counter - P.batch_id[i]) > P.max_n_kfs) { status = SVO_B200_SEED_TOO_OLD; break; }  // :216-219
+    if (!P.match_only && (P.batch_counter - P.batch_id[i]) > P.max_n_kfs) { status = SVO_B200_SEED_TOO_OLD; break; }  // :216-219
     const int r = P.ref_index[i];
     const Pose T_ref_w = pose_from_rt12(P.ref_T_f_w + 12 * (size_t)r);
     const Pose T_cur_w = pose_from_rt12(P.cur_T_f_w);
     const Pose T_ref_cur = pose_mul(T_ref_w, pose_inv(T_cur_w));  // :222
     const double fv[3] = {P.ftr_f[3 * i], P.ftr_f[3 * i + 1], P.ftr_f[3 * i + 2]};
-    {
+    float z_inv_min = 0.f;
+    double d_estimate, d_min, d_max;
+    if (!P.match_only) {
       const double inv_mu = 1.0 / (double)smu;
       const double p[3] = {fv[0] * inv_mu, fv[1] * inv_mu, fv[2] * inv_mu};
       double xyz_f[3];
@@ -153,11 +163,13 @@ __global__ void __launch_bounds__(kDfWarps * 32) depth_filter_kernel(const Depth
       const bool fin = fabs(cu) < 1e9 && fabs(cv) < 1e9;
       const int xi = fin ? (int)cu : -1, yi = fin ? (int)cv : -1;
       if (!(xi >= 0 && xi < cam.width && yi >= 0 && yi < cam.height)) { status = SVO_B200_SEED_NOT_IN_FRAME; break; }
+      const float sq = sqrtf(ssig);
+      z_inv_min = __fadd_rn(smu, sq);
+      const float z_inv_max = fmaxf(__fsub_rn(smu, sq), 0.00000001f);
+      d_estimate = 1.0 / (double)smu; d_min = 1.0 / (double)z_inv_min; d_max = 1.0 / (double)z_inv_max;
+    } else {
+      d_estimate = P.d_est[i]; d_min = P.d_min[i]; d_max = P.d_max[i];
     }
-    const float sq = sqrtf(ssig);
-    const float z_inv_min = __fadd_rn(smu, sq);
-    const float z_inv_max = fmaxf(__fsub_rn(smu, sq), 0.00000001f);
-    const double d_estimate = 1.0 / (double)smu, d_min = 1.0 / (double)z_inv_min, d_max = 1.0 / (double)z_inv_max;
 
     // ---------------- Matcher::findEpipolarMatchDirect (matcher.cpp:179-321) -----------------
     bool ok = false;
@@ -177,6 +189,8 @@ __global__ void __launch_bounds__(kDfWarps * 32) depth_filter_kernel(const Depth
     double Aff[4];
     get_warp_matrix_affine(cam, pxu, pxv, fv, d_estimate, T_cur_ref, lvl, Aff);
     bool reject = false;
+    int out_level = 0;
+    double out_epi_length = 0.0;
     if (P.ftr_type[i] == 1) {  // edgelet filtering (:204-212)
       const double gx0 = P.ftr_grad[2 * i], gy0 = P.ftr_grad[2 * i + 1];
       const double gx = Aff[0] * gx0 + Aff[1] * gy0, gy = Aff[2] * gx0 + Aff[3] * gy0;
@@ -191,6 +205,7 @@ __global__ void __launch_bounds__(kDfWarps * 32) depth_filter_kernel(const Depth
       cam_world2cam(cam, Bx, By, pBu, pBv);
       const double ddx = pAu - pBu, ddy = pAv - pBv;
       const double epi_length = sqrt(ddx * ddx + ddy * ddy) / (double)(1 << L);
+      out_level = L; out_epi_length = epi_length;
       const FrameDesc& rf = P.ref_frames[r];
       ImgView ref_img = {rf.lvl[lvl], rf.w[lvl], rf.h[lvl]};
       warp_warp_affine(Aff, ref_img, pxu, pxv, lvl, L, S);
@@ -264,6 +279,17 @@ __global__ void __launch_bounds__(kDfWarps * 32) depth_filter_kernel(const Depth
         }
       }
     }
+    if (P.match_only) {  // Matcher's public members after the call (matcher.h:92-101)
+      if (lane == 0) {
+        if (P.search_level_out) P.search_level_out[i] = out_level;
+        if (P.epi_length_out) P.epi_length_out[i] = out_epi_length;
+        if (P.reject_out) P.reject_out[i] = reject ? 1 : 0;
+        if (P.A_out) { P.A_out[4 * i] = Aff[0]; P.A_out[4 * i + 1] = Aff[1]; P.A_out[4 * i + 2] = Aff[2]; P.A_out[4 * i + 3] = Aff[3]; }
+      }
+      status = ok ? SVO_B200_SEED_UPDATED : SVO_B200_SEED_NO_MATCH;
+      out_z = ok ? depth : 0.0;
+      break;
+    }
     if (!ok) {
       sb = __fadd_rn(sb, 1.0f);  // it->b++  (:240)
       status = SVO_B200_SEED_NO_MATCH;
@@ -283,7 +309,7 @@ __global__ void __launch_bounds__(kDfWarps * 32) depth_filter_kernel(const Depth
   } while (false);
 
   if (lane == 0) {
-    P.a[i] = sa; P.b[i] = sb; P.mu[i] = smu; P.sigma2[i] = ssig;
+    if (!P.match_only) { P.a[i] = sa; P.b[i] = sb; P.mu[i] = smu; P.sigma2[i] = ssig; }
     P.status[i] = (uint8_t)status;
     if (P.px_cur) { P.px_cur[2 * i] = out_pu; P.px_cur[2 * i + 1] = out_pv; }
     if (P.z) P.z[i] = out_z;
@@ -395,6 +421,108 @@ extern "C" int svo_b200_depth_filter_update(svo_b200_ctx* ctx, const svo_b200_fr
   memcpy(status_out, h + o_st, M);
   if (px_cur_out) memcpy(px_cur_out, h + o_pc, sizeof(double) * 2 * M);
   if (z_out) memcpy(z_out, h + o_z, sizeof(double) * M);
+  if (n_zmssd_out) memcpy(n_zmssd_out, h + o_nz, sizeof(int) * M);
+  return 0;
+}
+
+
+// Matcher::findEpipolarMatchDirect (svo/src/matcher.cpp:179-321) for M independent candidates: the same device code as
+// inside DepthFilter::updateSeeds, with the depth range given explicitly and the Matcher's scratch members returned.
+extern "C" int svo_b200_find_epipolar_match_direct(svo_b200_ctx* ctx, const svo_b200_frame* const* ref_frames,
+                                                   const double* ref_T_f_w, int n_ref, const svo_b200_frame* cur,
+                                                   const double* cur_T_f_w, const svo_b200_camera* cam,
+                                                   const svo_b200_depth_options* opt, int M, const int* ref_index,
+                                                   const double* ftr_px, const double* ftr_f, const int* ftr_level,
+                                                   const int* ftr_type, const double* ftr_grad, const double* d_estimate,
+                                                   const double* d_min, const double* d_max, uint8_t* success_out,
+                                                   double* depth_out, double* px_cur_out, int* search_level_out,
+                                                   double* epi_length_out, uint8_t* reject_out, double* A_cur_ref_out,
+                                                   int* n_zmssd_out) {
+  if (!ctx || !ref_frames || !ref_T_f_w || n_ref <= 0 || !cur || !cur_T_f_w || !cam || !opt || M < 0)
+    return set_err(ctx, SVO_B200_EINVAL, "find_epipolar_match_direct: bad arguments");
+  if (M == 0) return 0;
+  if (!ref_index || !ftr_px || !ftr_f || !ftr_level || !ftr_type || !ftr_grad || !d_estimate || !d_min || !d_max || !success_out)
+    return set_err(ctx, SVO_B200_EINVAL, "find_epipolar_match_direct: NULL candidate arrays");
+  for (int m = 0; m < M; ++m) {
+    if (ref_index[m] < 0 || ref_index[m] >= n_ref)
+      return set_err(ctx, SVO_B200_EINVAL, "find_epipolar_match_direct: ref_index[%d] out of range", m);
+    if (ftr_level[m] < 0 || ftr_level[m] >= ref_frames[ref_index[m]]->n_levels)
+      return set_err(ctx, SVO_B200_EINVAL, "find_epipolar_match_direct: ftr_level[%d] outside the pyramid", m);
+  }
+  if (opt->max_search_level >= cur->n_levels)
+    return set_err(ctx, SVO_B200_EINVAL, "find_epipolar_match_direct: max_search_level %d >= %d pyramid levels",
+                   opt->max_search_level, cur->n_levels);
+  cudaSetDevice(ctx->device);
+  Carver c;
+  const size_t o_ri = c.take(sizeof(int) * M), o_px = c.take(sizeof(double) * 2 * M), o_f = c.take(sizeof(double) * 3 * M),
+               o_lv = c.take(sizeof(int) * M), o_ty = c.take(sizeof(int) * M), o_gr = c.take(sizeof(double) * 2 * M),
+               o_de = c.take(sizeof(double) * M), o_dn = c.take(sizeof(double) * M), o_dx = c.take(sizeof(double) * M),
+               o_rT = c.take(sizeof(double) * 12 * n_ref), o_fr = c.take(sizeof(FrameDesc) * n_ref);
+  const size_t in_bytes = c.off;
+  const size_t o_st = c.take(M), o_pc = c.take(sizeof(double) * 2 * M), o_z = c.take(sizeof(double) * M),
+               o_nz = c.take(sizeof(int) * M), o_sl = c.take(sizeof(int) * M), o_el = c.take(sizeof(double) * M),
+               o_rj = c.take(M), o_A = c.take(sizeof(double) * 4 * M);
+  int rc;
+  if ((rc = ensure_host(ctx, ctx->h_in, c.off))) return rc;
+  if ((rc = ensure_dev(ctx, ctx->d_in, c.off))) return rc;
+  SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  uint8_t* h = static_cast<uint8_t*>(ctx->h_in.p);
+  uint8_t* d = static_cast<uint8_t*>(ctx->d_in.p);
+  memcpy(h + o_ri, ref_index, sizeof(int) * M);
+  memcpy(h + o_px, ftr_px, sizeof(double) * 2 * M);
+  memcpy(h + o_f, ftr_f, sizeof(double) * 3 * M);
+  memcpy(h + o_lv, ftr_level, sizeof(int) * M);
+  memcpy(h + o_ty, ftr_type, sizeof(int) * M);
+  memcpy(h + o_gr, ftr_grad, sizeof(double) * 2 * M);
+  memcpy(h + o_de, d_estimate, sizeof(double) * M);
+  memcpy(h + o_dn, d_min, sizeof(double) * M);
+  memcpy(h + o_dx, d_max, sizeof(double) * M);
+  memcpy(h + o_rT, ref_T_f_w, sizeof(double) * 12 * n_ref);
+  for (int r = 0; r < n_ref; ++r) reinterpret_cast<FrameDesc*>(h + o_fr)[r] = make_desc(ref_frames[r]);
+  SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  SVO_CUDA_CHECK(ctx, cudaMemsetAsync(d + o_st, 0, c.off - o_st, ctx->stream));
+  DepthParams P;
+  memset(&P, 0, sizeof(P));
+  P.match_only = 1;
+  P.ref_frames = reinterpret_cast<const FrameDesc*>(d + o_fr);
+  P.ref_T_f_w = reinterpret_cast<const double*>(d + o_rT);
+  P.cur = make_desc(cur);
+  memcpy(P.cur_T_f_w, cur_T_f_w, sizeof(double) * 12);
+  if ((rc = cam_to_dev(ctx, cam, P.cam))) return rc;
+  P.M = M;
+  P.ref_index = reinterpret_cast<const int*>(d + o_ri);
+  P.ftr_px = reinterpret_cast<const double*>(d + o_px);
+  P.ftr_f = reinterpret_cast<const double*>(d + o_f);
+  P.ftr_level = reinterpret_cast<const int*>(d + o_lv);
+  P.ftr_type = reinterpret_cast<const int*>(d + o_ty);
+  P.ftr_grad = reinterpret_cast<const double*>(d + o_gr);
+  P.d_est = reinterpret_cast<const double*>(d + o_de);
+  P.d_min = reinterpret_cast<const double*>(d + o_dn);
+  P.d_max = reinterpret_cast<const double*>(d + o_dx);
+  P.max_search_level = opt->max_search_level;
+  P.align_max_iter = opt->align_max_iter;
+  P.max_epi_search_steps = opt->max_epi_search_steps;
+  P.status = d + o_st;
+  P.px_cur = reinterpret_cast<double*>(d + o_pc);
+  P.z = reinterpret_cast<double*>(d + o_z);
+  P.n_zmssd = reinterpret_cast<int*>(d + o_nz);
+  P.search_level_out = reinterpret_cast<int*>(d + o_sl);
+  P.epi_length_out = reinterpret_cast<double*>(d + o_el);
+  P.reject_out = d + o_rj;
+  P.A_out = reinterpret_cast<double*>(d + o_A);
+  const int blocks = (M + kDfWarps - 1) / kDfWarps;
+  depth_filter_kernel<<<blocks, kDfWarps * 32, 0, ctx->stream>>>(P);
+  ctx->launches++;
+  SVO_CUDA_CHECK(ctx, cudaGetLastError());
+  SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(h + o_st, d + o_st, c.off - o_st, cudaMemcpyDeviceToHost, ctx->stream));
+  SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int m = 0; m < M; ++m) success_out[m] = h[o_st + m] == SVO_B200_SEED_UPDATED;
+  if (depth_out) memcpy(depth_out, h + o_z, sizeof(double) * M);
+  if (px_cur_out) memcpy(px_cur_out, h + o_pc, sizeof(double) * 2 * M);
+  if (search_level_out) memcpy(search_level_out, h + o_sl, sizeof(int) * M);
+  if (epi_length_out) memcpy(epi_length_out, h + o_el, sizeof(double) * M);
+  if (reject_out) memcpy(reject_out, h + o_rj, M);
+  if (A_cur_ref_out) memcpy(A_cur_ref_out, h + o_A, sizeof(double) * 4 * M);
   if (n_zmssd_out) memcpy(n_zmssd_out, h + o_nz, sizeof(int) * M);
   return 0;
 }

@@ -16,10 +16,13 @@
 // counted end to end.  Differences from the reference, all forced by the missing third-party types:
 //   * Eigen/Sophus/cv::Mat are replaced by the minimal Vector2d/Vector3d/SE3/Image below;
 //   * FramePtr is std::shared_ptr (reference: boost::shared_ptr);
-//   * the camera is the pinhole-without-distortion model only;
-//   * DepthFilter has no detector: addKeyframe takes the new features explicitly, and the mapper
-//     thread / halt flag are the caller's (updateSeeds is synchronous, as in the reference when
-//     thread_ == NULL, depth_filter.cpp:95-96).
+//   * cv::Mat image levels are device-resident: Frame::img_pyr_[l] is an `Image` handle (frame, level), and that
+//     handle is what feature_alignment::align2D / align1D take where the reference takes `const cv::Mat& cur_img`;
+//   * cameras: vk::PinholeCamera (with the optional radial-tangential coefficients) and vk::ATANCamera, restated;
+//   * DepthFilter: updateSeeds is synchronous (the reference's thread_ == NULL branch, depth_filter.cpp:95-96); the
+//     mapper thread is the caller's (see FrameHandlerMono below / INTEGRATION.md: one Context per thread), and
+//     seeds_updating_halt_ is honoured before the launch and when the results are applied (the reference may stop
+//     mid-list; here a halted call leaves the list untouched).
 #pragma once
 #include <algorithm>
 #include <array>
@@ -27,11 +30,18 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <atomic>
+#include <condition_variable>
+#include <limits>
 #include <list>
 #include <map>
+#include <mutex>
 #include <memory>
 #include <stdexcept>
+#include <queue>
+#include <set>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/svo_b200.h"
@@ -64,16 +74,82 @@ struct SE3 {
   Vector3d translation() const { return {m[3], m[7], m[11]}; }
 };
 
-struct PinholeCamera {  // [EXT] vk::PinholeCamera without distortion
+// [EXT] vk::AbstractCamera and the two models the reference ships parameter files for (svo_ros/param/*.yaml), restated
+// from the published rpg_vikit sources; the device runs the same formulas (csrc/svo_math.cuh).
+struct AbstractCamera {
   int width_, height_;
-  double fx_, fy_, cx_, cy_;
-  PinholeCamera(int w, int h, double fx, double fy, double cx, double cy) : width_(w), height_(h), fx_(fx), fy_(fy), cx_(cx), cy_(cy) {}
-  Vector3d cam2world(const Vector2d& px) const {
-    double x = (px[0] - cx_) / fx_, y = (px[1] - cy_) / fy_, n = std::sqrt(x * x + y * y + 1.0);
+  AbstractCamera(int w, int h) : width_(w), height_(h) {}
+  virtual ~AbstractCamera() {}
+  virtual Vector3d cam2world(const Vector2d& px) const = 0;
+  virtual Vector2d world2cam(const Vector3d& xyz_c) const = 0;
+  virtual double errorMultiplier2() const = 0;
+  virtual svo_b200_camera c_abi() const = 0;
+  int width() const { return width_; }
+  int height() const { return height_; }
+  bool isInFrame(int x, int y, int boundary = 0) const {
+    return x >= boundary && x < width_ - boundary && y >= boundary && y < height_ - boundary;
+  }
+  bool isInFrame(int x, int y, int boundary, int level) const {
+    return x >= boundary && x < width_ / (1 << level) - boundary && y >= boundary && y < height_ / (1 << level) - boundary;
+  }
+};
+struct PinholeCamera : AbstractCamera {  // vk::PinholeCamera(width, height, fx, fy, cx, cy, d0..d4)
+  double fx_, fy_, cx_, cy_, d_[5];
+  bool distortion_;
+  PinholeCamera(int w, int h, double fx, double fy, double cx, double cy, double d0 = 0, double d1 = 0, double d2 = 0,
+                double d3 = 0, double d4 = 0)
+      : AbstractCamera(w, h), fx_(fx), fy_(fy), cx_(cx), cy_(cy), d_{d0, d1, d2, d3, d4}, distortion_(std::fabs(d0) > 0.0000001) {}
+  Vector3d cam2world(const Vector2d& px) const override {
+    double x, y;
+    if (!distortion_) {
+      x = (px[0] - cx_) / fx_; y = (px[1] - cy_) / fy_;
+    } else {  // cv::undistortPoints on one CV_32FC2 point [EXT OpenCV]
+      const double x0 = ((double)(float)px[0] - cx_) * (1.0 / fx_), y0 = ((double)(float)px[1] - cy_) * (1.0 / fy_);
+      x = x0; y = y0;
+      for (int j = 0; j < 5; ++j) {
+        const double r2 = x * x + y * y, icdist = 1.0 / (1.0 + ((d_[4] * r2 + d_[1]) * r2 + d_[0]) * r2);
+        const double dX = 2.0 * d_[2] * x * y + d_[3] * (r2 + 2.0 * x * x), dY = d_[2] * (r2 + 2.0 * y * y) + 2.0 * d_[3] * x * y;
+        x = (x0 - dX) * icdist; y = (y0 - dY) * icdist;
+      }
+      x = (double)(float)x; y = (double)(float)y;
+    }
+    const double n = std::sqrt(x * x + y * y + 1.0);
     return {x / n, y / n, 1.0 / n};
   }
-  double errorMultiplier2() const { return std::fabs(fx_); }
-  svo_b200_camera c_abi() const { return svo_b200_camera{fx_, fy_, cx_, cy_, width_, height_}; }
+  Vector2d world2cam(const Vector3d& p) const override {
+    const double x = p[0] / p[2], y = p[1] / p[2];
+    if (!distortion_) return {std::fma(fx_, x, cx_), std::fma(fy_, y, cy_)};
+    const double r2 = std::fma(x, x, y * y), r4 = r2 * r2, r6 = r4 * r2;
+    const double a1 = 2.0 * x * y, a2 = std::fma(2.0 * x, x, r2), a3 = std::fma(2.0 * y, y, r2);
+    const double cdist = std::fma(d_[4], r6, std::fma(d_[1], r4, std::fma(d_[0], r2, 1.0)));
+    const double xd = std::fma(d_[3], a2, std::fma(d_[2], a1, x * cdist)), yd = std::fma(d_[3], a1, std::fma(d_[2], a3, y * cdist));
+    return {std::fma(xd, fx_, cx_), std::fma(yd, fy_, cy_)};
+  }
+  double errorMultiplier2() const override { return std::fabs(fx_); }
+  svo_b200_camera c_abi() const override {
+    return svo_b200_camera{fx_, fy_, cx_, cy_, width_, height_, SVO_B200_CAM_PINHOLE, 0, {d_[0], d_[1], d_[2], d_[3], d_[4]}};
+  }
+};
+struct ATANCamera : AbstractCamera {  // vk::ATANCamera(width, height, fx, fy, cx, cy, s): normalised parameters in
+  double fx_, fy_, cx_, cy_, s_, tans_, tans_inv_, s_inv_;
+  ATANCamera(double width, double height, double fx, double fy, double cx, double cy, double s)
+      : AbstractCamera((int)width, (int)height), fx_(width * fx), fy_(height * fy), cx_(cx * width - 0.5), cy_(cy * height - 0.5),
+        s_(s), tans_(s != 0.0 ? 2.0 * std::tan(s / 2.0) : 0.0), tans_inv_(s != 0.0 ? 1.0 / tans_ : 0.0), s_inv_(s != 0.0 ? 1.0 / s : 0.0) {}
+  Vector3d cam2world(const Vector2d& px) const override {
+    const double dx = (px[0] - cx_) * (1.0 / fx_), dy = (px[1] - cy_) * (1.0 / fy_), dist_r = std::sqrt(dx * dx + dy * dy);
+    const double r = s_ != 0.0 ? std::tan(dist_r * s_) * tans_inv_ : dist_r, fac = dist_r > 0.01 ? r / dist_r : 1.0;
+    const double x = fac * dx, y = fac * dy, n = std::sqrt(x * x + y * y + 1.0);
+    return {x / n, y / n, 1.0 / n};
+  }
+  Vector2d world2cam(const Vector3d& p) const override {
+    const double x = p[0] / p[2], y = p[1] / p[2], r = std::sqrt(std::fma(x, x, y * y));
+    const double fac = (r < 0.001 || s_ == 0.0) ? 1.0 : s_inv_ * std::atan(r * tans_) / r;
+    return {std::fma(fx_ * fac, x, cx_), std::fma(fy_ * fac, y, cy_)};
+  }
+  double errorMultiplier2() const override { return std::fabs(fx_); }
+  svo_b200_camera c_abi() const override {
+    return svo_b200_camera{fx_, fy_, cx_, cy_, width_, height_, SVO_B200_CAM_ATAN, 0, {s_, 0, 0, 0, 0}};
+  }
 };
 
 // One CUDA context per calling thread, as include/svo_b200.h asks.
@@ -107,6 +183,7 @@ struct Point {  // svo/include/svo/point.h:35-106 (the fields the hot path reads
   explicit Point(const Vector3d& pos) : pos_(pos) {}
   Point(const Vector3d& pos, Feature* ftr) : pos_(pos) { obs_.push_front(ftr); }  // point.cpp:38-50
   void addFrameRef(Feature* ftr) { obs_.push_front(ftr); }                        // point.cpp:55-59
+  inline bool getCloseViewObs(const Vector3d& framepos, Feature*& ftr) const;     // point.cpp:97-117
 };
 
 struct Feature {  // svo/include/svo/feature.h:25-71
@@ -126,20 +203,30 @@ typedef std::list<Feature*> Features;
 
 // svo/include/svo/frame.h:40-139.  The image pyramid lives in HBM (level 0 uploaded once, the other
 // levels built on the device with the scalar vk::halfSample rule).
+// What the reference passes around as `const cv::Mat&` for one pyramid level: here the level lives in HBM, so the
+// handle names (device frame, level); cols / rows as cv::Mat has them.
+struct Image {
+  const class Frame* frame = nullptr;
+  int level = 0, cols = 0, rows = 0;
+};
+typedef std::vector<Image> ImgPyr;
+
 class Frame {
  public:
-  PinholeCamera* cam_;
+  AbstractCamera* cam_;
   SE3 T_f_w_;
+  ImgPyr img_pyr_;  // frame.h:52 (device-resident levels)
   Matrix6d Cov_{};
   Features fts_;
-  std::vector<Feature*> key_pts_ = std::vector<Feature*>(5, nullptr);  // frame.h:53 (maintained by the caller: setKeyPoints)
+  std::vector<Feature*> key_pts_ = std::vector<Feature*>(5, nullptr);  // frame.h:53
   bool is_keyframe_ = false;
-  Frame(Context& ctx, PinholeCamera* cam, const uint8_t* img, int n_levels, double /*timestamp*/) : cam_(cam), ctx_(ctx) {
+  Frame(Context& ctx, AbstractCamera* cam, const uint8_t* img, int n_levels, double /*timestamp*/) : cam_(cam), ctx_(ctx) {
     if (!img) throw std::runtime_error("Frame: provided image is empty");  // frame.cpp:51-52
     ctx_.check(svo_b200_frame_create(ctx_.get(), cam->width_, cam->height_, n_levels, &dev_));
     const uint8_t* lv[1] = {img};
-    ctx_.check(svo_b200_frame_upload(ctx_.get(), dev_, lv, 1));
+    ctx_.check(svo_b200_frame_upload(ctx_.get(), dev_, lv, 1));  // createImgPyramid on the device (frame.cpp:156-165)
     ctx_.check(svo_b200_synchronize(ctx_.get()));
+    for (int l = 0; l < n_levels; ++l) img_pyr_.push_back(Image{this, l, cam->width_ >> l, cam->height_ >> l});
   }
   ~Frame() {
     for (Feature* f : fts_) delete f;  // frame.cpp:43-46
@@ -147,9 +234,16 @@ class Frame {
   }
   Frame(const Frame&) = delete;
   void addFeature(Feature* ftr) { fts_.push_back(ftr); }
-  void setKeyframe() { is_keyframe_ = true; }
+  inline void setKeyPoints();                 // frame.cpp:71-79
+  inline void checkKeyPoints(Feature* ftr);   // frame.cpp:81-124
+  void setKeyframe() { is_keyframe_ = true; setKeyPoints(); }  // frame.cpp:60-64
   bool isKeyframe() const { return is_keyframe_; }
   Vector3d pos() const { return T_f_w_.inverse().translation(); }  // frame.h:112
+  Vector2d w2c(const Vector3d& xyz_w) const {                        // frame.h:88
+    const double* m = T_f_w_.m;
+    return cam_->world2cam({m[0] * xyz_w[0] + m[1] * xyz_w[1] + m[2] * xyz_w[2] + m[3], m[4] * xyz_w[0] + m[5] * xyz_w[1] + m[6] * xyz_w[2] + m[7],
+                            m[8] * xyz_w[0] + m[9] * xyz_w[1] + m[10] * xyz_w[2] + m[11]});
+  }
   size_t nObs() const { return fts_.size(); }
   svo_b200_frame* device() const { return dev_; }
   Context& context() const { return ctx_; }
@@ -162,6 +256,46 @@ typedef std::shared_ptr<Frame> FramePtr;
 
 inline Feature::Feature(Frame* _frame, const Vector2d& _px, int _level)
     : frame(_frame), px(_px), f(_frame->cam_->cam2world(_px)), level(_level) {}
+
+inline void Frame::setKeyPoints() {
+  for (size_t i = 0; i < 5; ++i)
+    if (key_pts_[i] != nullptr && key_pts_[i]->point == nullptr) key_pts_[i] = nullptr;
+  for (Feature* ftr : fts_)
+    if (ftr->point != nullptr) checkKeyPoints(ftr);
+}
+inline void Frame::checkKeyPoints(Feature* ftr) {  // including the reference's `px[0] < cv` comparisons (sic, frame.cpp:106,114)
+  const int cu = cam_->width() / 2, cv = cam_->height() / 2;
+  auto prod = [&](Feature* f) { return (f->px[0] - cu) * (f->px[1] - cv); };
+  if (key_pts_[0] == nullptr) key_pts_[0] = ftr;
+  else if (std::max(std::fabs(ftr->px[0] - cu), std::fabs(ftr->px[1] - cv)) <
+           std::max(std::fabs(key_pts_[0]->px[0] - cu), std::fabs(key_pts_[0]->px[1] - cv)))
+    key_pts_[0] = ftr;
+  if (ftr->px[0] >= cu && ftr->px[1] >= cv) { if (key_pts_[1] == nullptr || prod(ftr) > prod(key_pts_[1])) key_pts_[1] = ftr; }
+  if (ftr->px[0] >= cu && ftr->px[1] < cv) { if (key_pts_[2] == nullptr || prod(ftr) > prod(key_pts_[2])) key_pts_[2] = ftr; }
+  if (ftr->px[0] < cv && ftr->px[1] < cv) { if (key_pts_[3] == nullptr || prod(ftr) > prod(key_pts_[3])) key_pts_[3] = ftr; }
+  if (ftr->px[0] < cv && ftr->px[1] >= cv) { if (key_pts_[4] == nullptr || prod(ftr) > prod(key_pts_[4])) key_pts_[4] = ftr; }
+}
+
+// Point::getCloseViewObs (point.cpp:97-117): the observation with the smallest viewing-angle difference, refused
+// beyond 60 degrees.
+inline bool Point::getCloseViewObs(const Vector3d& framepos, Feature*& ftr) const {
+  Vector3d obs_dir{framepos[0] - pos_[0], framepos[1] - pos_[1], framepos[2] - pos_[2]};
+  const double n = std::sqrt(obs_dir[0] * obs_dir[0] + obs_dir[1] * obs_dir[1] + obs_dir[2] * obs_dir[2]);
+  for (double& v : obs_dir) v /= n;
+  auto min_it = obs_.begin();
+  double min_cos_angle = 0;
+  for (auto it = obs_.begin(), ite = obs_.end(); it != ite; ++it) {
+    const Vector3d fp = (*it)->frame->pos();
+    Vector3d dir{fp[0] - pos_[0], fp[1] - pos_[1], fp[2] - pos_[2]};
+    const double dn = std::sqrt(dir[0] * dir[0] + dir[1] * dir[1] + dir[2] * dir[2]);
+    const double cos_angle = (obs_dir[0] * dir[0] + obs_dir[1] * dir[1] + obs_dir[2] * dir[2]) / dn;
+    if (cos_angle > min_cos_angle) { min_cos_angle = cos_angle; min_it = it; }
+  }
+  if (obs_.empty()) return false;
+  ftr = *min_it;
+  if (min_cos_angle < 0.5) return false;  // assume that observations larger than 60 degrees are useless
+  return true;
+}
 
 // ------------------------------------------------------------------------------------------------
 // svo::SparseImgAlign (svo/include/svo/sparse_img_align.h:33-81)
@@ -255,27 +389,93 @@ inline void optimizeGaussNewton(const double reproj_thresh, const size_t n_iter,
 }  // namespace pose_optimizer
 
 // ------------------------------------------------------------------------------------------------
-// svo::feature_alignment (svo/include/svo/feature_alignment.h:29-44).  `cur_img` of the reference is
-// (frame, level) here because the pyramid lives on the device.
+// svo::feature_alignment (svo/include/svo/feature_alignment.h:29-44): the reference's argument lists, with the
+// device-resident `Image` handle (frame->img_pyr_[level]) where the reference has `const cv::Mat& cur_img`.
 // ------------------------------------------------------------------------------------------------
 namespace feature_alignment {
-inline bool align2D(const Frame& cur_frame, int level, uint8_t* ref_patch_with_border, uint8_t* ref_patch, const int n_iter,
-                    Vector2d& cur_px_estimate, bool /*no_simd*/ = false) {
+inline bool align1D(const Image& cur_img, const std::array<float, 2>& dir, uint8_t* ref_patch_with_border, uint8_t* ref_patch,
+                    const int n_iter, Vector2d& cur_px_estimate, double& h_inv) {
   uint8_t conv = 0;
-  Context& c = cur_frame.context();
-  c.check(svo_b200_align2d_batch(c.get(), cur_frame.device(), 1, &level, ref_patch_with_border, ref_patch, n_iter,
-                                 cur_px_estimate.data(), &conv));
-  return conv != 0;
-}
-inline bool align1D(const Frame& cur_frame, int level, const std::array<float, 2>& dir, uint8_t* ref_patch_with_border,
-                    uint8_t* ref_patch, const int n_iter, Vector2d& cur_px_estimate, double& h_inv) {
-  uint8_t conv = 0;
-  Context& c = cur_frame.context();
-  c.check(svo_b200_align1d_batch(c.get(), cur_frame.device(), 1, &level, dir.data(), ref_patch_with_border, ref_patch,
+  Context& c = cur_img.frame->context();
+  c.check(svo_b200_align1d_batch(c.get(), cur_img.frame->device(), 1, &cur_img.level, dir.data(), ref_patch_with_border, ref_patch,
                                  n_iter, cur_px_estimate.data(), &conv, &h_inv));
   return conv != 0;
 }
+inline bool align2D(const Image& cur_img, uint8_t* ref_patch_with_border, uint8_t* ref_patch, const int n_iter,
+                    Vector2d& cur_px_estimate, bool /*no_simd*/ = false) {
+  uint8_t conv = 0;
+  Context& c = cur_img.frame->context();
+  c.check(svo_b200_align2d_batch(c.get(), cur_img.frame->device(), 1, &cur_img.level, ref_patch_with_border, ref_patch, n_iter,
+                                 cur_px_estimate.data(), &conv));
+  return conv != 0;
+}
 }  // namespace feature_alignment
+
+// ------------------------------------------------------------------------------------------------
+// svo::Matcher (svo/include/svo/matcher.h:69-130): the two entry points the hot path calls, and the public scratch
+// members their callers read afterwards (reprojector.cpp:182-193, depth_filter.cpp:257).  Each call is one device
+// launch for one candidate; the batched paths (Reprojector, DepthFilter) use the batch entry points directly.
+// ------------------------------------------------------------------------------------------------
+class Matcher {
+ public:
+  static const int halfpatch_size_ = 4;
+  static const int patch_size_ = 8;
+  struct Options {
+    bool align_1d = false;
+    int align_max_iter = 10;
+    double max_epi_length_optim = 2.0;
+    size_t max_epi_search_steps = 1000;
+    bool subpix_refinement = true;
+    bool epi_search_edgelet_filtering = true;
+    double epi_search_edgelet_max_angle = 0.7;
+    int n_pyr_levels = 3;  // Config::nPyrLevels() (config.cpp:30)
+  } options_;
+  std::array<double, 4> A_cur_ref_{};  // affine warp matrix, row-major
+  double epi_length_ = 0.0;
+  double h_inv_ = 0.0;
+  int search_level_ = 0;
+  bool reject_ = false;
+  Feature* ref_ftr_ = nullptr;
+  Vector2d px_cur_{};
+
+  // matcher.cpp:135-177.  px_cur must hold an estimate within ~2-3 px of the result.
+  bool findMatchDirect(const Point& pt, const Frame& cur_frame, Vector2d& px_cur) {
+    if (!pt.getCloseViewObs(cur_frame.pos(), ref_ftr_)) return false;
+    const Frame& rf = *ref_ftr_->frame;
+    if (!rf.cam_->isInFrame((int)ref_ftr_->px[0] / (1 << ref_ftr_->level), (int)ref_ftr_->px[1] / (1 << ref_ftr_->level),
+                            halfpatch_size_ + 2, ref_ftr_->level))
+      return false;
+    const svo_b200_frame* ref_dev = rf.device();
+    const svo_b200_camera cam = cur_frame.cam_->c_abi();
+    const svo_b200_match_options opt = {options_.n_pyr_levels - 1, options_.align_max_iter};
+    const int ref_index = 0, type = ref_ftr_->type;
+    uint8_t ok = 0;
+    Context& c = cur_frame.context();
+    c.check(svo_b200_find_match_direct(c.get(), &ref_dev, rf.T_f_w_.m, 1, cur_frame.device(), cur_frame.T_f_w_.m, &cam, &opt, 1,
+                                       &ref_index, ref_ftr_->px.data(), ref_ftr_->f.data(), &ref_ftr_->level, &type,
+                                       ref_ftr_->grad.data(), pt.pos_.data(), px_cur.data(), &ok, &search_level_,
+                                       A_cur_ref_.data(), &h_inv_));
+    return ok != 0;
+  }
+  // matcher.cpp:179-321
+  bool findEpipolarMatchDirect(const Frame& ref_frame, const Frame& cur_frame, const Feature& ref_ftr, const double d_estimate,
+                               const double d_min, const double d_max, double& depth) {
+    const svo_b200_frame* ref_dev = ref_frame.device();
+    const svo_b200_camera cam = cur_frame.cam_->c_abi();
+    const svo_b200_depth_options opt = {3, 200.0, options_.n_pyr_levels - 1, options_.align_max_iter, (int)options_.max_epi_search_steps};
+    const int ref_index = 0, type = ref_ftr.type;
+    uint8_t ok = 0, rej = 0;
+    double z = 0.0;
+    Context& c = cur_frame.context();
+    c.check(svo_b200_find_epipolar_match_direct(c.get(), &ref_dev, ref_frame.T_f_w_.m, 1, cur_frame.device(), cur_frame.T_f_w_.m, &cam,
+                                                &opt, 1, &ref_index, ref_ftr.px.data(), ref_ftr.f.data(), &ref_ftr.level, &type,
+                                                ref_ftr.grad.data(), &d_estimate, &d_min, &d_max, &ok, &z, px_cur_.data(),
+                                                &search_level_, &epi_length_, &rej, A_cur_ref_.data(), nullptr));
+    reject_ = rej != 0;
+    if (ok) depth = z;
+    return ok != 0;
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // svo::DepthFilter (svo/include/svo/depth_filter.h:35-51,53-158)
@@ -291,7 +491,8 @@ class AbstractDetector {
       : cell_size_(cell_size), n_pyr_levels_(n_pyr_levels), grid_n_cols_((int)std::ceil((double)img_width / cell_size)),
         grid_n_rows_((int)std::ceil((double)img_height / cell_size)), grid_occupancy_((size_t)grid_n_cols_ * grid_n_rows_, 0) {}
   virtual ~AbstractDetector() {}
-  virtual void detect(Frame* frame, const double detection_threshold, Features& fts) = 0;  // img_pyr = the frame's device pyramid
+  // img_pyr = the frame's device pyramid; `ctx` = the calling thread's context (default: the frame's)
+  virtual void detect(Frame* frame, const double detection_threshold, Features& fts, Context* ctx = nullptr) = 0;
   void setGridOccpuancy(const Vector2d& px) {  // feature_detection.cpp:51-56 (spelling as in the reference)
     grid_occupancy_.at((size_t)((int)(px[1] / cell_size_) * grid_n_cols_ + (int)(px[0] / cell_size_))) = 1;
   }
@@ -308,12 +509,12 @@ class FastDetector : public AbstractDetector {
  public:
   FastDetector(int img_width, int img_height, int cell_size, int n_pyr_levels)
       : AbstractDetector(img_width, img_height, cell_size, n_pyr_levels) {}
-  void detect(Frame* frame, const double detection_threshold, Features& fts) override {  // feature_detection.cpp:66-115
+  void detect(Frame* frame, const double detection_threshold, Features& fts, Context* ctx = nullptr) override {  // feature_detection.cpp:66-115
     const svo_b200_detect_options opt = {cell_size_, n_pyr_levels_, 20, 0, detection_threshold};
     const int cap = (int)grid_occupancy_.size();
     std::vector<int> x(cap), y(cap), level(cap);
     int n = 0;
-    Context& c = frame->context();
+    Context& c = ctx ? *ctx : frame->context();
     c.check(svo_b200_fast_detect(c.get(), frame->device(), &opt, grid_occupancy_.data(), cap, x.data(), y.data(), level.data(),
                                  nullptr, &n));
     for (int i = 0; i < n; ++i) fts.push_back(new Feature(frame, Vector2d{(double)x[i], (double)y[i]}, level[i]));
@@ -344,31 +545,83 @@ class DepthFilter {
   explicit DepthFilter(callback_t seed_converged_cb) : seed_converged_cb_(seed_converged_cb) {}
   DepthFilter(feature_detection::DetectorPtr feature_detector, callback_t seed_converged_cb)  // depth_filter.h:88-90
       : seed_converged_cb_(seed_converged_cb), feature_detector_(feature_detector) {}
-  // addKeyframe + initializeSeeds (depth_filter.cpp:101-132): detect new corners away from the frame's features
-  void addKeyframe(FramePtr frame, double depth_mean, double depth_min, double triang_min_corner_score = 20.0) {
-    if (!feature_detector_) throw std::runtime_error("DepthFilter: no feature detector (use the overload that takes the features)");
-    Features new_features;
-    feature_detector_->setExistingFeatures(frame->fts_);
-    feature_detector_->detect(frame.get(), triang_min_corner_score, new_features);
-    addKeyframe(frame, std::vector<Feature*>(new_features.begin(), new_features.end()), depth_mean, depth_min);
+  virtual ~DepthFilter() { stopThread(); }
+  // The mapper thread issues its device work on a context (= CUDA stream + staging buffers) of its own, as
+  // include/svo_b200.h asks; without one the filter borrows the context of the frame it is handed.
+  void setContext(Context* ctx) { ctx_ = ctx; }
+  // depth_filter.cpp:64-86: the reference's mapper boost::thread
+  void startThread() { thread_.reset(new std::thread(&DepthFilter::updateSeedsLoop, this)); }
+  void stopThread() {
+    if (!thread_) return;
+    seeds_updating_halt_ = true;
+    { std::lock_guard<std::mutex> lock(frame_queue_mut_); quit_ = true; }
+    frame_queue_cond_.notify_one();
+    thread_->join();
+    thread_.reset();
+    quit_ = false;
   }
-  // the same with the detector's output passed in
+  // depth_filter.cpp:88-99
+  void addFrame(FramePtr frame) {
+    if (thread_) {
+      {
+        std::lock_guard<std::mutex> lock(frame_queue_mut_);
+        if (frame_queue_.size() > 2) frame_queue_.pop();
+        frame_queue_.push(frame);
+      }
+      seeds_updating_halt_ = false;
+      frame_queue_cond_.notify_one();
+    } else {
+      updateSeeds(frame);
+    }
+  }
+  // depth_filter.cpp:101-114 + initializeSeeds :116-132: detect new corners away from the frame's features
+  void addKeyframe(FramePtr frame, double depth_mean, double depth_min) {
+    if (!feature_detector_) throw std::runtime_error("DepthFilter: no feature detector (use the overload that takes the features)");
+    new_keyframe_min_depth_ = depth_min;
+    new_keyframe_mean_depth_ = depth_mean;
+    if (thread_) {
+      { std::lock_guard<std::mutex> lock(frame_queue_mut_); new_keyframe_ = frame; new_keyframe_set_ = true; }
+      seeds_updating_halt_ = true;
+      frame_queue_cond_.notify_one();
+    } else {
+      initializeSeeds(frame);
+    }
+  }
+  // the same with the detector's output passed in (synchronous)
   void addKeyframe(FramePtr frame, const std::vector<Feature*>& new_features, double depth_mean, double depth_min) {
+    seeds_updating_halt_ = true;
+    std::lock_guard<std::mutex> lock(seeds_mut_);
     keyframes_.push_back(frame);
     ++Seed::batch_counter();
     for (Feature* ftr : new_features) seeds_.push_back(Seed(ftr, (float)depth_mean, (float)depth_min));
+    seeds_updating_halt_ = false;
   }
-  void addFrame(FramePtr frame) { updateSeeds(frame); }  // synchronous branch (:95-96)
+  bool idle() {  // test helper: the mapper has drained its queue
+    std::lock_guard<std::mutex> lock(frame_queue_mut_);
+    return frame_queue_.empty() && !new_keyframe_set_ && !busy_;
+  }
   void removeKeyframe(FramePtr frame) {                  // :134-151
+    seeds_updating_halt_ = true;
+    std::lock_guard<std::mutex> lock(seeds_mut_);
     seeds_.remove_if([&](const Seed& s) { return s.ftr->frame == frame.get(); });
     keyframes_.remove(frame);
+    seeds_updating_halt_ = false;
   }
-  void reset() { seeds_.clear(); keyframes_.clear(); }
+  void reset() { seeds_updating_halt_ = true; { std::lock_guard<std::mutex> lock(seeds_mut_); seeds_.clear(); } keyframes_.clear(); seeds_updating_halt_ = false; }
   std::list<Seed>& getSeeds() { return seeds_; }
+  // depth_filter.cpp:182-195: copy of the seeds that belong to `frame`
+  void getSeedsCopy(const FramePtr& frame, std::list<Seed>& seeds) {
+    std::lock_guard<std::mutex> lock(seeds_mut_);
+    for (const Seed& s : seeds_)
+      if (s.ftr->frame == frame.get()) seeds.push_back(s);
+  }
+  std::atomic<bool> seeds_updating_halt_{false};  // depth_filter.h:140: set while the seed list is being edited elsewhere
   size_t n_failed_matches_ = 0, n_updates_ = 0;
 
   // depth_filter.cpp:197-291: one launch for all seeds, then the list side effects in list order
   virtual void updateSeeds(FramePtr frame) {
+    std::lock_guard<std::mutex> lock(seeds_mut_);  // lock_t lock(seeds_mut_)  (:202)
+    if (seeds_updating_halt_) return;              // (:212) checked before the launch ...
     const size_t M = seeds_.size();
     if (M == 0) return;
     std::vector<FramePtr> refs(keyframes_.begin(), keyframes_.end());
@@ -394,15 +647,20 @@ class DepthFilter {
     const svo_b200_camera cam = frame->cam_->c_abi();
     const svo_b200_depth_options opt = {options_.max_n_kfs, options_.seed_convergence_sigma2_thresh,
                                         options_.max_search_level, 10, 1000};
-    Context& c = frame->context();
+    Context& c = ctx_ ? *ctx_ : frame->context();
     c.check(svo_b200_depth_filter_update(c.get(), ref_dev.data(), ref_T.data(), (int)refs.size(), frame->device(),
                                          frame->T_f_w_.m, &cam, &opt, (int)M, ref_index.data(), px.data(), f.data(),
                                          level.data(), type.data(), grad.data(), batch.data(), Seed::batch_counter(),
                                          a.data(), b.data(), mu.data(), zr.data(), s2.data(), status.data(),
                                          px_cur.data(), z.data(), nullptr));
+    if (seeds_updating_halt_) return;  // ... and before the results are applied: a halted call changes nothing
     i = 0;
     for (auto it = seeds_.begin(); it != seeds_.end(); ++i) {
       it->a = a[i]; it->b = b[i]; it->mu = mu[i]; it->sigma2 = s2[i];
+      // the feature detector should not initialise new seeds close to a seed that was just matched in a keyframe (:254-258)
+      if (frame->isKeyframe() && feature_detector_ &&
+          (status[i] == SVO_B200_SEED_UPDATED || status[i] == SVO_B200_SEED_CONVERGED || status[i] == SVO_B200_SEED_NAN))
+        feature_detector_->setGridOccpuancy(Vector2d{px_cur[2 * i], px_cur[2 * i + 1]});
       switch (status[i]) {
         case SVO_B200_SEED_TOO_OLD: it = seeds_.erase(it); continue;                       // :216-219
         case SVO_B200_SEED_NO_MATCH: ++n_failed_matches_; break;                           // :240-244
@@ -413,7 +671,7 @@ class DepthFilter {
           const Vector3d p{it->ftr->f[0] * d, it->ftr->f[1] * d, it->ftr->f[2] * d};
           Vector3d xyz_world;
           for (int r = 0; r < 3; ++r) xyz_world[r] = T_w_f.m[r * 4] * p[0] + T_w_f.m[r * 4 + 1] * p[1] + T_w_f.m[r * 4 + 2] * p[2] + T_w_f.m[r * 4 + 3];
-          Point* point = new Point(xyz_world);
+          Point* point = new Point(xyz_world, it->ftr);  // (:265) the seed's feature is the point's first observation
           it->ftr->point = point;
           seed_converged_cb_(point, it->sigma2);
           it = seeds_.erase(it);
@@ -426,13 +684,58 @@ class DepthFilter {
       ++it;
     }
   }
-  virtual ~DepthFilter() = default;
 
  protected:
+  // depth_filter.cpp:116-132
+  void initializeSeeds(FramePtr frame) {
+    Features new_features;
+    feature_detector_->setExistingFeatures(frame->fts_);
+    feature_detector_->detect(frame.get(), triang_min_corner_score_, new_features, ctx_);
+    addKeyframe(frame, std::vector<Feature*>(new_features.begin(), new_features.end()), new_keyframe_mean_depth_,
+                new_keyframe_min_depth_);
+  }
+  // depth_filter.cpp:153-180: the mapper thread; a pending keyframe takes precedence over queued frames
+  void updateSeedsLoop() {
+    for (;;) {
+      FramePtr frame;
+      bool is_new_kf = false;
+      {
+        std::unique_lock<std::mutex> lock(frame_queue_mut_);
+        frame_queue_cond_.wait(lock, [&] { return quit_ || new_keyframe_set_ || !frame_queue_.empty(); });
+        if (quit_) return;
+        if (new_keyframe_set_) {
+          new_keyframe_set_ = false;
+          seeds_updating_halt_ = false;
+          while (!frame_queue_.empty()) frame_queue_.pop();  // clear_frame_queue (:166)
+          frame = new_keyframe_;
+          is_new_kf = true;
+        } else {
+          frame = frame_queue_.front();
+          frame_queue_.pop();
+        }
+        busy_ = true;
+      }
+      updateSeeds(frame);
+      if (is_new_kf) initializeSeeds(frame);  // frame->isKeyframe() (:176-177)
+      { std::lock_guard<std::mutex> lock(frame_queue_mut_); busy_ = false; }
+    }
+  }
   callback_t seed_converged_cb_;
   feature_detection::DetectorPtr feature_detector_;
   std::list<Seed> seeds_;
+  std::mutex seeds_mut_;
   std::list<FramePtr> keyframes_;
+  Context* ctx_ = nullptr;
+  std::unique_ptr<std::thread> thread_;
+  std::queue<FramePtr> frame_queue_;
+  std::mutex frame_queue_mut_;
+  std::condition_variable frame_queue_cond_;
+  FramePtr new_keyframe_;
+  bool new_keyframe_set_ = false, quit_ = false, busy_ = false;
+  double new_keyframe_min_depth_ = 0.0, new_keyframe_mean_depth_ = 0.0;
+
+ public:
+  double triang_min_corner_score_ = 20.0;  // Config::triangMinCornerScore() (config.cpp:44)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -443,11 +746,14 @@ class MapPointCandidates {
   typedef std::pair<Point*, Feature*> PointCandidate;
   std::list<PointCandidate> candidates_;
   std::list<Point*> trash_points_;
+  std::mutex mut_;  // map.h:47: the depth filter (mapper thread) appends while the tracker reads
   ~MapPointCandidates() { reset(); }
   void newCandidatePoint(Point* point, double /*depth_sigma2*/) {  // map.cpp:213-218
     point->type_ = Point::TYPE_CANDIDATE;
+    std::lock_guard<std::mutex> lock(mut_);
     candidates_.push_back(PointCandidate(point, point->obs_.front()));
   }
+  void addCandidatePointToFrame(const std::shared_ptr<Frame>& frame);  // map.cpp:220-237
   void deleteCandidate(PointCandidate& c) {  // map.cpp:280-287
     delete c.second; c.second = nullptr;
     c.first->type_ = Point::TYPE_DELETED;
@@ -497,7 +803,7 @@ class Reprojector {
   Options options_;
   size_t n_matches_ = 0, n_trials_ = 0;
 
-  Reprojector(PinholeCamera* cam, Map& map, Options opt = Options(), unsigned shuffle_seed = 1) : options_(opt), map_(map) {
+  Reprojector(AbstractCamera* cam, Map& map, Options opt = Options(), unsigned shuffle_seed = 1) : options_(opt), map_(map) {
     // initializeGrid (reprojector.cpp:47-58); the reference shuffles with rand(), here a seeded LCG Fisher-Yates
     const int cols = (cam->width_ + options_.grid_size - 1) / options_.grid_size, rows = (cam->height_ + options_.grid_size - 1) / options_.grid_size;
     cell_order_.resize((size_t)cols * rows);
@@ -603,6 +909,221 @@ class Reprojector {
  private:
   Map& map_;
   std::vector<int> cell_order_;
+};
+
+inline void MapPointCandidates::addCandidatePointToFrame(const FramePtr& frame) {
+  std::lock_guard<std::mutex> lock(mut_);
+  for (auto it = candidates_.begin(); it != candidates_.end();) {
+    if (it->first->obs_.front()->frame == frame.get()) {
+      it->first->type_ = Point::TYPE_UNKNOWN;
+      it->first->n_failed_reproj_ = 0;
+      it->second->frame->addFeature(it->second);
+      it = candidates_.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// svo::FrameHandlerMono (svo/include/svo/frame_handler_mono.h:34-61), the per-frame driver of the hot path:
+//   addImage -> processFrame (frame_handler_mono.cpp:129-245): SparseImgAlign::run -> Reprojector::reprojectMap ->
+//   pose_optimizer::optimizeGaussNewton -> optimizeStructure (Point::optimize) -> DepthFilter::addFrame / addKeyframe,
+// with the depth filter on a mapper thread that owns a second device context, as the reference's two threads do.
+// Outside the hot path and therefore the caller's job here: the two-view initialisation (KLT +
+// homography; setFirstFrame takes the keyframe that processSecondFrame would leave behind), relocalisation, bundle
+// adjustment and the keyframe-removal policy.
+// ------------------------------------------------------------------------------------------------
+struct FrameHandlerMonoOptions {  // svo/src/config.cpp:56-84 defaults
+  int n_pyr_levels = 3, klt_max_level = 4, klt_min_level = 2, grid_size = 30, max_fts = 120, quality_min_fts = 50,
+      quality_max_drop_fts = 40, poseoptim_num_iter = 10, structureoptim_max_pts = 20, structureoptim_num_iter = 5;
+  double poseoptim_thresh = 2.0, kfselect_mindist = 0.12, triang_min_corner_score = 20.0;
+  bool mapper_thread = true;
+};
+class FrameHandlerMono {
+ public:
+  enum Stage { STAGE_PAUSED, STAGE_FIRST_FRAME, STAGE_DEFAULT_FRAME };
+  enum UpdateResult { RESULT_NO_KEYFRAME, RESULT_IS_KEYFRAME, RESULT_FAILURE };
+  enum TrackingQuality { TRACKING_INSUFFICIENT, TRACKING_BAD, TRACKING_GOOD };
+  typedef FrameHandlerMonoOptions Options;
+  struct FrameLog { size_t img_align_n_tracked = 0, repr_n_matches = 0, repr_n_trials = 0, sfba_n_edges_final = 0; double sfba_error_init = 0, sfba_error_final = 0; };
+
+  FrameHandlerMono(AbstractCamera* cam, Options opt = Options(), int device = 0)
+      : cam_(cam), opt_(opt), tracking_ctx_(device), mapping_ctx_(device),
+        reprojector_(cam, map_, make_reprojector_options(opt)),
+        depth_filter_(feature_detection::DetectorPtr(new feature_detection::FastDetector(cam->width_, cam->height_, opt.grid_size, opt.n_pyr_levels)),
+                      std::bind(&MapPointCandidates::newCandidatePoint, &map_.point_candidates_, std::placeholders::_1, std::placeholders::_2)) {
+    depth_filter_.options_.max_search_level = opt.n_pyr_levels - 1;
+    depth_filter_.triang_min_corner_score_ = opt.triang_min_corner_score;
+    depth_filter_.setContext(&mapping_ctx_);
+    if (opt.mapper_thread) depth_filter_.startThread();
+  }
+  ~FrameHandlerMono() { depth_filter_.stopThread(); }
+  Context& trackingContext() { return tracking_ctx_; }
+  // The first keyframe, with its features and map points already attached (what the two-view initialisation produces).
+  void setFirstFrame(const FramePtr& first_frame) {
+    new_frame_ = first_frame;
+    new_frame_->setKeyframe();
+    double depth_mean = 0, depth_min = 0;
+    getSceneDepth(*new_frame_, depth_mean, depth_min);
+    for (Feature* f : new_frame_->fts_)
+      if (f->point && std::find(f->point->obs_.begin(), f->point->obs_.end(), f) == f->point->obs_.end()) f->point->addFrameRef(f);
+    depth_filter_.addKeyframe(new_frame_, depth_mean, 0.5 * depth_min);
+    map_.addKeyframe(new_frame_);
+    last_frame_ = new_frame_;
+    num_obs_last_ = last_frame_->nObs();
+    new_frame_.reset();
+    stage_ = STAGE_DEFAULT_FRAME;
+  }
+  // frame_handler_mono.cpp:62-86
+  UpdateResult addImage(const uint8_t* img, const double timestamp) {
+    if (stage_ != STAGE_DEFAULT_FRAME) return RESULT_FAILURE;
+    core_kfs_.clear();
+    overlap_kfs_.clear();
+    new_frame_.reset(new Frame(tracking_ctx_, cam_, img, std::max(opt_.n_pyr_levels, opt_.klt_max_level + 1), timestamp));
+    const UpdateResult res = processFrame();
+    last_frame_ = new_frame_;  // finishFrameProcessing (frame_handler_base.cpp:104-106)
+    new_frame_.reset();
+    num_obs_last_ = last_frame_->nObs();
+    return res;
+  }
+  FramePtr lastFrame() { return last_frame_; }
+  DepthFilter* depthFilter() { return &depth_filter_; }
+  Map& map() { return map_; }
+  const FrameLog& log() const { return log_; }
+  TrackingQuality trackingQuality() const { return tracking_quality_; }
+
+  static bool getSceneDepth(const Frame& frame, double& depth_mean, double& depth_min) {  // frame.cpp:167-188
+    std::vector<double> depth_vec;
+    depth_min = std::numeric_limits<double>::max();
+    const double* m = frame.T_f_w_.m;
+    for (Feature* f : frame.fts_) {
+      if (!f->point) continue;
+      const double z = m[8] * f->point->pos_[0] + m[9] * f->point->pos_[1] + m[10] * f->point->pos_[2] + m[11];
+      depth_vec.push_back(z);
+      depth_min = std::fmin(z, depth_min);
+    }
+    if (depth_vec.empty()) return false;
+    std::nth_element(depth_vec.begin(), depth_vec.begin() + depth_vec.size() / 2, depth_vec.end());  // vk::getMedian [EXT]
+    depth_mean = depth_vec[depth_vec.size() / 2];
+    return true;
+  }
+
+ protected:
+  static Reprojector::Options make_reprojector_options(const Options& o) {
+    Reprojector::Options r;
+    r.grid_size = o.grid_size; r.max_fts = o.max_fts; r.n_pyr_levels = o.n_pyr_levels;
+    return r;
+  }
+  // frame_handler_mono.cpp:129-245
+  UpdateResult processFrame() {
+    new_frame_->T_f_w_ = last_frame_->T_f_w_;  // set initial pose
+    SparseImgAlign img_align(opt_.klt_max_level, opt_.klt_min_level, 30, SparseImgAlign::GaussNewton, false, false);
+    log_ = FrameLog();
+    log_.img_align_n_tracked = img_align.run(last_frame_, new_frame_);
+    reprojector_.reprojectMap(new_frame_, overlap_kfs_);
+    log_.repr_n_matches = reprojector_.n_matches_;
+    log_.repr_n_trials = reprojector_.n_trials_;
+    if ((int)log_.repr_n_matches < opt_.quality_min_fts) {
+      new_frame_->T_f_w_ = last_frame_->T_f_w_;  // reset to avoid crazy pose jumps
+      tracking_quality_ = TRACKING_INSUFFICIENT;
+      return RESULT_FAILURE;
+    }
+    double sfba_thresh = 0;
+    pose_optimizer::optimizeGaussNewton(opt_.poseoptim_thresh, (size_t)opt_.poseoptim_num_iter, false, new_frame_, sfba_thresh,
+                                        log_.sfba_error_init, log_.sfba_error_final, log_.sfba_n_edges_final);
+    if (log_.sfba_n_edges_final < 20) return RESULT_FAILURE;
+    optimizeStructure(new_frame_, (size_t)opt_.structureoptim_max_pts, opt_.structureoptim_num_iter);
+    core_kfs_.insert(new_frame_);
+    setTrackingQuality(log_.sfba_n_edges_final);
+    if (tracking_quality_ == TRACKING_INSUFFICIENT) {
+      new_frame_->T_f_w_ = last_frame_->T_f_w_;
+      return RESULT_FAILURE;
+    }
+    double depth_mean = 0, depth_min = 0;
+    getSceneDepth(*new_frame_, depth_mean, depth_min);
+    if (!needNewKf(depth_mean) || tracking_quality_ == TRACKING_BAD) {
+      depth_filter_.addFrame(new_frame_);
+      return RESULT_NO_KEYFRAME;
+    }
+    new_frame_->setKeyframe();
+    for (Feature* f : new_frame_->fts_)
+      if (f->point) f->point->addFrameRef(f);
+    map_.point_candidates_.addCandidatePointToFrame(new_frame_);
+    depth_filter_.addKeyframe(new_frame_, depth_mean, 0.5 * depth_min);
+    map_.addKeyframe(new_frame_);
+    return RESULT_IS_KEYFRAME;
+  }
+  // frame_handler_base.cpp:157-171
+  void setTrackingQuality(const size_t num_observations) {
+    tracking_quality_ = TRACKING_GOOD;
+    if ((int)num_observations < opt_.quality_min_fts) tracking_quality_ = TRACKING_INSUFFICIENT;
+    const int feature_drop = (int)std::min(num_obs_last_, (size_t)opt_.max_fts) - (int)num_observations;
+    if (feature_drop > opt_.quality_max_drop_fts) tracking_quality_ = TRACKING_INSUFFICIENT;
+  }
+  // frame_handler_mono.cpp:304-315
+  bool needNewKf(double scene_depth_mean) {
+    for (auto& kf : overlap_kfs_) {
+      const Vector3d p = kf.first->pos();
+      const double* m = new_frame_->T_f_w_.m;
+      const double rx = m[0] * p[0] + m[1] * p[1] + m[2] * p[2] + m[3], ry = m[4] * p[0] + m[5] * p[1] + m[6] * p[2] + m[7],
+                   rz = m[8] * p[0] + m[9] * p[1] + m[10] * p[2] + m[11];
+      if (std::fabs(rx) / scene_depth_mean < opt_.kfselect_mindist && std::fabs(ry) / scene_depth_mean < opt_.kfselect_mindist * 0.8 &&
+          std::fabs(rz) / scene_depth_mean < opt_.kfselect_mindist * 1.3)
+        return false;
+    }
+    return true;
+  }
+  // frame_handler_base.cpp:178-196: Point::optimize on the points optimised longest ago, one batched device call
+  void optimizeStructure(FramePtr frame, size_t max_n_pts, int max_iter) {
+    std::vector<Point*> pts;
+    for (Feature* f : frame->fts_)
+      if (f->point) pts.push_back(f->point);
+    max_n_pts = std::min(max_n_pts, pts.size());
+    if (max_n_pts == 0) return;
+    std::nth_element(pts.begin(), pts.begin() + max_n_pts, pts.end(),
+                     [&](Point* a, Point* b) { return last_structure_optim_[a] < last_structure_optim_[b]; });
+    std::vector<int> obs_offset(1, 0), obs_frame;
+    std::vector<double> obs_f, frame_T, pos;
+    std::map<const Frame*, int> fidx;
+    for (size_t k = 0; k < max_n_pts; ++k) {
+      for (Feature* o : pts[k]->obs_) {
+        auto it = fidx.find(o->frame);
+        if (it == fidx.end()) {
+          it = fidx.emplace(o->frame, (int)fidx.size()).first;
+          frame_T.insert(frame_T.end(), o->frame->T_f_w_.m, o->frame->T_f_w_.m + 12);
+        }
+        obs_frame.push_back(it->second);
+        obs_f.insert(obs_f.end(), o->f.begin(), o->f.end());
+      }
+      obs_offset.push_back((int)obs_frame.size());
+      pos.insert(pos.end(), pts[k]->pos_.begin(), pts[k]->pos_.end());
+    }
+    if (obs_frame.empty()) return;
+    tracking_ctx_.check(svo_b200_point_optimize_batch(tracking_ctx_.get(), (int)max_n_pts, max_iter, obs_offset.data(), obs_frame.data(),
+                                                      obs_f.data(), frame_T.data(), (int)fidx.size(), pos.data()));
+    for (size_t k = 0; k < max_n_pts; ++k) {
+      for (int c = 0; c < 3; ++c) pts[k]->pos_[c] = pos[3 * k + c];
+      last_structure_optim_[pts[k]] = frame_counter_;
+    }
+    ++frame_counter_;
+  }
+
+  AbstractCamera* cam_;
+  Options opt_;
+  Context tracking_ctx_, mapping_ctx_;  // one device context per host thread (include/svo_b200.h)
+  Map map_;
+  Reprojector reprojector_;
+  DepthFilter depth_filter_;
+  FramePtr new_frame_, last_frame_;
+  std::set<FramePtr> core_kfs_;
+  std::vector<std::pair<FramePtr, size_t>> overlap_kfs_;
+  std::map<Point*, int> last_structure_optim_;
+  int frame_counter_ = 0;
+  size_t num_obs_last_ = 0;
+  Stage stage_ = STAGE_PAUSED;
+  TrackingQuality tracking_quality_ = TRACKING_INSUFFICIENT;
+  FrameLog log_;
 };
 
 }  // namespace svo
