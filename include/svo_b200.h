@@ -71,6 +71,9 @@ const char* svo_b200_last_error(const svo_b200_ctx* ctx);
 /* cudaStream_t of the context (for CUDA-event timing by the caller) */
 void* svo_b200_stream(svo_b200_ctx* ctx);
 int svo_b200_synchronize(svo_b200_ctx* ctx);
+/* device time (CUDA events on the context's stream) of the kernel launch(es) of the most recent entry point that
+ * launched any, excluding its host<->device copies; synchronises on that launch */
+int svo_b200_last_kernel_ms(svo_b200_ctx* ctx, float* ms_out);
 /* number of kernels this context has launched since creation */
 uint64_t svo_b200_launch_count(const svo_b200_ctx* ctx);
 const char* svo_b200_version(void);

@@ -432,6 +432,26 @@ def ref_image_pyramid(img, n_levels):
     return pyr
 
 
+def ref_last_seconds() -> float:
+    """Seconds the reference algorithm itself took inside the most recent ref_* call (setup / copies excluded)."""
+    L = ref_lib()
+    L.ref_last_seconds.restype = C.c_double
+    return float(L.ref_last_seconds())
+
+
+def ref_align2d_batch(level0, n_levels, level, pwb, patch, n_iter, px):
+    """feature_alignment::align2D of the compiled reference for M problems in one C loop."""
+    lv = np.ascontiguousarray(level, np.int32)
+    M = len(lv)
+    p = c64(px).copy().reshape(M, 2)
+    conv = np.zeros(M, np.uint8)
+    h, w = level0.shape
+    ref_lib().ref_align2d_batch(_p(np.ascontiguousarray(level0, np.uint8)), w, h, n_levels, M, _p(lv),
+                                _p(np.ascontiguousarray(pwb, np.uint8)), _p(np.ascontiguousarray(patch, np.uint8)), int(n_iter), _p(p),
+                                _p(conv))
+    return conv.astype(bool), p
+
+
 def ref_pose_optimize(reproj_thresh, n_iter, cam, T_f_w, f, pos, level, has_point):
     T = c64(T_f_w).copy().reshape(12)
     hp = np.ascontiguousarray(has_point, np.uint8).copy()

@@ -32,6 +32,14 @@ vk::AbstractCamera* ref_make_camera(int w, int h, const double* c) {
   return new vk::PinholeCamera(w, h, c[0], c[1], c[2], c[3], c[5], c[6], c[7], c[8], c[9]);
 }
 
+// wall-clock seconds of the reference algorithm inside the most recent ref_* call (object construction, pyramid building
+// and result copying excluded): what bench.py's CPU legs report
+double g_ref_last_seconds = 0.0;
+struct RefTimer {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  ~RefTimer() { g_ref_last_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
 namespace {
 SE3 se3_from12(const double* T) {
   Matrix3d R;
@@ -203,7 +211,7 @@ void ref_pose_optimize(double reproj_thresh, int n_iter, const double* cam4, int
   }
   double scale = 0, e_init = 0, e_final = 0;
   size_t num_obs = 0;
-  pose_optimizer::optimizeGaussNewton(reproj_thresh, (size_t)n_iter, false, fr, scale, e_init, e_final, num_obs);
+  { RefTimer tm; pose_optimizer::optimizeGaussNewton(reproj_thresh, (size_t)n_iter, false, fr, scale, e_init, e_final, num_obs); }
   se3_to12(fr->T_f_w_, T_f_w_io);
   int i = 0;
   for (auto it = fr->fts_.begin(); it != fr->fts_.end(); ++it, ++i) has_point_io[i] = (*it)->point != NULL;
@@ -272,6 +280,25 @@ int ref_align2d(const uint8_t* img, int cols, int rows, int step, uint8_t* pwb, 
   px_io[0] = px[0]; px_io[1] = px[1];
   return ok ? 1 : 0;
 }
+double ref_last_seconds() { return g_ref_last_seconds; }
+
+// M align2D calls in one C loop (no per-call FFI overhead): problem i runs on level[i] of the pyramid built from l0
+void ref_align2d_batch(const uint8_t* l0, int w, int h, int n_levels, int M, const int* level, const uint8_t* pwb, const uint8_t* patch,
+                       int n_iter, double* px_io, uint8_t* conv_out) {
+  vk::PinholeCamera cam(w, h, 300, 300, w / 2.0, h / 2.0);
+  const double I[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+  FramePtr fr = make_frame(&cam, l0, w, h, n_levels, I);
+  std::vector<uint8_t> a(100), b(64);
+  RefTimer tm;
+  for (int i = 0; i < M; ++i) {
+    std::memcpy(a.data(), pwb + 100 * (size_t)i, 100);
+    std::memcpy(b.data(), patch + 64 * (size_t)i, 64);
+    Eigen::Vector2d px(px_io[2 * i], px_io[2 * i + 1]);
+    conv_out[i] = svo::feature_alignment::align2D(fr->img_pyr_[level[i]], a.data(), b.data(), n_iter, px, true) ? 1 : 0;
+    px_io[2 * i] = px[0]; px_io[2 * i + 1] = px[1];
+  }
+}
+
 int ref_align1d(const uint8_t* img, int cols, int rows, int step, const float* dir, uint8_t* pwb, uint8_t* patch, int n_iter,
                 double* px_io, double* h_inv) {
   cv::Mat m(rows, cols, const_cast<uint8_t*>(img), (size_t)step);
@@ -316,7 +343,7 @@ void ref_depth_filter_update(const uint8_t* ref_l0s /*n_ref images*/, const doub
     df.getSeeds().push_back(s);
   }
   Seed::batch_counter = batch_counter;
-  df.update(cur);
+  { RefTimer tm; df.update(cur); }
   for (int i = 0; i < M; ++i) status_out[i] = 2;
   for (auto& s : df.getSeeds()) {
     const int i = s.id;
@@ -346,7 +373,7 @@ int ref_fast_detect(const uint8_t* l0, int w, int h, int n_levels, int n_pyr_lev
       for (int c = 0; c < n_cols; ++c)
         if (grid_occupancy[r * n_cols + c]) det.setGridOccpuancy(Vector2d(c * cell_size + 0.5, r * cell_size + 0.5));
   Features fts;
-  det.detect(fr.get(), fr->img_pyr_, detection_threshold, fts);
+  { RefTimer tm; det.detect(fr.get(), fr->img_pyr_, detection_threshold, fts); }
   int n = 0;
   for (Feature* f : fts) {
     if (n < cap) { out_x[n] = (int)f->px[0]; out_y[n] = (int)f->px[1]; out_level[n] = f->level; }

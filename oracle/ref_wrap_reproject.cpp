@@ -12,6 +12,7 @@
 #undef private
 #include <vikit/abstract_camera.h>
 
+#include <chrono>
 #include <map>
 #include <memory>
 #include <set>
@@ -20,6 +21,7 @@
 #include "svo_oracle.h"
 
 vk::AbstractCamera* ref_make_camera(int w, int h, const double* c);  // oracle/ref_wrap.cpp
+extern double g_ref_last_seconds;                                       // oracle/ref_wrap.cpp
 
 using namespace svo;
 
@@ -104,7 +106,11 @@ extern "C" void ref_reproject_map(const orc_map_view* m, const uint8_t* kf_l0s /
     rp.options_.find_match_direct = opt->find_match_direct != 0;
     for (size_t i = 0; i < rp.grid_.cell_order.size(); ++i) rp.grid_.cell_order[i] = cell_order[i];
     std::vector<std::pair<FramePtr, size_t>> overlap;
-    rp.reprojectMap(cur, overlap);
+    {
+      const auto t0 = std::chrono::steady_clock::now();
+      rp.reprojectMap(cur, overlap);
+      g_ref_last_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
 
     memset(st, 0, sizeof(*st));
     st->n_matches = (int64_t)rp.n_matches_;

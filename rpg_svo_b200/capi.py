@@ -215,6 +215,12 @@ class Context:
     def synchronize(self):
         self._check(self.lib.svo_b200_synchronize(self.h))
 
+    def last_kernel_ms(self) -> float:
+        """Device time of the kernel(s) of the last entry point (CUDA events inside the library, no copies)."""
+        ms = C.c_float(0)
+        self._check(self.lib.svo_b200_last_kernel_ms(self.h, C.byref(ms)))
+        return float(ms.value)
+
     def launch_count(self) -> int:
         return int(self.lib.svo_b200_launch_count(self.h))
 

@@ -121,11 +121,13 @@ static int align_batch(svo_b200_ctx* ctx, const svo_b200_frame* cur, int M, cons
   memcpy(h + o_px, px_io, sizeof(double) * 2 * M);
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
   const int blocks = (M + kWarpsPerCta - 1) / kWarpsPerCta;
+  kt_begin(ctx);
   align_batch_kernel<<<blocks, kWarpsPerCta * 32, 0, ctx->stream>>>(
       make_desc(cur), M, reinterpret_cast<const int*>(d + o_lvl), dir ? reinterpret_cast<const float*>(d + o_dir) : nullptr,
       d + o_pwb, d + o_pat, n_iter, reinterpret_cast<double*>(d + o_px), d + o_conv,
       h_inv_out ? reinterpret_cast<double*>(d + o_h) : nullptr);
   ctx->launches++;
+  kt_end(ctx);
   SVO_CUDA_CHECK(ctx, cudaGetLastError());
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(h + o_px, d + o_px, c.off - o_px, cudaMemcpyDeviceToHost, ctx->stream));
   SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -213,9 +215,11 @@ int svo_b200_find_match_direct(svo_b200_ctx* ctx, const svo_b200_frame* const* r
   Cam cm;
   { const int rc_cam = cam_to_dev(ctx, cam, cm); if (rc_cam) return rc_cam; }
   const int blocks = (M + kWarpsPerCta - 1) / kWarpsPerCta;
+  kt_begin(ctx);
   find_match_direct_kernel<<<blocks, kWarpsPerCta * 32, 0, ctx->stream>>>(
       make_desc(cur), cm, M, in, out, opt->max_search_level, opt->align_max_iter, reinterpret_cast<const double*>(d + o_cT));
   ctx->launches++;
+  kt_end(ctx);
   SVO_CUDA_CHECK(ctx, cudaGetLastError());
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(h + o_pc, d + o_pc, c.off - o_pc, cudaMemcpyDeviceToHost, ctx->stream));
   SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

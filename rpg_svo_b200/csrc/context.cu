@@ -237,7 +237,8 @@ static inline int pyr_avg(const svo_b200_ctx* ctx, int src_w) {
   return ctx->pyramid_rule == SVO_B200_PYR_X86 && (src_w % 16) == 0;
 }
 
-static int build_levels(svo_b200_ctx* ctx, svo_b200_frame* fr, int from_level) {
+static int build_levels(svo_b200_ctx* ctx, svo_b200_frame* fr, int from_level, bool timed = true) {
+  if (timed) kt_begin(ctx);
   for (int l = from_level; l < fr->n_levels; ++l) {
     const int total = ((fr->w[l] + 3) / 4) * fr->h[l];
     if (total <= 0) continue;
@@ -248,6 +249,7 @@ static int build_levels(svo_b200_ctx* ctx, svo_b200_frame* fr, int from_level) {
                                                             fr->lvl(l), fr->w[l], fr->h[l], pyr_avg(ctx, fr->w[l - 1]));
     ctx->launches++;
   }
+  if (timed) kt_end(ctx);
   SVO_CUDA_CHECK(ctx, cudaGetLastError());
   return 0;
 }
@@ -257,6 +259,14 @@ static int build_levels(svo_b200_ctx* ctx, svo_b200_frame* fr, int from_level) {
 using namespace svo;
 
 extern "C" {
+
+int svo_b200_last_kernel_ms(svo_b200_ctx* ctx, float* ms_out) {
+  if (!ctx || !ms_out) return SVO_B200_EINVAL;
+  cudaSetDevice(ctx->device);
+  SVO_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->ev_k1));
+  SVO_CUDA_CHECK(ctx, cudaEventElapsedTime(ms_out, ctx->ev_k0, ctx->ev_k1));
+  return 0;
+}
 
 int svo_b200_set_pyramid_rule(svo_b200_ctx* ctx, int rule) {
   if (!ctx) return SVO_B200_EINVAL;
@@ -286,6 +296,8 @@ int svo_b200_create(svo_b200_ctx** ctx_out, int device) {
     delete ctx;
     return SVO_B200_ECUDA;
   }
+  cudaEventCreate(&ctx->ev_k0);
+  cudaEventCreate(&ctx->ev_k1);
   cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaDeviceGetAttribute(&ctx->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   *ctx_out = ctx;
@@ -302,6 +314,8 @@ void svo_b200_destroy(svo_b200_ctx* ctx) {
   if (ctx->d_scratch.p) cudaFree(ctx->d_scratch.p);
   if (ctx->h_in.p) cudaFreeHost(ctx->h_in.p);
   if (ctx->h_out.p) cudaFreeHost(ctx->h_out.p);
+  if (ctx->ev_k0) cudaEventDestroy(ctx->ev_k0);
+  if (ctx->ev_k1) cudaEventDestroy(ctx->ev_k1);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -451,6 +465,7 @@ int svo_b200_frame_pool_upload(svo_b200_ctx* ctx, svo_b200_frame_pool* pool, int
     // level 1 with the fused tile kernel (base level shifted by one); otherwise everything from level 0.
     const bool stream01 = (f0.w[0] % 16) == 0;
     const int base = stream01 ? 1 : 0;
+    kt_begin(ctx);
     if (stream01) {
       const int blocks = ctx->sm_count * 8;
       pyramid_l0_l1_stream_kernel<<<blocks, 256, 0, ctx->stream>>>(pool->slab[0], pool->stride[0], pool->slab[1],
@@ -479,9 +494,10 @@ int svo_b200_frame_pool_upload(svo_b200_ctx* ctx, svo_b200_frame_pool* pool, int
     }
     SVO_CUDA_CHECK(ctx, cudaGetLastError());
     for (int i = 0; i < count && f0.n_levels > base + 5; ++i) {  // deeper levels: plain per-level kernel
-      int rc = build_levels(ctx, &pool->frames[first + i], base + 5);
+      int rc = build_levels(ctx, &pool->frames[first + i], base + 5, false);
       if (rc) return rc;
     }
+    kt_end(ctx);
   }
   return 0;
 }

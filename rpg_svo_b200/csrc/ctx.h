@@ -56,6 +56,7 @@ struct svo_b200_ctx {
   DevBuf d_in, d_out, d_scratch;
   HostBuf h_in, h_out;
   svo::SiaBatchState* sia = nullptr;
+  cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the kernel(s) of the last entry point (svo_b200_last_kernel_ms)
   int pyramid_rule = SVO_B200_PYR_X86;  // svo_b200_set_pyramid_rule
   int sia_cluster = -1;  // svo_b200_sia_config: CTAs per pair (-1 = by batch size)
   int sia_fpt = 0;       //                      features per thread (0 = automatic)
@@ -87,6 +88,10 @@ struct Carver {
 };
 
 void sia_batch_free(svo_b200_ctx* ctx);
+// CUDA events on the context's stream bracketing the kernel launch(es) of an entry point (no copies): the live
+// per-kernel device time bench.py's roofline figures divide by
+inline void kt_begin(svo_b200_ctx* ctx) { if (ctx->ev_k0) cudaEventRecord(ctx->ev_k0, ctx->stream); }
+inline void kt_end(svo_b200_ctx* ctx) { if (ctx->ev_k1) cudaEventRecord(ctx->ev_k1, ctx->stream); }
 
 // Device-side camera ([EXT] vk::PinholeCamera / vk::ATANCamera): the C-ABI parameters plus the derived constants
 // the vikit constructors precompute.  Passed by value inside kernel parameter structs.

@@ -127,7 +127,7 @@ __device__ inline double compute_tau(const Pose& T_ref_cur, const double* f, dou
   return z_plus - z;
 }
 
-__global__ void __launch_bounds__(kDfWarps * 32) depth_filter_kernel(const DepthParams P) {
+__global__ void __launch_bounds__(kDfWarps * 32, 4) depth_filter_kernel(const DepthParams P) {  // <= 128 registers: the 500 CTAs of C2 (2000 seeds) are resident at once
   __shared__ WarpAlignScratch scratch[kDfWarps];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = blockIdx.x * kDfWarps + warp;
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(kDfWarps * 32) depth_filter_kernel(const Depth
       ImgView ref_img = {rf.lvl[lvl], rf.w[lvl], rf.h[lvl]};
       warp_warp_affine(Aff, ref_img, pxu, pxv, lvl, L, S);
       ImgView cur_img = {P.cur.lvl[L], P.cur.w[L], P.cur.h[L]};
-      const double sc = (double)(1 << L);
+      const double sc = (double)(1 << L), inv_sc = 1.0 / sc;  // a power of two: x * inv_sc == x / sc exactly
       bool have_start = false;
       double start_u = 0, start_v = 0;
       if (epi_length < 2.0) {  // :226-246
@@ -237,13 +237,13 @@ __global__ void __launch_bounds__(kDfWarps * 32) depth_filter_kernel(const Depth
             const double uk = fma((double)k, step_x, u0), vk = fma((double)k, step_y, v0);
             double wu, wv;
             cam_world2cam(cam, uk, vk, wu, wv);  // cam_->world2cam(uv)  (:272)
-            const int qx = (int)(wu / sc + 0.5), qy = (int)(wv / sc + 0.5);
+            const int qx = (int)(wu * inv_sc + 0.5), qy = (int)(wv * inv_sc + 0.5);
             int px_prev = 0, py_prev = 0;  // last_checked_pxi starts at (0,0)
             if (k > 0) {
               const double up = fma((double)(k - 1), step_x, u0), vp = fma((double)(k - 1), step_y, v0);
               cam_world2cam(cam, up, vp, wu, wv);
-              px_prev = (int)(wu / sc + 0.5);
-              py_prev = (int)(wv / sc + 0.5);
+              px_prev = (int)(wu * inv_sc + 0.5);
+              py_prev = (int)(wv * inv_sc + 0.5);
             }
             if (qx == px_prev && qy == py_prev) continue;                 // :273-275
             if (!(qx >= 8 && qx < lim_x && qy >= 8 && qy < lim_y)) continue;  // isInFrame(pxi, 8, level)
@@ -409,8 +409,10 @@ extern "C" int svo_b200_depth_filter_update(svo_b200_ctx* ctx, const svo_b200_fr
   P.z = reinterpret_cast<double*>(d + o_z);
   P.n_zmssd = reinterpret_cast<int*>(d + o_nz);
   const int blocks = (M + kDfWarps - 1) / kDfWarps;
+  kt_begin(ctx);
   depth_filter_kernel<<<blocks, kDfWarps * 32, 0, ctx->stream>>>(P);
   ctx->launches++;
+  kt_end(ctx);
   SVO_CUDA_CHECK(ctx, cudaGetLastError());
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(h + o_a, d + o_a, c.off - o_a, cudaMemcpyDeviceToHost, ctx->stream));
   SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -511,8 +513,10 @@ extern "C" int svo_b200_find_epipolar_match_direct(svo_b200_ctx* ctx, const svo_
   P.reject_out = d + o_rj;
   P.A_out = reinterpret_cast<double*>(d + o_A);
   const int blocks = (M + kDfWarps - 1) / kDfWarps;
+  kt_begin(ctx);
   depth_filter_kernel<<<blocks, kDfWarps * 32, 0, ctx->stream>>>(P);
   ctx->launches++;
+  kt_end(ctx);
   SVO_CUDA_CHECK(ctx, cudaGetLastError());
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(h + o_st, d + o_st, c.off - o_st, cudaMemcpyDeviceToHost, ctx->stream));
   SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

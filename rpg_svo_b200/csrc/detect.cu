@@ -186,10 +186,12 @@ extern "C" int svo_b200_fast_detect(svo_b200_ctx* ctx, const svo_b200_frame* fra
   for (int k = 0; k < n_cells; ++k) reinterpret_cast<unsigned long long*>(h + o_cells)[k] = init;
   if (grid_occupancy) std::memcpy(h + o_occ, grid_occupancy, n_cells);
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(d, h, c.off, cudaMemcpyHostToDevice, ctx->stream));
+  kt_begin(ctx);
   fast_detect_kernel<<<lv.tile_base[lv.n_levels], 256, 0, ctx->stream>>>(
       lv, opt->fast_threshold, opt->nonmax_ties_suppress, opt->cell_size, grid_n_cols, grid_occupancy ? d + o_occ : nullptr,
       reinterpret_cast<unsigned long long*>(d + o_cells));
   ctx->launches++;
+  kt_end(ctx);
   SVO_CUDA_CHECK(ctx, cudaGetLastError());
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(h + o_cells, d + o_cells, sizeof(unsigned long long) * n_cells, cudaMemcpyDeviceToHost, ctx->stream));
   SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -490,8 +490,10 @@ extern "C" int svo_b200_pose_optimize_batch(svo_b200_ctx* ctx, int B, double rep
   P.T_io = reinterpret_cast<double*>(d + o_T);
   P.out = reinterpret_cast<svo_b200_pose_opt_result*>(d + o_out);
   SVO_CUDA_CHECK(ctx, cudaFuncSetAttribute(pose_opt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kt_begin(ctx);
   pose_opt_kernel<<<B, kPoThreads, smem, ctx->stream>>>(P);
   ctx->launches++;
+  kt_end(ctx);
   SVO_CUDA_CHECK(ctx, cudaGetLastError());
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(h, d, io_end, cudaMemcpyDeviceToHost, ctx->stream));
   SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -634,12 +636,14 @@ extern "C" int svo_b200_point_optimize_batch(svo_b200_ctx* ctx, int P, int n_ite
   memcpy(h + o_T, frame_T_f_w, sizeof(double) * 12 * n_frames);
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(d, h, c.off, cudaMemcpyHostToDevice, ctx->stream));
   const int threads = 128, blocks = (P + threads - 1) / threads;
+  kt_begin(ctx);
   point_optimize_kernel<<<blocks, threads, 0, ctx->stream>>>(P, n_iter, reinterpret_cast<const int*>(d + o_off),
                                                              reinterpret_cast<const int*>(d + o_fr),
                                                              reinterpret_cast<const double*>(d + o_f),
                                                              reinterpret_cast<const double*>(d + o_T),
                                                              reinterpret_cast<double*>(d + o_pos));
   ctx->launches++;
+  kt_end(ctx);
   SVO_CUDA_CHECK(ctx, cudaGetLastError());
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(h + o_pos, d + o_pos, io_end - o_pos, cudaMemcpyDeviceToHost, ctx->stream));
   SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

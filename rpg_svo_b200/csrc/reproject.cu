@@ -266,10 +266,12 @@ extern "C" int svo_b200_reproject_map(svo_b200_ctx* ctx, const svo_b200_map_view
                    reinterpret_cast<double*>(d + o_pm), reinterpret_cast<int*>(d + o_sl), reinterpret_cast<double*>(d + o_A),
                    reinterpret_cast<int*>(d + o_rf)};
   const int blocks = (E + kRpWarps - 1) / kRpWarps;
+  kt_begin(ctx);
   reproject_match_kernel<<<blocks, kRpWarps * 32, sizeof(double) * 3 * m->n_kfs, ctx->stream>>>(
       make_desc(cur), cm, E, m->n_kfs, in, out, reinterpret_cast<const double*>(d + o_cT), cell_size, grid_n_cols,
       opt->find_match_direct, opt->max_search_level, opt->align_max_iter);
   ctx->launches++;
+  kt_end(ctx);
   SVO_CUDA_CHECK(ctx, cudaGetLastError());
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(h + o_px, d + o_px, c.off - o_px, cudaMemcpyDeviceToHost, ctx->stream));
   SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -1105,7 +1105,9 @@ static int launch_sia(svo_b200_ctx* ctx, const SiaParams& P, int B, int threads,
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = cluster > 1 ? 1 : 0;
+    kt_begin(ctx);
     SVO_CUDA_CHECK(ctx, cudaLaunchKernelEx(&cfg, kern, P));
+    kt_end(ctx);
     ctx->launches++;
     SVO_CUDA_CHECK(ctx, cudaGetLastError());
     return 0;

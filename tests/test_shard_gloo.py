@@ -1,11 +1,10 @@
-"""CPU, world_size 2, gloo: the N>1 path of the benchmark (independent units sharded over ranks, no
-data-path collective; barrier + max-over-ranks timing)."""
+"""CPU, world_size 2, gloo: the N>1 path of the benchmark.  bench.py's rank logic lives in rpg_svo_b200.shard.RankGroup
+(rank / seed assignment, barrier, max-over-ranks timing, whole-job throughput, NUMA binding helpers); this test drives that
+same class with the gloo backend -- independent units sharded over ranks, no data-path collective."""
 import os
 import socket
 
 import pytest
-import torch
-import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from rpg_svo_b200 import shard
@@ -25,19 +24,18 @@ def test_shard_range_covers_everything_once():
 
 
 def _worker(rank, world, port, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    b, e = shard.shard_range(256, rank, world)          # BASELINE config C4: 256 pairs over the ranks
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world))
+    grp = shard.RankGroup("gloo")                        # what bench.py builds with "nccl"
+    assert (grp.rank, grp.world) == (rank, world)
     my_ms = 10.0 + 5.0 * rank                            # pretend device time of this rank
-    dist.barrier()
-    worst = shard.max_over_ranks(my_ms, dist)
-    counts = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
-    dist.all_gather(counts, torch.tensor([e - b]))
-    q.put((rank, worst, int(sum(c.item() for c in counts)), shard.stream_seed(rank)))
-    dist.destroy_process_group()
+    grp.barrier()
+    worst = grp.max_over_ranks(my_ms)
+    value = grp.throughput(32, my_ms * 1e-3)             # BASELINE configs[4]: 32 pairs per rank, weak scaling
+    q.put((rank, worst, value, grp.seed))
+    grp.close()
 
 
-def test_two_rank_gloo_sharding_and_timing():
+def test_two_rank_gloo_timing_and_throughput():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
@@ -50,7 +48,24 @@ def test_two_rank_gloo_sharding_and_timing():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    assert [r[1] for r in res] == [15.0, 15.0]           # every rank sees the max
-    assert [r[2] for r in res] == [256, 256]             # all units owned exactly once
-    assert [r[3] for r in res] == [1000, 1001]           # one synthetic stream per rank
-    assert shard.aggregate_throughput(128, 2, 0.015) == pytest.approx(256 / 0.015)
+    assert [r[1] for r in res] == [15.0, 15.0]                       # every rank sees the max
+    assert [r[2] for r in res] == [pytest.approx(64 / 0.015)] * 2    # all ranks' units over the slowest rank's time
+    assert [r[3] for r in res] == [1000, 1001]                       # one synthetic stream per rank
+
+
+def test_single_process_group_is_the_identity():
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE"):
+        os.environ.pop(k, None)
+    grp = shard.RankGroup("gloo")
+    assert (grp.rank, grp.world, grp.seed) == (0, 1, 1000)
+    grp.barrier()
+    assert grp.max_over_ranks(3.5) == 3.5 and grp.throughput(100, 0.5) == 200.0
+    grp.close()
+
+
+def test_host_limits_and_numa_helpers():
+    lim = shard.host_cpu_limits()
+    assert lim["affinity"] >= 1 and 1 <= shard.usable_threads() <= lim["affinity"]
+    assert shard._parse_cpulist("0-3,8,10-11") == [0, 1, 2, 3, 8, 10, 11]
+    assert shard.numa_node_of_gpu("0000:ff:1f.0") in (None, 0, 1, 2, 3)   # unknown device -> None
+    assert shard.bind_to_numa_node(None) == {"numa_node": None, "bound": False}
