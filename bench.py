@@ -301,7 +301,7 @@ def measure_latency_and_c4(ctx, capi, torch, stream, inp, host_l0, pool) -> dict
     return out
 
 
-def measure_kernels(ctx, capi, peak_gbs: float) -> dict:
+def measure_kernels(ctx, capi, peak_gbs: float, quick: bool = False) -> dict:
     """Every kernel of the path at its BASELINE config through the C ABI, next to oracle/_ref on one host thread (algorithm
     time only, no per-item FFI): live device time from the library's CUDA events -> achieved GB/s on the algorithmic bytes of
     SURVEY.md 8d -> fraction of the measured HBM peak.  `e2e_ms` = the whole ABI call with host buffers."""
@@ -316,7 +316,10 @@ def measure_kernels(ctx, capi, peak_gbs: float) -> dict:
     out = {}
 
     def timed(fn, reps):
-        fn(); fn()
+        if quick:  # one launch per kernel: the ncu capture list of scripts/profile_kernels.sh
+            reps = 1
+        else:
+            fn(); fn()
         ks, t0 = [], time.perf_counter()
         for _ in range(reps):
             fn()

@@ -409,6 +409,11 @@ enum { kModeGlobal = 0, kModeImage = 1, kModeWindow = 2 };
 
 // One CTA (CS == 1) or one cluster of CS CTAs per frame pair; the pair's features are dealt to the CTAs in
 // contiguous blocks of S = MAXT*FPT slots.
+// (__launch_bounds__(160, 3) yields 128 registers although 3 x 160 x 136 <= 64 K: the register file is split over the
+// four SM sub-partitions, 15 warps put 4 on one of them, and 4 warps x 32 lanes x 136 > 16 K.  Measured: forcing 136 with
+// __maxnreg__ drops the kernel to two CTAs per SM and costs 20 % throughput.  Also measured and not kept: laying the
+// two-feature residual pass out phase by phase for instruction-level parallelism (no change), and issuing both features'
+// reference-footprint loads before computing either patch (-5 %: the extra live registers spill).)
 template <int FPT, bool EVAL, int MAXT, int MINB, int CS>
 __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -7,5 +7,5 @@ import bench
 from rpg_svo_b200 import capi
 
 ctx = capi.Context(0)
-out = bench.measure_kernels(ctx, capi, 6570.9)
+out = bench.measure_kernels(ctx, capi, 6570.9, quick="--quick" in sys.argv)
 print(json.dumps({k: v["kernel_ms"] for k, v in out.items()}))
