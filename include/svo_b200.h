@@ -176,6 +176,23 @@ int svo_b200_sia_batch_fetch(svo_b200_ctx* ctx, double* T_out /*B*12*/, uint8_t*
  *   features_per_thread: 0 = automatic, 1, 2 (one CTA per pair only). */
 int svo_b200_sia_config(svo_b200_ctx* ctx, int ctas_per_pair, int features_per_thread);
 
+/* ---- one stream's features split over several GPUs (a demonstration mode: a pair fits one GPU) ----
+ * Every rank (one process or thread per GPU) holds both pyramids and passes ITS contiguous slice of the pair's features
+ * to svo_b200_sparse_img_align / svo_b200_sia_batch_*; the kernels of the ranks exchange the per-iteration sums
+ * (6 Jres + chi2 + counts, and the 21 H entries once per level) directly through peer memory over NVLink -- no host
+ * round trip, no collective-library call inside the Gauss-Newton loop -- and all ranks finish with the same pose, H and
+ * n_tracked; the visibility mask covers the rank's slice.  All ranks must issue the same sequence of alignment calls.
+ *   create   allocates this rank's exchange buffer (max_pairs pairs per launch) and returns its CUDA IPC handle
+ *            (SVO_B200_IPC_HANDLE_BYTES bytes) and / or its device pointer;
+ *   connect  maps the peers: `ipc_handles` = world handles in rank order (other processes; all-gather them with the
+ *            launcher's own means), or `in_process_ptrs` = world device pointers (ranks that share the process).
+ *            Every rank must have connected before any rank launches (launcher barrier);
+ *   destroy  unmaps / frees.  An exchange a peer never joins times out after ~2 s: the next fetch returns SVO_B200_ECUDA. */
+#define SVO_B200_IPC_HANDLE_BYTES 64
+int svo_b200_sia_split_create(svo_b200_ctx* ctx, int rank, int world, int max_pairs, void* ipc_handle_out, void** local_ptr_out);
+int svo_b200_sia_split_connect(svo_b200_ctx* ctx, const void* ipc_handles, void* const* in_process_ptrs);
+int svo_b200_sia_split_destroy(svo_b200_ctx* ctx);
+
 /* computeResiduals(model, linearize=true) at one level and pose, exposing the caches; visible_io
  * carries the set-only visibility flags in and out. */
 int svo_b200_sparse_residuals(svo_b200_ctx* ctx, const svo_b200_frame* ref, const svo_b200_frame* cur,

@@ -279,6 +279,27 @@ class Context:
         """1 = PYR_X86 (vikit's SSE2 rounding where an x86 build of the reference takes it; default), 0 = PYR_SCALAR."""
         self._check(self.lib.svo_b200_set_pyramid_rule(self.h, int(rule)))
 
+    # ---- feature split of single pairs over GPUs (svo_b200_sia_split_*)
+    def sia_split_create(self, rank: int, world: int, max_pairs: int = 1):
+        """Returns (ipc_handle: bytes[64], device_ptr: int) of this rank's exchange buffer."""
+        h = (C.c_ubyte * 64)()
+        ptr = C.c_void_p()
+        self._check(self.lib.svo_b200_sia_split_create(self.h, int(rank), int(world), int(max_pairs), h, C.byref(ptr)))
+        return bytes(h), int(ptr.value)
+
+    def sia_split_connect(self, ipc_handles=None, in_process_ptrs=None):
+        """ipc_handles: list of `world` 64-byte handles (other processes) or in_process_ptrs: list of `world` device pointers."""
+        if in_process_ptrs is not None:
+            arr = (C.c_void_p * len(in_process_ptrs))(*[C.c_void_p(p) for p in in_process_ptrs])
+            self._check(self.lib.svo_b200_sia_split_connect(self.h, None, arr))
+        else:
+            blob = b"".join(ipc_handles)
+            buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+            self._check(self.lib.svo_b200_sia_split_connect(self.h, buf, None))
+
+    def sia_split_destroy(self):
+        self._check(self.lib.svo_b200_sia_split_destroy(self.h))
+
     def sia_config(self, ctas_per_pair=-1, features_per_thread=0):
         """Launch geometry of the alignment kernel (svo_b200_sia_config): -1 / 0 = automatic."""
         self._check(self.lib.svo_b200_sia_config(self.h, int(ctas_per_pair), int(features_per_thread)))

@@ -309,6 +309,7 @@ void svo_b200_destroy(svo_b200_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   sia_batch_free(ctx);
+  sia_split_free(ctx);
   if (ctx->d_in.p) cudaFree(ctx->d_in.p);
   if (ctx->d_out.p) cudaFree(ctx->d_out.p);
   if (ctx->d_scratch.p) cudaFree(ctx->d_scratch.p);

@@ -58,6 +58,12 @@ struct svo_b200_ctx {
   svo::SiaBatchState* sia = nullptr;
   cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the kernel(s) of the last entry point (svo_b200_last_kernel_ms)
   int pyramid_rule = SVO_B200_PYR_X86;  // svo_b200_set_pyramid_rule
+  // feature split of single pairs over GPUs (svo_b200_sia_split_*): exchange buffers in peer memory
+  int xg_rank = 0, xg_world = 1, xg_pairs = 0;
+  bool xg_connected = false;
+  void* xg_buf = nullptr;      // our exchange buffer
+  void* xg_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // rank r's buffer as mapped here
+  bool xg_peer_ipc[8] = {false, false, false, false, false, false, false, false};
   int sia_cluster = -1;  // svo_b200_sia_config: CTAs per pair (-1 = by batch size)
   int sia_fpt = 0;       //                      features per thread (0 = automatic)
 };
@@ -88,6 +94,7 @@ struct Carver {
 };
 
 void sia_batch_free(svo_b200_ctx* ctx);
+void sia_split_free(svo_b200_ctx* ctx);
 // CUDA events on the context's stream bracketing the kernel launch(es) of an entry point (no copies): the live
 // per-kernel device time bench.py's roofline figures divide by
 inline void kt_begin(svo_b200_ctx* ctx) { if (ctx->ev_k0) cudaEventRecord(ctx->ev_k0, ctx->stream); }

@@ -30,6 +30,7 @@
 //     in all lanes), so the new pose never has to be published through shared memory.
 // Precision follows the reference per quantity: f32 interpolation/residual/chi2, f64 geometry and
 // normal equations.
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -65,8 +66,30 @@ struct SiaJob {  // one frame pair; array lives in device memory
   double ref_pos[3];
 };
 
+// ---- single-stream feature split over GPUs: the per-iteration sums of one pair are exchanged between the
+// ranks' kernels through peer memory (NVLink P2P stores into every rank's exchange buffer, system-scope flags), so the
+// whole coarse-to-fine loop still runs inside ONE kernel per GPU -- no host round trip, no collective library call.
+constexpr int kMaxSplit = 8;
+struct XgSlot {  // what one rank publishes for one exchange
+  double v[kPartK];
+  int cnt[2];
+  unsigned seq;  // sequence number of the exchange this slot holds (written last, release)
+  unsigned pad_;
+};
+struct XgPair {  // per frame pair, in every rank's exchange buffer
+  XgSlot slot[2][kMaxSplit];  // [parity of the exchange][publishing rank]
+  unsigned xseq;              // exchanges completed so far (persists across launches; identical on all ranks)
+  unsigned err;               // sticky: a peer did not arrive within the timeout
+  unsigned pad_[2];
+};
+struct XgParams {
+  int rank, world;
+  XgPair* peer[kMaxSplit];  // rank r's exchange buffer as mapped in this process (peer[rank] = our own)
+};
+
 struct SiaParams {
   const SiaJob* jobs;
+  XgParams xg;
   int w[SVO_B200_MAX_LEVELS], h[SVO_B200_MAX_LEVELS];
   CamDev cam;
   int max_level, min_level, n_iter;
@@ -116,6 +139,8 @@ struct SiaSharedT {
   SiaState st[2];                               // double-buffered like `part`
   int h_is_tot, n_iters, sum_vis, sum_in, n_in_last, n_trace;  // thread 0 of CTA rank 0 only
   unsigned mbar_phase;
+  unsigned xg_seq;     // feature split over GPUs: exchanges completed (warp 0) ...
+  unsigned xg_failed;  // ... and "an exchange timed out" (must directly follow xg_seq)
   double pub[12];      // CS == 1: the pose (R row-major, t) warp 0 publishes after its Gauss-Newton tail
   int pub_done, pub_slow;
 #if SVO_SIA_DEBUG
@@ -215,6 +240,61 @@ __device__ __forceinline__ void st_cluster_v2s32(int* local_ptr, unsigned rank, 
   asm volatile("st.shared::cluster.v2.s32 [%0], {%1, %2};" ::"r"(remote), "r"(a), "r"(b) : "memory");
 }
 
+// ---- system-scope accesses to (peer) global memory
+__device__ __forceinline__ void st_sys_f64(double* p, double v) { asm volatile("st.relaxed.sys.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory"); }
+__device__ __forceinline__ void st_sys_s32(int* p, int v) { asm volatile("st.relaxed.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_release_sys_u32(unsigned* p, unsigned v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) { unsigned v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ double ld_sys_f64(const double* p) { double v; asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory"); return v; }
+__device__ __forceinline__ int ld_sys_s32(const int* p) { int v; asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+
+// All-reduce (sum) of K <= 24 doubles + two counts of one pair over the ranks of a feature split, executed by ONE warp of
+// the pair's CTA on every rank: lane k holds value k.  Every rank stores its values into slot [parity][rank] of EVERY
+// rank's exchange buffer (peer memory), then its sequence number (release); it then waits until all slots of its own
+// buffer carry that number (acquire) and adds them in rank order, so all ranks obtain bit-identical sums.  A slot is
+// rewritten two exchanges later, by which time every peer has consumed it (a rank cannot run more than one exchange
+// ahead).  A peer that never arrives trips a ~2 s timeout: the sticky error flag is set and the kernel finishes with
+// meaningless numbers instead of hanging the GPU.
+template <int K>
+__device__ __forceinline__ void xg_allreduce(const XgParams& X, int pair, unsigned* seq_smem, double& val, int& c0, int& c1) {
+  const int lane = threadIdx.x & 31;
+  const unsigned failed = seq_smem[1];  // a previous exchange of this launch already timed out: do not wait again
+  const unsigned xseq = *seq_smem;
+  const unsigned par = xseq & 1u, want = xseq + 1u;
+  for (int r = 0; r < X.world; ++r) {
+    XgSlot* dst = &X.peer[r][pair].slot[par][X.rank];
+    if (lane < K) st_sys_f64(&dst->v[lane], val);
+    if (lane == 0) { st_sys_s32(&dst->cnt[0], c0); st_sys_s32(&dst->cnt[1], c1); }
+  }
+  __threadfence_system();
+  __syncwarp();
+  if (lane == 0)
+    for (int r = 0; r < X.world; ++r) st_release_sys_u32(&X.peer[r][pair].slot[par][X.rank].seq, want);
+  XgPair* own = &X.peer[X.rank][pair];
+  bool ok = true;
+  if (lane < X.world && !failed) {
+    const long long t0 = clock64();
+    while (ld_acquire_sys_u32(&own->slot[par][lane].seq) != want) {
+      if (clock64() - t0 > 4000000000LL) { ok = false; break; }
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
+  __threadfence_system();
+  double acc = 0.0;
+  int a0 = 0, a1 = 0;
+  for (int r = 0; r < X.world; ++r) {
+    if (lane < K) acc += ld_sys_f64(&own->slot[par][r].v[lane]);
+    a0 += ld_sys_s32(&own->slot[par][r].cnt[0]);
+    a1 += ld_sys_s32(&own->slot[par][r].cnt[1]);
+  }
+  val = acc; c0 = a0; c1 = a1;
+  if (lane == 0) {
+    *seq_smem = want;
+    if (!ok) { own->err = 1u; seq_smem[1] = 1u; }
+  }
+  __syncwarp();
+}
+
 // Sum of the 21 unique H entries + one count over the per-feature moments of the whole pair, once per level
 // (and in the rare "slow path"): three transposed 8-value warp reductions computed chunk by chunk so that
 // only ~8 accumulators are live at a time (no register spills), one shared-memory hop, warp 0 adds the
@@ -222,7 +302,7 @@ __device__ __forceinline__ void st_cluster_v2s32(int* local_ptr, unsigned rank, 
 // barrier).  On return the totals are in s.sums[0..23] of EVERY CTA of the pair, visible to warp 0 only
 // (callers that need them elsewhere synchronise).  `get(k, x, y, zi, sxx, sxy, syy, cnt)` yields feature k's data.
 template <int FPT, int CS, class SH, class Get>
-__device__ __forceinline__ void pair_sum_h_to_warp0(Get get, SH& s, int nwarps) {
+__device__ __forceinline__ void pair_sum_h_to_warp0(Get get, SH& s, int nwarps, const XgParams& xg, int xg_pair) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   auto do_chunk = [&](auto chunk_tag) {
     constexpr int CH = decltype(chunk_tag)::value;
@@ -253,11 +333,14 @@ __device__ __forceinline__ void pair_sum_h_to_warp0(Get get, SH& s, int nwarps) 
   __syncthreads();
   if constexpr (CS == 1) {
     if (warp == 0) {
-      if (lane < kPartK) {
-        double acc = 0.0;
+      double acc = 0.0;
+      if (lane < kPartK)
         for (int wv = 0; wv < nwarps; ++wv) acc += s.hpart[wv * kPartK + lane];
-        s.sums[lane] = acc;
+      if (xg.world > 1) {  // feature split over GPUs: the other ranks' partial sums arrive through peer memory
+        int z0 = 0, z1 = 0;
+        xg_allreduce<kPartK>(xg, xg_pair, &s.xg_seq, acc, z0, z1);
       }
+      if (lane < kPartK) s.sums[lane] = acc;
       __syncwarp();
     }
   } else {
@@ -446,6 +529,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
     s.st[0].old_model = s.st[0].model;
     s.h_is_tot = 0; s.n_in_last = 0;
     s.n_iters = 0; s.sum_vis = 0; s.sum_in = 0; s.n_trace = 0;
+    s.xg_seq = (CS == 1 && P.xg.world > 1) ? P.xg.peer[P.xg.rank][pair].xseq : 0u;
+    s.xg_failed = 0u;
 #if SVO_SIA_DEBUG
     for (int k = 0; k < 8; ++k) s.tk[k] = 0;
     for (int k = 0; k < 4; ++k) s.tkx[k] = 0;
@@ -669,7 +754,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           // parked in local memory (17 doubles per thread, written once and re-read every level)
           asm volatile("" : "+d"(x), "+d"(y), "+d"(zi));
         },
-        s, nwarps);
+        s, nwarps, P.xg, pair);
     // The scaling and LDL^T factorisation of this level's H is serial work nobody needs before the first solve: warp 0
     // does it while the other warps already run the first residual pass; its results (s.sol_tot, s.Htot) become
     // visible to everybody through the barrier of that pass.
@@ -839,7 +924,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
               x = fx_[k]; y = fy_[k]; zi = fzi_[k]; sxx = q_sxx[k]; sxy = q_sxy[k]; syy = q_syy[k]; cnt = 0.0;
               asm volatile("" : "+d"(x), "+d"(y), "+d"(zi));  // see the per-level call: no hoisting into local memory
             },
-            s, nwarps);
+            s, nwarps, P.xg, pair);
       };
       auto eval_outputs = [&]() {  // EVAL, leader: computeResiduals' scalar outputs
         for (int k = 0; k < 6; ++k) P.Jres_out[k] = -(tot[k] * jscale);
@@ -866,6 +951,14 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         bool slow = false;
         if (warp == 0) {
           compute_totals();
+          if (P.xg.world > 1) {  // feature split over GPUs: sum the 7 doubles + 2 counts of this pass over the ranks
+            double v = 0.0;
+#pragma unroll
+            for (int e = 0; e < 7; ++e) v = lane == e ? tot[e] : v;
+            xg_allreduce<8>(P.xg, pair, &s.xg_seq, v, n_in, n_out);
+#pragma unroll
+            for (int e = 0; e < 7; ++e) tot[e] = __shfl_sync(0xffffffffu, v, e);
+          }
       SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { ti2 = clock64(); s.tk[1] += ti1 - ti0; s.tk[2] += ti2 - ti1; })
           slow = EVAL || (n_out > 0 && n_in > 0);
           if (!slow) {
@@ -970,6 +1063,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       P.stats[pair] = st;
     }
     if (P.n_trace) *P.n_trace = s.n_trace;
+    if (CS == 1 && P.xg.world > 1) P.xg.peer[P.xg.rank][pair].xseq = s.xg_seq;
 #if SVO_SIA_DEBUG
     if (SVO_SIA_DEBUG && P.debug && (pair == 0 || pair == (int)(gridDim.x / CS) / 2 || pair == (int)(gridDim.x / CS) - 1))
       printf("[sia dbg] pair %d iters %d cycles: setup %lld pass %lld reduce %lld tail %lld (solve %lld update %lld) total %lld | setup parts: loads+patches %lld hsum %lld factor+wait %lld\n", pair, s.n_iters,
@@ -1007,6 +1101,17 @@ void sia_batch_free(svo_b200_ctx* ctx) {
   }
   delete ctx->sia;
   ctx->sia = nullptr;
+}
+
+void sia_split_free(svo_b200_ctx* ctx) {
+  for (int r = 0; r < 8; ++r) {
+    if (ctx->xg_peer_ipc[r] && ctx->xg_peer[r]) cudaIpcCloseMemHandle(ctx->xg_peer[r]);
+    ctx->xg_peer[r] = nullptr;
+    ctx->xg_peer_ipc[r] = false;
+  }
+  if (ctx->xg_buf) cudaFree(ctx->xg_buf);
+  ctx->xg_buf = nullptr;
+  ctx->xg_world = 1; ctx->xg_rank = 0; ctx->xg_pairs = 0; ctx->xg_connected = false;
 }
 
 // tuning knobs, read once from the environment (defaults are the measured best)
@@ -1052,12 +1157,20 @@ static int pick_launch(svo_b200_ctx* ctx, int B, int max_feat, int& threads, int
     return set_err(ctx, SVO_B200_ELIMIT, "sparse_img_align: %d features per pair > 1024 (shared-memory patch cache)", max_feat);
   cluster = 1;
   int want = ctx->sia_cluster >= 0 ? ctx->sia_cluster : g_sia_cluster;
+  if (ctx->xg_connected) {
+    // feature split over GPUs: the ranks' CTAs of a pair wait for each other, so every CTA must be resident at once
+    if (B > ctx->xg_pairs || B > 2 * ctx->sm_count)
+      return set_err(ctx, SVO_B200_ELIMIT, "sia split: %d pairs per launch exceed the split's capacity (%d) or the resident CTAs (%d)",
+                     B, ctx->xg_pairs, 2 * ctx->sm_count);
+    want = 1;
+  }
   // small batch (live streams, BASELINE configs[4]'s 32 pairs per GPU): spread each pair over 4 SMs while every CTA
   // still has an SM of its own (measured: 4*B = 296 CTAs, two per SM, is already slower than one 320-thread CTA per pair)
   if (want < 0) want = (B * 4 <= ctx->sm_count) ? 4 : 1;
   // full batches (more pairs than 2 per SM): 160 threads x 2 features, three CTAs per SM; in between, 320 x 1 with windows
   int fpt2 = ctx->sia_fpt > 0 ? (ctx->sia_fpt == 2 ? 1 : 0) : g_sia_fpt2;
   if (ctx->sia_fpt == 0 && B <= 2 * ctx->sm_count) fpt2 = 0;
+  if (ctx->xg_connected) fpt2 = 0;
   if (want > 1 && max_feat <= 96 * want && (want == 2 || want == 4 || want == 8)) cluster = want;
   if (cluster > 1) {
     fpt = 1;
@@ -1158,6 +1271,11 @@ static int fill_common(svo_b200_ctx* ctx, SiaParams& P, const svo_b200_frame* fr
   read_env_once();
   P.use_windows = g_sia_windows;
   P.use_prefetch = g_sia_prefetch;
+  P.xg.rank = 0; P.xg.world = 1;
+  if (ctx->xg_connected) {
+    P.xg.rank = ctx->xg_rank; P.xg.world = ctx->xg_world;
+    for (int r = 0; r < ctx->xg_world; ++r) P.xg.peer[r] = static_cast<XgPair*>(ctx->xg_peer[r]);
+  }
   return 0;
 }
 
@@ -1166,6 +1284,57 @@ static int fill_common(svo_b200_ctx* ctx, SiaParams& P, const svo_b200_frame* fr
 using namespace svo;
 
 extern "C" {
+
+int svo_b200_sia_split_create(svo_b200_ctx* ctx, int rank, int world, int max_pairs, void* ipc_handle_out, void** local_ptr_out) {
+  if (!ctx || world < 1 || world > kMaxSplit || rank < 0 || rank >= world || max_pairs < 1)
+    return set_err(ctx, SVO_B200_EINVAL, "sia_split_create: need 1 <= world <= %d, 0 <= rank < world, max_pairs >= 1", kMaxSplit);
+  cudaSetDevice(ctx->device);
+  sia_split_free(ctx);
+  const size_t bytes = sizeof(XgPair) * (size_t)max_pairs;
+  SVO_CUDA_CHECK(ctx, cudaMalloc(&ctx->xg_buf, bytes));
+  SVO_CUDA_CHECK(ctx, cudaMemset(ctx->xg_buf, 0, bytes));
+  ctx->xg_rank = rank; ctx->xg_world = world; ctx->xg_pairs = max_pairs;
+  if (ipc_handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == SVO_B200_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    SVO_CUDA_CHECK(ctx, cudaIpcGetMemHandle(&h, ctx->xg_buf));
+    memcpy(ipc_handle_out, &h, sizeof(h));
+  }
+  if (local_ptr_out) *local_ptr_out = ctx->xg_buf;
+  return 0;
+}
+
+int svo_b200_sia_split_connect(svo_b200_ctx* ctx, const void* ipc_handles, void* const* in_process_ptrs) {
+  if (!ctx || !ctx->xg_buf || (!ipc_handles && !in_process_ptrs))
+    return set_err(ctx, SVO_B200_EINVAL, "sia_split_connect: call sia_split_create first and pass the peers' handles or pointers");
+  cudaSetDevice(ctx->device);
+  for (int r = 0; r < ctx->xg_world; ++r) {
+    if (r == ctx->xg_rank) { ctx->xg_peer[r] = ctx->xg_buf; continue; }
+    if (in_process_ptrs) {
+      if (!in_process_ptrs[r]) return set_err(ctx, SVO_B200_EINVAL, "sia_split_connect: NULL pointer for rank %d", r);
+      ctx->xg_peer[r] = in_process_ptrs[r];
+    } else {
+      cudaIpcMemHandle_t h;
+      memcpy(&h, static_cast<const uint8_t*>(ipc_handles) + (size_t)r * sizeof(h), sizeof(h));
+      SVO_CUDA_CHECK(ctx, cudaIpcOpenMemHandle(&ctx->xg_peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+      ctx->xg_peer_ipc[r] = true;
+    }
+  }
+  // the buffers start from a known state on every rank (sequence counters 0): the caller connects all ranks before any
+  // of them launches (a barrier of the launcher's own, e.g. torch.distributed.barrier)
+  SVO_CUDA_CHECK(ctx, cudaMemset(ctx->xg_buf, 0, sizeof(XgPair) * (size_t)ctx->xg_pairs));
+  SVO_CUDA_CHECK(ctx, cudaDeviceSynchronize());
+  ctx->xg_connected = ctx->xg_world > 1;
+  return 0;
+}
+
+int svo_b200_sia_split_destroy(svo_b200_ctx* ctx) {
+  if (!ctx) return SVO_B200_EINVAL;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  sia_split_free(ctx);
+  return 0;
+}
 
 int svo_b200_sia_config(svo_b200_ctx* ctx, int ctas_per_pair, int features_per_thread) {
   if (!ctx) return SVO_B200_EINVAL;
@@ -1274,6 +1443,13 @@ int svo_b200_sia_batch_fetch(svo_b200_ctx* ctx, double* T_out, uint8_t* visible_
   SiaBatchState& st = *ctx->sia;
   SVO_CUDA_CHECK(ctx, cudaMemcpyAsync(st.h_out.p, st.d_out.p, st.out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   SVO_CUDA_CHECK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->xg_connected) {  // did every peer take part in every exchange?
+    std::vector<unsigned> err((size_t)st.B, 0u);
+    SVO_CUDA_CHECK(ctx, cudaMemcpy2D(err.data(), sizeof(unsigned), static_cast<const uint8_t*>(ctx->xg_buf) + offsetof(XgPair, err),
+                                     sizeof(XgPair), sizeof(unsigned), (size_t)st.B, cudaMemcpyDeviceToHost));
+    for (int b = 0; b < st.B; ++b)
+      if (err[b]) return set_err(ctx, SVO_B200_ECUDA, "sia split: a peer rank did not arrive at an exchange of pair %d (timeout); reconnect the split", b);
+  }
   const uint8_t* h = static_cast<const uint8_t*>(st.h_out.p);
   if (T_out) memcpy(T_out, h + st.o_T, sizeof(double) * 12 * (size_t)st.B);
   if (H_out) memcpy(H_out, h + st.o_H, sizeof(double) * 36 * (size_t)st.B);

@@ -86,3 +86,102 @@ def test_split_on_gpu_matches_one_cta_kernel(ctx, pair300):
     dt, dr = synth.pose_error(r["T"], g["T"])
     assert dt < 1e-5 and dr < 1e-5 and r["n_tracked"] == g["n_tracked"]
     ref.destroy(); cur.destroy()
+
+
+# ---- the product path of the split: the kernels of the ranks exchange their sums through peer memory ---------------------
+def _run_split_in_process(contexts, d, max_level, min_level, frames=None):
+    """`world` contexts = `world` ranks sharing this process (and, on the one-GPU test box, the GPU): each rank aligns its
+    contiguous slice of the pair's features from a host thread of its own; the kernels meet in the exchange buffers."""
+    import threading
+
+    from rpg_svo_b200 import shard
+
+    world = len(contexts)
+    if frames is None:
+        frames = [(c.frame(d["ref_pyr"]), c.frame(d["cur_pyr"])) for c in contexts]
+    out, errs = [None] * world, [None] * world
+
+    def work(r):
+        lo, hi = shard.shard_range(len(d["px"]), r, world)
+        try:
+            out[r] = contexts[r].sparse_img_align(frames[r][0], frames[r][1], d["cam"], synth.se3_identity(), d["px"][lo:hi],
+                                                  d["f"][lo:hi], d["pos"][lo:hi], d["has_point"][lo:hi], d["ref_pos"], max_level,
+                                                  min_level)
+        except Exception as e:  # noqa: BLE001
+            errs[r] = e
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    return out, errs, frames
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 3])
+def test_split_through_peer_memory_matches_the_single_kernel(ctx, oracle, pair300, world):
+    """svo_b200_sia_split_*: every rank runs ONE kernel for the whole coarse-to-fine loop; the per-iteration sums cross
+    between the ranks' kernels through the exchange buffers (system-scope stores + flags).  All ranks must end bit-identical,
+    equal to the undivided kernel up to summation order, and the set-only visibility masks of the slices must concatenate to
+    the undivided mask."""
+    from rpg_svo_b200 import capi
+
+    d = pair300
+    contexts = [capi.Context(0) for _ in range(world)]
+    try:
+        ptrs = [c.sia_split_create(r, world, 1)[1] for r, c in enumerate(contexts)]
+        for c in contexts:
+            c.sia_split_connect(in_process_ptrs=ptrs)
+        ref, cur = ctx.frame(d["ref_pyr"]), ctx.frame(d["cur_pyr"])
+        g = ctx.sparse_img_align(ref, cur, d["cam"], synth.se3_identity(), d["px"], d["f"], d["pos"], d["has_point"], d["ref_pos"], 4, 0)
+        frames = None
+        for rep in range(2):  # the exchange sequence numbers carry over from launch to launch
+            out, errs, frames = _run_split_in_process(contexts, d, 4, 0, frames)
+            assert errs == [None] * world, errs
+            for r in range(1, world):
+                assert np.array_equal(out[r]["T"], out[0]["T"]) and np.array_equal(out[r]["H"], out[0]["H"])
+                assert out[r]["n_tracked"] == out[0]["n_tracked"]
+            dt, dr = synth.pose_error(out[0]["T"], g["T"])
+            assert dt < 1e-7 and dr < 1e-7, (dt, dr)
+            assert out[0]["n_tracked"] == g["n_tracked"]
+            assert np.array_equal(np.concatenate([o["visible"] for o in out]), g["visible"])
+            assert np.allclose(out[0]["H"], g["H"], rtol=1e-9, atol=1e-6)
+        o = oracle.sparse_img_align(d["ref_pyr"], d["cur_pyr"], d["cam"], synth.se3_identity(), d["px"], d["f"], d["pos"],
+                                    d["has_point"], d["ref_pos"], 4, 0)
+        dt, dr = synth.pose_error(out[0]["T"], o["T"])
+        assert dt < 1e-4 and dr < 1e-4
+        for fr in frames:
+            fr[0].destroy(); fr[1].destroy()
+        ref.destroy(); cur.destroy()
+    finally:
+        for c in contexts:
+            c.sia_split_destroy()
+            c.close()
+
+
+@pytest.mark.gpu
+def test_split_peer_that_never_arrives_times_out_instead_of_hanging(pair300):
+    """Only rank 0 of a 2-way split launches: its kernel waits ~2 s at the first exchange, gives up, and the call reports the
+    error -- the GPU is never left spinning."""
+    import time
+
+    from rpg_svo_b200 import capi
+
+    d = pair300
+    contexts = [capi.Context(0) for _ in range(2)]
+    try:
+        ptrs = [c.sia_split_create(r, 2, 1)[1] for r, c in enumerate(contexts)]
+        for c in contexts:
+            c.sia_split_connect(in_process_ptrs=ptrs)
+        ref, cur = contexts[0].frame(d["ref_pyr"]), contexts[0].frame(d["cur_pyr"])
+        t0 = time.perf_counter()
+        with pytest.raises(capi.SvoB200Error, match="did not arrive"):
+            contexts[0].sparse_img_align(ref, cur, d["cam"], synth.se3_identity(), d["px"][:150], d["f"][:150], d["pos"][:150],
+                                         d["has_point"][:150], d["ref_pos"], 4, 0)
+        assert time.perf_counter() - t0 < 10.0   # one ~2 s timeout, not one per exchange
+        ref.destroy(); cur.destroy()
+    finally:
+        for c in contexts:
+            c.sia_split_destroy()
+            c.close()
