@@ -418,6 +418,29 @@ def ref_sparse_img_align(ref_l0, cur_l0, n_levels, cam, T_ref_w, T_cur_w, px, f,
     return dict(T_cur_w=T.reshape(3, 4), n_tracked=int(ret), visible=vis, H=H.reshape(6, 6), ref_patch=cache)
 
 
+def ref_sparse_residuals(ref_l0, cur_l0, n_levels, cam, T_ref_w, T_cur_w, px, f, pos, has_point, level):
+    """svo::SparseImgAlign::computeResiduals(T_cur_from_ref, true, true) of the compiled reference at one level and one
+    pose (fresh object, precomputeReferencePatches included): visibility mask, patch cache, H_, Jres_, chi2, n_meas_ and
+    |res| of every pixel of every in-image patch in feature order (`abs_res`, n_meas values)."""
+    h, w = ref_l0.shape
+    px, f, pos = c64(px), c64(f), c64(pos)
+    hp = np.ascontiguousarray(has_point, np.uint8)
+    n = len(hp)
+    vis = np.zeros(n, np.uint8)
+    cache = np.zeros((n, 16), np.float32)
+    H, Jres = np.zeros(36), np.zeros(6)
+    chi2 = C.c_double(0)
+    absres = np.zeros(16 * max(n, 1), np.float32)
+    L = ref_lib()
+    L.ref_sparse_residuals.restype = C.c_longlong
+    nm = L.ref_sparse_residuals(_p(np.ascontiguousarray(ref_l0)), _p(np.ascontiguousarray(cur_l0)), w, h, n_levels,
+                                _p(_cam4(cam)), _p(c64(T_ref_w).reshape(12)), _p(c64(T_cur_w).reshape(12)), _p(px), _p(f),
+                                _p(pos), _p(hp), n, int(level), _p(vis), _p(cache), _p(H), _p(Jres), C.byref(chi2), _p(absres),
+                                C.c_longlong(len(absres)))
+    return dict(visible=vis, ref_patch=cache, H=H.reshape(6, 6), Jres=Jres, chi2=chi2.value, n_meas=int(nm),
+                abs_res=absres[:int(nm)].reshape(-1, 16))
+
+
 def ref_image_pyramid(img, n_levels):
     """frame_utils::createImgPyramid of the compiled reference (svo/src/frame.cpp:156-165 over the shim's vk::halfSample,
     real SSE2 intrinsics on this x86 host)."""

@@ -140,6 +140,64 @@ long long ref_sparse_img_align(const uint8_t* ref_l0, const uint8_t* cur_l0, int
   return (long long)ret;
 }
 
+// svo::SparseImgAlign::computeResiduals (sparse_img_align.cpp:147-243) of the compiled reference at ONE level and ONE
+// pose, called directly (it is protected: the derived class below reaches it), with everything it leaves behind:
+// the visibility mask and patch cache of precomputeReferencePatches, H_, Jres_, chi2, n_meas_ -- and the per-pixel
+// residual magnitudes, captured by handing the solver a scale estimator that copies the `errors` vector the reference
+// fills when compute_weight_scale is set (|res| of every pixel of every in-image patch, in feature order).
+namespace {
+struct CapturingScale : public vk::robust_cost::ScaleEstimator {
+  mutable std::vector<float> got;
+  float compute(std::vector<float>& errors) const override { got = errors; return 1.0f; }
+};
+struct SIAResiduals : public SparseImgAlign {
+  static const int kArea = 16;  // patch_size_ * patch_size_ (sparse_img_align.h:35-37, private there)
+  std::shared_ptr<CapturingScale> cap{new CapturingScale};
+  SIAResiduals(int level) : SparseImgAlign(level, level, 1, GaussNewton, false, false) { scale_estimator_ = cap; }
+  double eval(FramePtr ref, FramePtr cur, int level, const SE3& T_cur_from_ref) {
+    ref_frame_ = ref; cur_frame_ = cur; level_ = level;
+    ref_patch_cache_ = cv::Mat(ref->fts_.size(), kArea, CV_32F);   // as run() sizes them (:55-57); patch_area_ is private
+    jacobian_cache_.resize(Eigen::NoChange, ref_patch_cache_.rows * kArea);
+    visible_fts_.assign(ref_patch_cache_.rows, false);
+    jacobian_cache_.setZero();
+    have_ref_patch_cache_ = false;
+    H_.setZero(); Jres_.setZero(); n_meas_ = 0; iter_ = 0;
+    return computeResiduals(T_cur_from_ref, true, true);
+  }
+  const std::vector<bool>& visible() const { return visible_fts_; }
+  const cv::Mat& patch_cache() const { return ref_patch_cache_; }
+  const Matrix<double, 6, 6>& H() const { return H_; }
+  const Matrix<double, 6, 1>& Jres() const { return Jres_; }
+  size_t n_meas() const { return n_meas_; }
+};
+}  // namespace
+long long ref_sparse_residuals(const uint8_t* ref_l0, const uint8_t* cur_l0, int w, int h, int n_levels, const double* cam4,
+                               const double* T_ref_w, const double* T_cur_w, const double* px, const double* f, const double* pos,
+                               const uint8_t* has_point, int N, int level, uint8_t* visible_out, float* patch_cache_out,
+                               double* H_out, double* Jres_out, double* chi2_out, float* abs_res_out, long long abs_res_cap) {
+  std::unique_ptr<vk::AbstractCamera> cam_owner(ref_make_camera(w, h, cam4));
+  vk::AbstractCamera& cam = *cam_owner;
+  FramePtr ref = make_frame(&cam, ref_l0, w, h, n_levels, T_ref_w);
+  FramePtr cur = make_frame(&cam, cur_l0, w, h, n_levels, T_cur_w);
+  std::vector<std::unique_ptr<Point>> pts;
+  for (int i = 0; i < N; ++i) {
+    Point* p = nullptr;
+    if (has_point[i]) { pts.emplace_back(new Point(Vector3d(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]))); p = pts.back().get(); }
+    ref->addFeature(new Feature(ref.get(), p, Vector2d(px[2 * i], px[2 * i + 1]), Vector3d(f[3 * i], f[3 * i + 1], f[3 * i + 2]), 0));
+  }
+  SIAResiduals sia(level);
+  const SE3 T_cur_from_ref(cur->T_f_w_ * ref->T_f_w_.inverse());  // as run() forms it (:66)
+  const double chi2 = sia.eval(ref, cur, level, T_cur_from_ref);
+  if (visible_out) for (int i = 0; i < N; ++i) visible_out[i] = sia.visible()[i];
+  if (patch_cache_out && N) memcpy(patch_cache_out, sia.patch_cache().data, sizeof(float) * 16 * (size_t)N);
+  if (H_out) for (int a = 0; a < 6; ++a) for (int b = 0; b < 6; ++b) H_out[a * 6 + b] = sia.H()(a, b);
+  if (Jres_out) for (int a = 0; a < 6; ++a) Jres_out[a] = sia.Jres()(a);
+  if (chi2_out) *chi2_out = chi2;
+  const long long n_abs = (long long)sia.cap->got.size();
+  if (abs_res_out) for (long long k = 0; k < n_abs && k < abs_res_cap; ++k) abs_res_out[k] = sia.cap->got[k];
+  return (long long)sia.n_meas();
+}
+
 // ---- a stream of frame pairs kept alive between calls, for timing svo::SparseImgAlign::run alone (bench.py's
 // --impl reference arm and cpu_baseline leg): pair k = (frame k, frame k+1); pyramids are built at create time.
 struct RefStream {

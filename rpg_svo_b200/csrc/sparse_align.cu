@@ -490,6 +490,16 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
 
 enum { kModeGlobal = 0, kModeImage = 1, kModeWindow = 2 };
 
+template <bool CG>
+__device__ __forceinline__ void sia_world2cam(const CamDev& c, double x, double y, double& u, double& v) {
+  if constexpr (CG) {
+    cam_world2cam(c, x, y, u, v);
+  } else {  // undistorted pinhole (the host dispatches on svo_b200_camera: model == PINHOLE, no distortion)
+    u = fma(c.fx, x, c.cx);
+    v = fma(c.fy, y, c.cy);
+  }
+}
+
 // One CTA (CS == 1) or one cluster of CS CTAs per frame pair; the pair's features are dealt to the CTAs in
 // contiguous blocks of S = MAXT*FPT slots.
 // (__launch_bounds__(160, 3) yields 128 registers although 3 x 160 x 136 <= 64 K: the register file is split over the
@@ -497,7 +507,11 @@ enum { kModeGlobal = 0, kModeImage = 1, kModeWindow = 2 };
 // __maxnreg__ drops the kernel to two CTAs per SM and costs 20 % throughput.  Also measured and not kept: laying the
 // two-feature residual pass out phase by phase for instruction-level parallelism (no change), and issuing both features'
 // reference-footprint loads before computing either patch (-5 %: the extra live registers spill).)
-template <int FPT, bool EVAL, int MAXT, int MINB, int CS>
+//
+// CG = false compiles the projection for the undistorted pinhole only (px = fx * uv + cx): the general vk::AbstractCamera
+// dispatch (radial-tangential pinhole, ATAN with its atan() slow path) stays out of the instruction stream of the
+// residual loop, which is what BASELINE's synthetic camera and any rectified stream run.
+template <int FPT, bool EVAL, int MAXT, int MINB, int CS, bool CG>
 __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SH = SiaSharedT<MAXT / 32, CS>;
@@ -666,7 +680,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         const double zc = fma(R[6], x, fma(R[7], y, fma(R[8], z, t[2])));
         const double rz = fast_rcp(zc);
         double ud, vd;
-        cam_world2cam(P.cam, div_rn(xc, zc, rz), div_rn(yc, zc, rz), ud, vd);
+        sia_world2cam<CG>(P.cam, div_rn(xc, zc, rz), div_rn(yc, zc, rz), ud, vd);
         const float u0 = __fmul_rn((float)ud, scale), v0 = __fmul_rn((float)vd, scale);
         if (u0 >= 0.f && v0 >= 0.f && u0 < 1e6f && v0 < 1e6f) {
           float tmp;
@@ -788,7 +802,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         const double zc = fma(R[6], x, fma(R[7], y, fma(R[8], z, t[2])));
         const double rz = fast_rcp(zc);
         double ud, vd;
-        cam_world2cam(P.cam, div_rn(xc, zc, rz), div_rn(yc, zc, rz), ud, vd);  // [EXT] world2cam(project2d(xyz))
+        sia_world2cam<CG>(P.cam, div_rn(xc, zc, rz), div_rn(yc, zc, rz), ud, vd);  // [EXT] world2cam(project2d(xyz))
         const float u_cur = __fmul_rn((float)ud, scale);  // .cast<float>() * scale (:183)
         const float v_cur = __fmul_rn((float)vd, scale);
         // negative / non-finite / huge coordinates can never pass the border test (:190)
@@ -1122,6 +1136,7 @@ static int g_sia_prefetch = 1;    // SVO_B200_SIA_PREFETCH=0: no bulk L2 prefetc
                                   // (Per-feature L2 prefetches of the next level's footprints were measured and removed: the extra
                                   // uncoalesced requests cost more L1 time than the DRAM latency they hide.)
 static int g_sia_cluster = -1;    // SVO_B200_SIA_CLUSTER: force the CTAs per pair (1, 2, 4, 8); -1 = by batch size
+static int g_sia_plain = 1;       // SVO_B200_SIA_PLAIN=0: the undistorted pinhole runs the general-camera instantiation too
 static int g_sia_fpt2 = 1;        // SVO_B200_SIA_FPT2: <= 320 features per CTA as 160 threads x 2 features: 1 = three CTAs per SM (default,
                                   // measured best for full batches), 2 = two CTAs per SM with windows, 0 = 320 threads x 1 feature
 
@@ -1135,6 +1150,7 @@ static void read_env_once() {
   if (const char* e = getenv("SVO_B200_SIA_PREFETCH")) g_sia_prefetch = atoi(e) != 0;
   if (const char* e = getenv("SVO_B200_SIA_CLUSTER")) g_sia_cluster = atoi(e);
   if (const char* e = getenv("SVO_B200_SIA_FPT2")) g_sia_fpt2 = atoi(e);
+  if (const char* e = getenv("SVO_B200_SIA_PLAIN")) g_sia_plain = atoi(e) != 0;
 }
 
 // Launch geometry for a batch of B pairs with at most max_feat features each.
@@ -1230,18 +1246,21 @@ static int launch_sia(svo_b200_ctx* ctx, const SiaParams& P, int B, int threads,
     SVO_CUDA_CHECK(ctx, cudaGetLastError());
     return 0;
   };
-  if (cluster == 2) return go(sia_kernel<1, EVAL, 96, 2, 2>);
-  if (cluster == 4) return go(sia_kernel<1, EVAL, 96, 2, 4>);
-  if (cluster == 8) return go(sia_kernel<1, EVAL, 96, 2, 8>);
+  // the undistorted pinhole gets its own instantiation of the two geometries that carry the throughput / latency figures
+  // (the general-camera code also handles it; EVAL and the rarely used geometries are compiled once)
+  const bool plain = !EVAL && !P.cam.distorted && P.cam.model == SVO_B200_CAM_PINHOLE && g_sia_plain;
+  if (cluster == 2) return go(sia_kernel<1, EVAL, 96, 2, 2, true>);
+  if (cluster == 4) return plain ? go(sia_kernel<1, EVAL, 96, 2, 4, EVAL>) : go(sia_kernel<1, EVAL, 96, 2, 4, true>);
+  if (cluster == 8) return go(sia_kernel<1, EVAL, 96, 2, 8, true>);
   // <= 384 threads: cap registers so that two CTAs are resident per SM
   if (fpt == 1) {
-    if (threads <= 320 && g_sia_minb == 3) return go(sia_kernel<1, EVAL, 320, 3, 1>);
-    if (threads <= 320) return go(sia_kernel<1, EVAL, 320, 2, 1>);
-    if (threads <= 384) return go(sia_kernel<1, EVAL, 384, 2, 1>);
-    return go(sia_kernel<1, EVAL, 512, 1, 1>);
+    if (threads <= 320 && g_sia_minb == 3) return go(sia_kernel<1, EVAL, 320, 3, 1, true>);
+    if (threads <= 320) return plain ? go(sia_kernel<1, EVAL, 320, 2, 1, EVAL>) : go(sia_kernel<1, EVAL, 320, 2, 1, true>);
+    if (threads <= 384) return go(sia_kernel<1, EVAL, 384, 2, 1, true>);
+    return go(sia_kernel<1, EVAL, 512, 1, 1, true>);
   }
-  if (threads == 160) return go(sia_kernel<2, EVAL, 160, 3, 1>);
-  return go(sia_kernel<2, EVAL, 512, 1, 1>);
+  if (threads == 160) return plain ? go(sia_kernel<2, EVAL, 160, 3, 1, EVAL>) : go(sia_kernel<2, EVAL, 160, 3, 1, true>);
+  return go(sia_kernel<2, EVAL, 512, 1, 1, true>);
 }
 
 static inline int pad16(int n) { return (n + 15) / 16 * 16; }

@@ -237,6 +237,39 @@ def test_oracle_sparse_img_align_equals_reference_source_compiled_here(oracle, s
     assert np.array_equal(r["ref_patch"][v], q["ref_patch"][v])
 
 
+@pytest.mark.parametrize("level", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("camera", ["pinhole", "atan", "pinhole_radtan"])
+def test_oracle_residual_pass_equals_reference_source_compiled_here(oracle, level, camera):
+    """svo::SparseImgAlign::computeResiduals of the compiled reference (sparse_img_align.cpp:147-243), called directly at one
+    level and a perturbed pose, vs the oracle's restatement: visibility, patch cache and the magnitude of EVERY per-pixel
+    residual bit for bit (the reference's `errors` vector, captured through the solver's scale estimator), chi2 / n_meas
+    equal, Jres_ and H_ to rounding of the summation."""
+    _need_ref(oracle)
+    if camera == "pinhole":
+        p = synth.make_frame_pair(1000, n_feat=300, n_levels=5)
+    else:  # the parameter files the reference ships (752x480)
+        cam = synth.reference_param_camera(camera)
+        p = synth.make_frame_pair(1000, width=cam.width, height=cam.height, n_feat=300, n_levels=5, cam=cam)
+    p["has_point"][::19] = 0
+    T = synth.se3_exp(np.array([0.004, -0.003, 0.002, 0.001, -0.002, 0.0015]))
+    r = oracle.ref_sparse_residuals(p["ref_pyr"][0], p["cur_pyr"][0], p["n_levels"], p["cam"], p["T_ref_w"],
+                                    synth.se3_mul(T, p["T_ref_w"]), p["px"], p["f"], p["pos"], p["has_point"], level)
+    o = oracle.sparse_residuals(p["ref_pyr"][level], p["cur_pyr"][level], level, p["cam"], T, p["px"], p["f"], p["pos"],
+                                p["has_point"], p["ref_pos"])
+    v, m = o["visible"].astype(bool), o["in_image"].astype(bool)
+    assert np.array_equal(r["visible"], o["visible"])
+    assert np.array_equal(r["ref_patch"][v], o["ref_patch"][v])
+    assert r["n_meas"] == o["n_meas"] == 16 * int(m.sum()) and m.sum() > 200
+    assert r["abs_res"].shape == (int(m.sum()), 16)
+    # T_cur_from_ref is re-formed by the reference as T_cur_w * T_ref_w^-1 (1e-16 away from T): allow the rare pixel whose
+    # f32 coordinate lands on the other side of a rounding boundary, demand identity for (nearly) all of them
+    same = np.abs(o["residuals"][m]) == r["abs_res"]
+    assert same.mean() >= 0.99 and np.max(np.abs(np.abs(o["residuals"][m]) - r["abs_res"])) <= 1e-4
+    assert abs(r["chi2"] - o["chi2"]) <= 1e-6 * abs(o["chi2"])
+    assert np.allclose(r["H"], o["H"], rtol=1e-12, atol=1e-9 * np.abs(o["H"]).max())
+    assert np.allclose(r["Jres"], o["Jres"], rtol=1e-9, atol=1e-6)
+
+
 def test_oracle_pose_optimizer_equals_reference_source_compiled_here(oracle):
     _need_ref(oracle)
     for seed in (3, 4):

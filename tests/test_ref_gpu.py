@@ -34,6 +34,30 @@ def test_sparse_img_align_vs_compiled_reference(ctx, ref, seed, levels):
     assert synth.pose_error(r["T_cur_w"], p["T_cur_w"])[0] < 1e-3         # and the reference really tracked the motion
 
 
+@pytest.mark.parametrize("level", [0, 2, 4])
+def test_residual_pass_vs_compiled_reference(ctx, ref, level):
+    """The kernel's residual pass against the reference's own computeResiduals object code (no oracle in between): masks
+    and patch cache bit-exact, every per-pixel residual magnitude within the north_star's 1e-4 (and bit-identical for
+    nearly all pixels), chi2 / n_meas / Jres_ / H_."""
+    p = synth.make_frame_pair(45, n_feat=300, n_levels=5)
+    p["has_point"][::19] = 0
+    T = synth.se3_exp(np.array([0.004, -0.003, 0.002, 0.001, -0.002, 0.0015]))
+    r = ref.ref_sparse_residuals(p["ref_pyr"][0], p["cur_pyr"][0], p["n_levels"], p["cam"], p["T_ref_w"],
+                                 synth.se3_mul(T, p["T_ref_w"]), p["px"], p["f"], p["pos"], p["has_point"], level)
+    fr, fc = ctx.frame(p["ref_pyr"]), ctx.frame(p["cur_pyr"])
+    g = ctx.sparse_residuals(fr, fc, p["cam"], level, T, p["px"], p["f"], p["pos"], p["has_point"], p["ref_pos"])
+    fr.destroy(); fc.destroy()
+    v, m = g["visible"].astype(bool), g["in_image"].astype(bool)
+    assert np.array_equal(g["visible"], r["visible"])
+    assert np.array_equal(g["ref_patch"][v], r["ref_patch"][v])
+    assert g["n_meas"] == r["n_meas"] == 16 * int(m.sum()) and m.sum() > 200
+    d = np.abs(np.abs(g["residuals"][m]) - r["abs_res"])
+    assert d.max() <= 1e-4 and (d == 0).mean() >= 0.99, (d.max(), (d == 0).mean())
+    assert abs(g["chi2"] - r["chi2"]) <= 1e-5 * abs(r["chi2"])
+    assert np.allclose(g["H"], r["H"], rtol=1e-9, atol=1e-6)
+    assert np.allclose(g["Jres"], r["Jres"], rtol=1e-5, atol=1e-3)
+
+
 def test_pose_optimizer_vs_compiled_reference(ctx, ref):
     c = synth.make_pose_opt_case(43, 800, 752, 480)
     r = ref.ref_pose_optimize(2.0, 10, c["cam"], c["T_init"], c["f"], c["pos"], c["level"], c["has_point"])
