@@ -175,6 +175,10 @@ int svo_b200_sia_batch_fetch(svo_b200_ctx* ctx, double* T_out /*B*12*/, uint8_t*
  *                  small batches; one CTA per pair otherwise), or 1, 2, 4, 8 (clusters need <= 96*ctas features per pair).
  *   features_per_thread: 0 = automatic, 1, 2 (one CTA per pair only). */
 int svo_b200_sia_config(svo_b200_ctx* ctx, int ctas_per_pair, int features_per_thread);
+/* Small batches in the 4-CTA cluster geometry (every CTA alone on an SM) prepare the reference patches, H and its
+ * factorisation of ALL pyramid levels before the first Gauss-Newton iteration ("upfront"; none of it depends on the pose,
+ * svo/src/sparse_img_align.cpp:84-145 runs it lazily per level).  mode: -1 = automatic (default), 0 = per level, 1 = as -1. */
+int svo_b200_sia_upfront(svo_b200_ctx* ctx, int mode);
 
 /* ---- one stream's features split over several GPUs (a demonstration mode: a pair fits one GPU) ----
  * Every rank (one process or thread per GPU) holds both pyramids and passes ITS contiguous slice of the pair's features

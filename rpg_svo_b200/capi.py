@@ -300,6 +300,10 @@ class Context:
     def sia_split_destroy(self):
         self._check(self.lib.svo_b200_sia_split_destroy(self.h))
 
+    def sia_upfront(self, mode=-1):
+        """Small-batch cluster geometry: all levels prepared before the first iteration (svo_b200_sia_upfront): -1 auto, 0 off."""
+        self._check(self.lib.svo_b200_sia_upfront(self.h, int(mode)))
+
     def sia_config(self, ctas_per_pair=-1, features_per_thread=0):
         """Launch geometry of the alignment kernel (svo_b200_sia_config): -1 / 0 = automatic."""
         self._check(self.lib.svo_b200_sia_config(self.h, int(ctas_per_pair), int(features_per_thread)))

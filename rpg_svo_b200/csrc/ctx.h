@@ -66,6 +66,7 @@ struct svo_b200_ctx {
   bool xg_peer_ipc[8] = {false, false, false, false, false, false, false, false};
   int sia_cluster = -1;  // svo_b200_sia_config: CTAs per pair (-1 = by batch size)
   int sia_fpt = 0;       //                      features per thread (0 = automatic)
+  int sia_upfront = -1;  // svo_b200_sia_upfront: all levels prepared before the first iteration (-1 = automatic, 0 = off)
 };
 
 namespace svo {

@@ -16,6 +16,7 @@
 //     MSB-first radix select on order-preserving keys that stops as soon as one candidate is left (3-4 passes of
 //     8 bits instead of 8); error_init and error_final are selected in the same passes.
 // All arithmetic is f64 except the f32 error vector / Tukey weight, as in the reference.
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -23,6 +24,15 @@
 #include "svo_math.cuh"
 
 namespace svo {
+
+#ifndef SVO_SIA_DEBUG
+#define SVO_SIA_DEBUG 0  // instrumented build (scripts/r02*_probe.sh): thread 0 of frame 0 prints clock64 section timings
+#endif
+#if SVO_SIA_DEBUG
+#define PO_DBG(...) __VA_ARGS__
+#else
+#define PO_DBG(...)
+#endif
 
 constexpr int kPoThreads = 512;
 constexpr int kPoWarps = kPoThreads / 32;
@@ -225,6 +235,7 @@ __global__ void __launch_bounds__(kPoThreads) pose_opt_kernel(PoseOptParams P) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double fx = P.fx[fr];
   uint8_t* has_point = P.has_point + o0;
+  PO_DBG(long long tc[8]; tc[0] = clock64();)
 
   // ---- per-observation constants, once ------------------------------------------------------------
   double cnt[1] = {0.0};
@@ -262,6 +273,7 @@ __global__ void __launch_bounds__(kPoThreads) pose_opt_kernel(PoseOptParams P) {
     }
     return;
   }
+  PO_DBG(tc[1] = clock64();)
   // ---- scale of the error for robust estimation (:47-60) ------------------------------------
   for (int i = tid; i < N; i += kPoThreads) {
     if (!o.valid[i]) continue;
@@ -278,6 +290,7 @@ __global__ void __launch_bounds__(kPoThreads) pose_opt_kernel(PoseOptParams P) {
   const double estimated_scale = (double)__fmul_rn(1.48f, (float)s.med[0]);
   double scale = estimated_scale;
 
+  PO_DBG(tc[2] = clock64();)
   // ---- Gauss-Newton (:63-121) -------------------------------------------------------------------
   for (int iter = 0; iter < P.n_iter; ++iter) {
     if (iter == 5) scale = 0.85 / fx;  // (:69-70)
@@ -375,6 +388,7 @@ __global__ void __launch_bounds__(kPoThreads) pose_opt_kernel(PoseOptParams P) {
     if (s.done) break;
   }
 
+  PO_DBG(tc[3] = clock64();)
   // ---- remove measurements with too large reprojection error (:129-145) ------------------------
   const double thresh = P.reproj_thresh / fx;
   double del[1] = {0.0};
@@ -393,6 +407,7 @@ __global__ void __launch_bounds__(kPoThreads) pose_opt_kernel(PoseOptParams P) {
     const double* const arr[2] = {o.init, o.work};
     block_kth<2>(arr, o.valid, N, num_obs / 2, s);
   }
+  PO_DBG(tc[4] = clock64();)
   const double med_init = (P.n_iter > 0) ? s.med[0] : 0.0;
   const double med_final = s.med[1];
   for (int i = tid; i < N; i += kPoThreads)
@@ -429,6 +444,8 @@ __global__ void __launch_bounds__(kPoThreads) pose_opt_kernel(PoseOptParams P) {
     r.n_iter_done = s.iters;
     P.out[fr] = r;
     pose_to_rt12(s.T, P.T_io + 12 * (size_t)fr);
+    PO_DBG(if (fr == 0) printf("[po dbg] N %d iters %d cycles: constants %lld scale-median %lld gauss-newton %lld cull+medians %lld cov+out %lld\n",
+                              N, s.iters, tc[1] - tc[0], tc[2] - tc[1], tc[3] - tc[2], tc[4] - tc[3], (long long)clock64() - tc[4]);)
   }
 }
 

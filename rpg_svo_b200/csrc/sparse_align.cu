@@ -141,12 +141,25 @@ struct SiaSharedT {
   unsigned mbar_phase;
   unsigned xg_seq;     // feature split over GPUs: exchanges completed (warp 0) ...
   unsigned xg_failed;  // ... and "an exchange timed out" (must directly follow xg_seq)
-  double pub[12];      // CS == 1: the pose (R row-major, t) warp 0 publishes after its Gauss-Newton tail
+  alignas(16) double pub[12];  // CS == 1: the pose (R row-major, t) warp 0 publishes after its Gauss-Newton tail
   int pub_done, pub_slow;
 #if SVO_SIA_DEBUG
   long long tkx[4];
   long long tk[8];  // debug: cycles in [level setup, pass, reduce, tail, total]
 #endif
+};
+
+// "Upfront" variant (small batches: a thread-block cluster per pair, every CTA with an SM of its own): the reference patches,
+// H sums and factorisations of ALL pyramid levels -- none of which depends on the pose -- are computed before the first
+// Gauss-Newton iteration, with one cluster exchange for all levels, so a level starts with nothing but the staging of its
+// current image.  Per-level results live here (behind the control block) and in per-level patch arrays.
+template <int NWC, int CS>
+struct SiaUpT {
+  double hpart[SVO_B200_MAX_LEVELS][NWC * kPartK];      // per-warp partials of every level
+  double hsum_cta[SVO_B200_MAX_LEVELS][CS][kPartK];     // per-CTA sums of every level (written remotely)
+  double sums[SVO_B200_MAX_LEVELS][kPartK];
+  double Htot[SVO_B200_MAX_LEVELS][36];
+  Solver6 sol[SVO_B200_MAX_LEVELS];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -295,15 +308,13 @@ __device__ __forceinline__ void xg_allreduce(const XgParams& X, int pair, unsign
   __syncwarp();
 }
 
-// Sum of the 21 unique H entries + one count over the per-feature moments of the whole pair, once per level
-// (and in the rare "slow path"): three transposed 8-value warp reductions computed chunk by chunk so that
-// only ~8 accumulators are live at a time (no register spills), one shared-memory hop, warp 0 adds the
-// per-warp partials (and, in the cluster variant, CTA rank 0's warp 0 adds the per-CTA sums after a cluster
-// barrier).  On return the totals are in s.sums[0..23] of EVERY CTA of the pair, visible to warp 0 only
-// (callers that need them elsewhere synchronise).  `get(k, x, y, zi, sxx, sxy, syy, cnt)` yields feature k's data.
-template <int FPT, int CS, class SH, class Get>
-__device__ __forceinline__ void pair_sum_h_to_warp0(Get get, SH& s, int nwarps, const XgParams& xg, int xg_pair) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// Per-warp part of the H reduction: the 24 values (21 unique entries of sum_f Sxx aa^T + Sxy (ab^T + ba^T) + Syy bb^T, the
+// feature count, two pads) of this warp's features, into dst[0..23] (shared memory): three transposed 8-value warp
+// reductions computed chunk by chunk so that only ~8 accumulators are live at a time.
+// `get(k, x, y, zi, sxx, sxy, syy, cnt)` yields feature k's data.
+template <int FPT, class Get>
+__device__ __forceinline__ void warp_h_partials(Get get, double* dst) {
+  const int lane = threadIdx.x & 31;
   auto do_chunk = [&](auto chunk_tag) {
     constexpr int CH = decltype(chunk_tag)::value;
     double v[8];
@@ -325,11 +336,21 @@ __device__ __forceinline__ void pair_sum_h_to_warp0(Get get, SH& s, int nwarps, 
       v[7] += h_chunk_value<CH, 7>(a, b, sxx, sxy, syy, cnt);
     }
     warp_reduce_t<8>(v);
-    if ((lane & 3) == 0) s.hpart[warp * kPartK + CH * 8 + (lane >> 2)] = v[0];
+    if ((lane & 3) == 0) dst[CH * 8 + (lane >> 2)] = v[0];
   };
   do_chunk(std::integral_constant<int, 0>{});
   do_chunk(std::integral_constant<int, 1>{});
   do_chunk(std::integral_constant<int, 2>{});
+}
+
+// Sum of the 21 unique H entries + one count over the per-feature moments of the whole pair, once per level
+// (and in the rare "slow path"): per-warp partials, one shared-memory hop, warp 0 adds the per-warp partials (and, in the
+// cluster variant, the per-CTA sums every CTA received through DSMEM, after a cluster barrier).  On return the totals are in
+// s.sums[0..23] of EVERY CTA of the pair, visible to warp 0 only (callers that need them elsewhere synchronise).
+template <int FPT, int CS, class SH, class Get>
+__device__ __forceinline__ void pair_sum_h_to_warp0(Get get, SH& s, int nwarps, const XgParams& xg, int xg_pair) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  warp_h_partials<FPT>(get, &s.hpart[warp * kPartK]);
   __syncthreads();
   if constexpr (CS == 1) {
     if (warp == 0) {
@@ -367,12 +388,11 @@ __device__ __forceinline__ void pair_sum_h_to_warp0(Get get, SH& s, int nwarps, 
 // Warp 0: scale the 21 summed H entries into the full symmetric 6x6 `Hdst` and factorise it into `S`.
 // Every lane runs the register-resident unpivoted LDL^T redundantly (same cost as one lane), lane 0 stores
 // the factors; the pivoted Eigen-like fallback handles a degenerate H.
-template <class SH>
-__device__ __forceinline__ void warp0_scale_and_factor(SH& s, double s2, double* Hdst, Solver6& S) {
+__device__ __forceinline__ void warp_scale_and_factor(const double* sums, double s2, double* Hdst, Solver6& S) {
   const int lane = threadIdx.x & 31;
   double h[21];
 #pragma unroll
-  for (int k = 0; k < 21; ++k) h[k] = s.sums[k] * s2;
+  for (int k = 0; k < 21; ++k) h[k] = sums[k] * s2;
   if (lane == 0) {
 #pragma unroll
     for (int r = 0; r < 6; ++r)
@@ -484,11 +504,36 @@ __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src_gmem)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
 enum { kModeGlobal = 0, kModeImage = 1, kModeWindow = 2 };
+
+// xyz_cur = T_cur_from_ref * xyz_ref.  One CTA per pair (CS == 1): the pose is read from shared memory (s.pub, published by
+// warp 0's Gauss-Newton tail) at the point of use -- six 128-bit shared loads per feature instead of 24 registers that stay
+// live across the residual loops (at 128 registers per thread those were spilled to local memory, which misses the small L1
+// left beside 3 x 75 KB of shared memory: ncu r02c, 15 M local loads per launch, 17 % L1 hits).  Cluster per pair: every
+// warp runs the tail itself and keeps the pose in registers.
+template <int CS>
+__device__ __forceinline__ void sia_transform(const double* pub, const double (&R)[9], const double (&t)[3], double x, double y,
+                                              double z, double& xc, double& yc, double& zc) {
+  if constexpr (CS == 1) {
+    double r[12];
+    const uint32_t a = smem_u32(pub);
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r[2 * k]), "=d"(r[2 * k + 1]) : "r"(a + 16u * k));
+    xc = fma(r[0], x, fma(r[1], y, fma(r[2], z, r[9])));
+    yc = fma(r[3], x, fma(r[4], y, fma(r[5], z, r[10])));
+    zc = fma(r[6], x, fma(r[7], y, fma(r[8], z, r[11])));
+  } else {
+    xc = fma(R[0], x, fma(R[1], y, fma(R[2], z, t[0])));
+    yc = fma(R[3], x, fma(R[4], y, fma(R[5], z, t[1])));
+    zc = fma(R[6], x, fma(R[7], y, fma(R[8], z, t[2])));
+  }
+}
 
 template <bool CG>
 __device__ __forceinline__ void sia_world2cam(const CamDev& c, double x, double y, double& u, double& v) {
@@ -511,16 +556,28 @@ __device__ __forceinline__ void sia_world2cam(const CamDev& c, double x, double 
 // CG = false compiles the projection for the undistorted pinhole only (px = fx * uv + cx): the general vk::AbstractCamera
 // dispatch (radial-tangential pinhole, ATAN with its atan() slow path) stays out of the instruction stream of the
 // residual loop, which is what BASELINE's synthetic camera and any rectified stream run.
-template <int FPT, bool EVAL, int MAXT, int MINB, int CS, bool CG>
+//
+// UP = true (cluster geometry, every CTA alone on its SM): patches / H / factorisations of all levels are computed before
+// the first iteration (SiaUpT); shared memory then holds one patch array set per level.
+template <int FPT, bool EVAL, int MAXT, int MINB, int CS, bool CG, bool UP>
 __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
+  static_assert(!UP || (CS > 1 && FPT == 1 && !EVAL), "the upfront variant exists for the cluster geometry only");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   using SH = SiaSharedT<MAXT / 32, CS>;
+  using UPT = SiaUpT<MAXT / 32, CS>;
   SH& s = *reinterpret_cast<SH*>(smem_raw);
   constexpr int S = MAXT * FPT;  // feature slots of this CTA (== P.slots, checked on the host)
-  float* pat_ref = reinterpret_cast<float*>(smem_raw + ((sizeof(SH) + 15) & ~size_t(15)));
-  float2* pat_dxy = reinterpret_cast<float2*>(pat_ref + kPatchArea * S);
-  uint8_t* stage = reinterpret_cast<uint8_t*>(pat_dxy + kPatchArea * S);  // 16-byte aligned
-  uint4* win = reinterpret_cast<uint4*>(stage);                            // [kWinRows][S] 16-byte window rows
+  constexpr size_t kCtlBytes = ((sizeof(SH) + 15) & ~size_t(15)) + (UP ? ((sizeof(UPT) + 15) & ~size_t(15)) : 0);
+  UPT& up = *reinterpret_cast<UPT*>(smem_raw + ((sizeof(SH) + 15) & ~size_t(15)));  // only touched when UP
+  const int n_lvl_bufs = UP ? (P.max_level - P.min_level + 1) : 1;  // patch array sets (one per level when UP)
+  float* const pat_base = reinterpret_cast<float*>(smem_raw + kCtlBytes);
+  // set li (0 = coarsest level) : [16][S] f32 reference patch, then [16][S] float2 gradients
+  auto pat_ref_of = [&](int li) -> float* { return pat_base + (size_t)li * 3 * kPatchArea * S; };
+  auto pat_dxy_of = [&](int li) -> float2* { return reinterpret_cast<float2*>(pat_ref_of(li) + kPatchArea * S); };
+  float* pat_ref = pat_ref_of(0);
+  float2* pat_dxy = pat_dxy_of(0);
+  uint8_t* stage = reinterpret_cast<uint8_t*>(pat_base + (size_t)n_lvl_bufs * 3 * kPatchArea * S);  // 16-byte aligned
+  uint4* win = reinterpret_cast<uint4*>(stage);                                                      // [kWinRows][S] 16-byte window rows
 
   const unsigned crank = CS == 1 ? 0u : cluster_rank();
   const int pair = CS == 1 ? (int)blockIdx.x : (int)(blockIdx.x / CS);
@@ -612,46 +669,92 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       s.pub_done = 0; s.pub_slow = 0;
     }
   }
+  if constexpr (UP) {
+    // Latency of a live pair is a chain of first-touch DRAM reads (reference footprints and current-image windows of every
+    // level, ~0.7 us each): all of them are known now -- the footprints exactly, the windows at the initial pose, which the
+    // iterations move by a few pixels at most -- so every thread pulls its feature's rows of every level into L2 at once.
+    // (Only here: with the CTA alone on its SM the extra L1 requests cost nothing; in the batched geometries they do.)
+    const int i = tid;
+    if (i < n_loc) {
+      const double2 pxy = *reinterpret_cast<const double2*>(blob + (size_t)i * 16);
+      double xc, yc, zc;
+      sia_transform<CS>(s.pub, R, t, fx_[0], fy_[0], fz_[0], xc, yc, zc);
+      const double rz = fast_rcp(zc);
+      double ud, vd;
+      sia_world2cam<CG>(P.cam, div_rn(xc, zc, rz), div_rn(yc, zc, rz), ud, vd);
+      for (int level = P.max_level; level >= P.min_level; --level) {
+        const int W = P.w[level], Hh = P.h[level];
+        const double sc = 1.0 / (double)(1 << level);
+        const int ur = (int)(pxy.x * sc), vr = (int)(pxy.y * sc);
+        if (ur - 3 >= 0 && vr - 3 >= 0 && ur + 4 < W && vr + 4 < Hh) {
+          const uint8_t* p0 = job.ref_lvl[level] + (size_t)(vr - 3) * W + (ur - 3);
+#pragma unroll
+          for (int r = 0; r < 7; ++r) prefetch_l2(p0 + (size_t)r * W);
+        }
+        const int uc = (int)(ud * sc), vc = (int)(vd * sc);
+        if ((uint32_t)(W * Hh) + 32u > (uint32_t)P.stage_cap && uc - 4 >= 0 && vc - 4 >= 0 && uc + 4 < W && vc + 4 < Hh && ud >= 0.0 && vd >= 0.0) {
+          const uint8_t* p0 = job.cur_lvl[level] + (size_t)(vc - 4) * W + (uc - 4);
+#pragma unroll
+          for (int r = 0; r < kWinRows; ++r) prefetch_l2(p0 + (size_t)r * W);
+        }
+      }
+    }
+    if (tid == 0 && crank == 0) {  // the coarse current images that are staged whole
+      for (int level = P.max_level; level >= P.min_level; --level) {
+        const uint32_t nb = ((uint32_t)(P.w[level] * P.h[level]) + 15u) & ~15u;
+        if (nb + 16u <= (uint32_t)P.stage_cap) prefetch_l2_bulk(job.cur_lvl[level], nb);
+      }
+    }
+  }
   pair_sync<CS>();  // everyone is done with the staged blob (the patch arrays may be written) and, in the cluster
                     // variant, every CTA's shared memory is initialised before remote stores arrive
 
-  const int lvl_hi = EVAL ? P.eval_level : P.max_level;
-  const int lvl_lo = EVAL ? P.eval_level : P.min_level;
-  for (int level = lvl_hi; level >= lvl_lo; --level) {
+  // ---- one feature's window of the current image at this level (kModeWindow): 16 columns x 8 rows around the projection
+  //      with the pose the level starts from, requested with cp.async (completion: cp_async_wait_all by the same thread)
+  auto stage_window = [&](const int k, const int slot, const int W, const int Hh, const float scale, const uint8_t* cur_img) {
+    const double x = fx_[k], y = fy_[k], z = fz_[k];
+    double xc, yc, zc;
+    sia_transform<CS>(s.pub, R, t, x, y, z, xc, yc, zc);
+    const double rz = fast_rcp(zc);
+    double ud, vd;
+    sia_world2cam<CG>(P.cam, div_rn(xc, zc, rz), div_rn(yc, zc, rz), ud, vd);
+    const float u0 = __fmul_rn((float)ud, scale), v0 = __fmul_rn((float)vd, scale);
+    if (u0 >= 0.f && v0 >= 0.f && u0 < 1e6f && v0 < 1e6f) {
+      float tmp;
+      const int cu = floor_pos(__fadd_rn(u0, 0.5f), tmp), cv = floor_pos(__fadd_rn(v0, 0.5f), tmp);
+      {
+        // 16 columns x 8 rows around (round(u), round(v)): the 5x5 footprint stays inside for at least +-1.5 px of
+        // drift.  One 16-byte cp.async per row when columns round(u)-4 .. round(u)+3 fall into one 16-byte aligned
+        // block (and the pitch keeps every row 16-byte aligned), else two 8-byte copies from the 8-byte aligned column.
+        const int c4 = cu - 4, wy = cv - 4;
+        const bool one = ((c4 & 15) <= 8) && (W & 15) == 0;
+        const int wx = one ? (c4 & ~15) : (c4 & ~7);
+        if (wx >= 0 && wy >= 0 && wx + 16 <= W && wy + kWinRows <= Hh) {
+          wx_[k] = wx; wy_[k] = wy;
+          const uint8_t* src = cur_img + (size_t)wy * W + wx;
+          if (one) {
+#pragma unroll
+            for (int r = 0; r < kWinRows; ++r) cp_async16(win + r * S + slot, src + (size_t)r * W);
+          } else {
+#pragma unroll
+            for (int r = 0; r < kWinRows; ++r) {
+              cp_async8(reinterpret_cast<uint8_t*>(win + r * S + slot), src + (size_t)r * W);
+              cp_async8(reinterpret_cast<uint8_t*>(win + r * S + slot) + 8, src + (size_t)r * W + 8);
+            }
+          }
+        }
+      }
+    }
+  };
+  // ---- precomputeReferencePatches (:84-145) of one level into the patch arrays (pr, pd): visibility bits, the f32 patch and
+  //      its gradients, and the per-feature gradient moments m_* the H reduction needs.  `with_windows`: also request the
+  //      current-image windows (between the footprint loads and the arithmetic, so that both latencies overlap).
+  auto level_patches = [&](const int level, float* pr, float2* pd, const float* pr_stale, const int mode, const bool with_windows,
+                           double (&m_sxx)[FPT], double (&m_sxy)[FPT], double (&m_syy)[FPT], double (&m_cnt)[FPT]) {
     const int W = P.w[level], Hh = P.h[level];
     const float scale = 1.0f / (float)(1 << level);
-    const double jscale = P.cam.fx / (double)(1 << level);  // focal_length / (1<<level_)  (:140)
     const uint8_t* ref_img = job.ref_lvl[level];
     const uint8_t* cur_img = job.cur_lvl[level];
-
-    // ---- how the current image of this level reaches the residual loop --------------------------
-    const uint32_t img_bytes = ((uint32_t)(W * Hh) + 15u) & ~15u;
-    int mode = kModeGlobal;
-    if (img_bytes + 16u <= (uint32_t)P.stage_cap) mode = kModeImage;
-    else if (P.use_windows && (W & 7) == 0 && kWinBytes * S <= P.stage_cap) mode = kModeWindow;
-    if (mode == kModeImage && tid == 0) {
-      s.mbar_phase ^= 1u;
-      fence_proxy_async();
-      mbar_expect_tx(&s.mbar, img_bytes);
-      tma_bulk_g2s(stage, cur_img, img_bytes, &s.mbar);
-    }
-    if (cta_leader) s.st[g & 1u].old_model = s.st[g & 1u].model;  // optimizeGaussNewton: ModelType old_model(model) [EXT]
-    if constexpr (CS == 1) {
-      // the pose lives in shared memory between uses: re-reading it here keeps 24 registers free during the residual loops
-#pragma unroll
-      for (int k = 0; k < 9; ++k) R[k] = s.pub[k];
-      t[0] = s.pub[9]; t[1] = s.pub[10]; t[2] = s.pub[11];
-    }
-    // next level: pull its current image (coarse levels, staged whole) into L2 while this level iterates
-    if (P.use_prefetch && tid == 0 && crank == 0 && level > lvl_lo) {
-      const uint32_t nb = ((uint32_t)(P.w[level - 1] * P.h[level - 1]) + 15u) & ~15u;
-      if (nb + 16u <= (uint32_t)P.stage_cap) prefetch_l2_bulk(job.cur_lvl[level - 1], nb);
-    }
-
-    SIA_DBG(long long tq0 = 0;)
-      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) tq0 = clock64();)
-    // ---- precomputeReferencePatches (:84-145), one feature per thread -----------------------
-    double m_sxx[FPT], m_sxy[FPT], m_syy[FPT], m_cnt[FPT];
 #pragma unroll
     for (int k = 0; k < FPT; ++k) {
       m_sxx[k] = m_sxy[k] = m_syy[k] = m_cnt[k] = 0.0;
@@ -672,42 +775,9 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         for (int r = 0; r < 7; ++r) fetch7_g64(ref_img, (vi - 3 + r) * W + (ui - 3), rlo[r], rhi[r]);
       }
       // ---- current-image window of this feature (fine levels): projected with the pose the level starts from
-      wx_[k] = wy_[k] = -(1 << 20);
-      if (((vis_mask >> k) & 1u) && mode == kModeWindow) {
-        const double x = fx_[k], y = fy_[k], z = fz_[k];
-        const double xc = fma(R[0], x, fma(R[1], y, fma(R[2], z, t[0])));
-        const double yc = fma(R[3], x, fma(R[4], y, fma(R[5], z, t[1])));
-        const double zc = fma(R[6], x, fma(R[7], y, fma(R[8], z, t[2])));
-        const double rz = fast_rcp(zc);
-        double ud, vd;
-        sia_world2cam<CG>(P.cam, div_rn(xc, zc, rz), div_rn(yc, zc, rz), ud, vd);
-        const float u0 = __fmul_rn((float)ud, scale), v0 = __fmul_rn((float)vd, scale);
-        if (u0 >= 0.f && v0 >= 0.f && u0 < 1e6f && v0 < 1e6f) {
-          float tmp;
-          const int cu = floor_pos(__fadd_rn(u0, 0.5f), tmp), cv = floor_pos(__fadd_rn(v0, 0.5f), tmp);
-          if (mode == kModeWindow) {
-            // 16 columns x 8 rows around (round(u), round(v)): the 5x5 footprint stays inside for at least +-1.5 px of
-            // drift.  One 16-byte cp.async per row when columns round(u)-4 .. round(u)+3 fall into one 16-byte aligned
-            // block (and the pitch keeps every row 16-byte aligned), else two 8-byte copies from the 8-byte aligned column.
-            const int c4 = cu - 4, wy = cv - 4;
-            const bool one = ((c4 & 15) <= 8) && (W & 15) == 0;
-            const int wx = one ? (c4 & ~15) : (c4 & ~7);
-            if (wx >= 0 && wy >= 0 && wx + 16 <= W && wy + kWinRows <= Hh) {
-              wx_[k] = wx; wy_[k] = wy;
-              const uint8_t* src = cur_img + (size_t)wy * W + wx;
-              if (one) {
-#pragma unroll
-                for (int r = 0; r < kWinRows; ++r) cp_async16(win + r * S + slot, src + (size_t)r * W);
-              } else {
-#pragma unroll
-                for (int r = 0; r < kWinRows; ++r) {
-                  cp_async8(reinterpret_cast<uint8_t*>(win + r * S + slot), src + (size_t)r * W);
-                  cp_async8(reinterpret_cast<uint8_t*>(win + r * S + slot) + 8, src + (size_t)r * W + 8);
-                }
-              }
-            }
-          }
-        }
+      if (with_windows) {
+        wx_[k] = wy_[k] = -(1 << 20);
+        if (((vis_mask >> k) & 1u) && mode == kModeWindow) stage_window(k, slot, W, Hh, scale, cur_img);
       }
       if (ok) {
         float wtl, wtr, wbl, wbr;
@@ -737,8 +807,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
               const float val = b1[x + 1];
               const float dx = __fmul_rn(0.5f, __fsub_rn(b1[x + 2], b1[x]));
               const float dy = __fmul_rn(0.5f, __fsub_rn(b2[x + 1], b0[x + 1]));
-              pat_ref[p * S + slot] = val;
-              pat_dxy[p * S + slot] = make_float2(dx, dy);
+              pr[p * S + slot] = val;
+              pd[p * S + slot] = make_float2(dx, dy);
               sxx = fma((double)dx, (double)dx, sxx);
               sxy = fma((double)dx, (double)dy, sxy);
               syy = fma((double)dy, (double)dy, syy);
@@ -755,28 +825,124 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         // and a zeroed Jacobian (jacobian_cache_.setZero() per level, :64).  Unreachable for
         // dyadic pyramids but kept bit-faithful.
 #pragma unroll
-        for (int p = 0; p < kPatchArea; ++p) pat_dxy[p * S + slot] = make_float2(0.f, 0.f);
+        for (int p = 0; p < kPatchArea; ++p) pd[p * S + slot] = make_float2(0.f, 0.f);
+        if (pr_stale)  // per-level arrays (upfront variant): the stale patch is the previous level's
+          for (int p = 0; p < kPatchArea; ++p) pr[p * S + slot] = pr_stale[p * S + slot];
         m_cnt[k] = 1.0;
       }
     }
+  };
+
+  const int lvl_hi = EVAL ? P.eval_level : P.max_level;
+  const int lvl_lo = EVAL ? P.eval_level : P.min_level;
+  unsigned vis_levels = 0;  // UP: bit li = this thread's feature is visible at level lvl_hi - li (set-only across levels)
+  if constexpr (UP) {
+    SIA_DBG(long long tu0 = 0;)
+      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) tu0 = clock64();)
+    // ---- all levels' reference patches and per-warp H partials, coarse to fine (the visibility mask accumulates in that order)
+    for (int level = lvl_hi; level >= lvl_lo; --level) {
+      const int li = lvl_hi - level;
+      double m_sxx[FPT], m_sxy[FPT], m_syy[FPT], m_cnt[FPT];
+      level_patches(level, pat_ref_of(li), pat_dxy_of(li), li > 0 ? pat_ref_of(li - 1) : (const float*)nullptr, kModeGlobal, false,
+                    m_sxx, m_sxy, m_syy, m_cnt);
+      vis_levels |= (vis_mask & 1u) << li;
+      warp_h_partials<FPT>(
+          [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
+            x = fx_[k]; y = fy_[k]; zi = fzi_[k]; sxx = m_sxx[k]; sxy = m_sxy[k]; syy = m_syy[k]; cnt = m_cnt[k];
+          },
+          &up.hpart[li][warp * kPartK]);
+    }
+    __syncthreads();
+    // ---- one exchange for all levels: every CTA receives every CTA's per-level sums (DSMEM), one cluster barrier
+    const int nlv = lvl_hi - lvl_lo + 1;
+    for (int e = tid; e < nlv * kPartK; e += T) {
+      const int li = e / kPartK, j = e - li * kPartK;
+      double acc = 0.0;
+      for (int wv = 0; wv < nwarps; ++wv) acc += up.hpart[li][wv * kPartK + j];
+#pragma unroll
+      for (int r = 0; r < CS; ++r) st_cluster_f64(&up.hsum_cta[li][crank][j], (unsigned)r, acc);
+    }
+    pair_sync<CS>();
+    // ---- every CTA scales and factorises its own copy, the levels dealt to its warps
+    for (int li = warp; li < nlv; li += nwarps) {
+      if (lane < kPartK) {
+        double acc = 0.0;
+#pragma unroll
+        for (int r = 0; r < CS; ++r) acc += up.hsum_cta[li][r][lane];
+        up.sums[li][lane] = acc;
+      }
+      __syncwarp();
+      const double js = P.cam.fx / (double)(1 << (lvl_hi - li));
+      warp_scale_and_factor(up.sums[li], js * js, up.Htot[li], up.sol[li]);
+    }
+    __syncthreads();
+      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) s.tkx[2] += clock64() - tu0;)
+  }
+  for (int level = lvl_hi; level >= lvl_lo; --level) {
+    const int W = P.w[level], Hh = P.h[level];
+    const float scale = 1.0f / (float)(1 << level);
+    const double jscale = P.cam.fx / (double)(1 << level);  // focal_length / (1<<level_)  (:140)
+    const uint8_t* cur_img = job.cur_lvl[level];
+
+    // ---- how the current image of this level reaches the residual loop --------------------------
+    const uint32_t img_bytes = ((uint32_t)(W * Hh) + 15u) & ~15u;
+    int mode = kModeGlobal;
+    if (img_bytes + 16u <= (uint32_t)P.stage_cap) mode = kModeImage;
+    else if (P.use_windows && (W & 7) == 0 && kWinBytes * S <= P.stage_cap) mode = kModeWindow;
+    if (mode == kModeImage && tid == 0) {
+      s.mbar_phase ^= 1u;
+      fence_proxy_async();
+      mbar_expect_tx(&s.mbar, img_bytes);
+      tma_bulk_g2s(stage, cur_img, img_bytes, &s.mbar);
+    }
+    if (cta_leader) s.st[g & 1u].old_model = s.st[g & 1u].model;  // optimizeGaussNewton: ModelType old_model(model) [EXT]
+    // next level: pull its current image (coarse levels, staged whole) into L2 while this level iterates
+    if (P.use_prefetch && tid == 0 && crank == 0 && level > lvl_lo) {
+      const uint32_t nb = ((uint32_t)(P.w[level - 1] * P.h[level - 1]) + 15u) & ~15u;
+      if (nb + 16u <= (uint32_t)P.stage_cap) prefetch_l2_bulk(job.cur_lvl[level - 1], nb);
+    }
+
+    SIA_DBG(long long tq0 = 0;)
+      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) tq0 = clock64();)
     SIA_DBG(long long tq1 = 0;)
-      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { tq1 = clock64(); s.tk[7] += tq1 - tq0; })
-    pair_sum_h_to_warp0<FPT, CS, SH>(
-        [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
-          x = fx_[k]; y = fy_[k]; zi = fzi_[k]; sxx = m_sxx[k]; sxy = m_sxy[k]; syy = m_syy[k]; cnt = m_cnt[k];
-          // opaque to the optimiser: otherwise the level-invariant Jacobian rows are hoisted out of the level loop and
-          // parked in local memory (17 doubles per thread, written once and re-read every level)
-          asm volatile("" : "+d"(x), "+d"(y), "+d"(zi));
-        },
-        s, nwarps, P.xg, pair);
-    // The scaling and LDL^T factorisation of this level's H is serial work nobody needs before the first solve: warp 0
-    // does it while the other warps already run the first residual pass; its results (s.sol_tot, s.Htot) become
-    // visible to everybody through the barrier of that pass.
     SIA_DBG(long long tq2 = 0;)
+    const Solver6* sol_level = &s.sol_tot;  // factorisation of this level's H over its visible set
+    if constexpr (!UP) {
+      // ---- precomputeReferencePatches (:84-145), one feature per thread; the windows of the current image are requested
+      //      between the footprint loads and the patch arithmetic
+      double m_sxx[FPT], m_sxy[FPT], m_syy[FPT], m_cnt[FPT];
+      level_patches(level, pat_ref, pat_dxy, (const float*)nullptr, mode, true, m_sxx, m_sxy, m_syy, m_cnt);
+      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { tq1 = clock64(); s.tk[7] += tq1 - tq0; })
+      pair_sum_h_to_warp0<FPT, CS, SH>(
+          [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
+            x = fx_[k]; y = fy_[k]; zi = fzi_[k]; sxx = m_sxx[k]; sxy = m_sxy[k]; syy = m_syy[k]; cnt = m_cnt[k];
+            // opaque to the optimiser: otherwise the level-invariant Jacobian rows are hoisted out of the level loop and
+            // parked in local memory (17 doubles per thread, written once and re-read every level)
+            asm volatile("" : "+d"(x), "+d"(y), "+d"(zi));
+          },
+          s, nwarps, P.xg, pair);
+      // The scaling and LDL^T factorisation of this level's H is serial work nobody needs before the first solve: warp 0
+      // does it while the other warps already run the first residual pass; its results (s.sol_tot, s.Htot) become
+      // visible to everybody through the barrier of that pass.
       SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { tq2 = clock64(); s.tkx[0] += tq2 - tq1; })
-    if (warp == 0) {
-      if (leader) s.sum_vis += (int)s.sums[21];
-      warp0_scale_and_factor(s, jscale * jscale, s.Htot, s.sol_tot);
+      if (warp == 0) {
+        if (leader) s.sum_vis += (int)s.sums[21];
+        warp_scale_and_factor(s.sums, jscale * jscale, s.Htot, s.sol_tot);
+      }
+    } else {
+      // everything pose independent was prepared before the first level: select this level's arrays, request the windows
+      const int li = lvl_hi - level;
+      pat_ref = pat_ref_of(li);
+      pat_dxy = pat_dxy_of(li);
+      sol_level = &up.sol[li];
+      vis_mask = (vis_levels >> li) & 1u;
+#pragma unroll
+      for (int k = 0; k < FPT; ++k) {
+        wx_[k] = wy_[k] = -(1 << 20);
+        if (((vis_mask >> k) & 1u) && mode == kModeWindow) stage_window(k, tid + k * T, W, Hh, scale, cur_img);
+      }
+      if (leader) s.sum_vis += (int)up.sums[li][21];
+      SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { tq1 = tq2 = clock64(); s.tk[7] += tq1 - tq0; })
     }
     if (mode == kModeImage) mbar_wait(&s.mbar, s.mbar_phase);
     if (mode == kModeWindow) cp_async_wait_all();  // each thread reads only the window it copied itself
@@ -797,9 +963,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         if (!((vis_mask >> k) & 1u)) continue;
         const int slot = tid + k * T;
         const double x = fx_[k], y = fy_[k], z = fz_[k];
-        const double xc = fma(R[0], x, fma(R[1], y, fma(R[2], z, t[0])));
-        const double yc = fma(R[3], x, fma(R[4], y, fma(R[5], z, t[1])));
-        const double zc = fma(R[6], x, fma(R[7], y, fma(R[8], z, t[2])));
+        double xc, yc, zc;
+        sia_transform<CS>(s.pub, R, t, x, y, z, xc, yc, zc);
         const double rz = fast_rcp(zc);
         double ud, vd;
         sia_world2cam<CG>(P.cam, div_rn(xc, zc, rz), div_rn(yc, zc, rz), ud, vd);  // [EXT] world2cam(project2d(xyz))
@@ -956,7 +1121,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           return nullptr;
         }
         if (leader) s.h_is_tot = 1;
-        return &s.sol_tot;
+        return sol_level;
       };
       SIA_DBG(long long ti2 = 0;)
       if constexpr (CS == 1) {
@@ -992,7 +1157,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         if (s.pub_slow) {
           slow_sum_h();
           if (warp == 0) {
-            warp0_scale_and_factor(s, jscale * jscale, s.Hs, s.sol_cur);
+            warp_scale_and_factor(s.sums, jscale * jscale, s.Hs, s.sol_cur);
             if (leader) s.h_is_tot = 0;
             if (EVAL) {
               if (leader) eval_outputs();
@@ -1009,12 +1174,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           }
           __syncthreads();  // barrier C
         }
-        if (!EVAL) {
-#pragma unroll
-          for (int k = 0; k < 9; ++k) R[k] = s.pub[k];
-          t[0] = s.pub[9]; t[1] = s.pub[10]; t[2] = s.pub[11];
-          done = s.pub_done;
-        }
+        if (!EVAL) done = s.pub_done;  // the new pose stays in s.pub: sia_transform reads it there
       } else {
         // Cluster per pair: every warp of every CTA adds the partials in the same order and runs the tail redundantly in
         // registers (bit-identical everywhere), which saves a second cluster barrier + DSMEM broadcast per iteration.
@@ -1027,7 +1187,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         } else {
           slow_sum_h();
           if (warp == 0) {
-            warp0_scale_and_factor(s, jscale * jscale, s.Hs, s.sol_cur);
+            warp_scale_and_factor(s.sums, jscale * jscale, s.Hs, s.sol_cur);
             if (leader) s.h_is_tot = 0;
           }
           if (EVAL && leader) eval_outputs();
@@ -1069,7 +1229,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
   if (leader) {
     if (P.T_out) pose_to_rt12(s.st[g & 1u].model, P.T_out + 12 * (size_t)pair);
     if (P.H_out)
-      for (int k = 0; k < 36; ++k) P.H_out[36 * (size_t)pair + k] = s.h_is_tot ? s.Htot[k] : s.Hs[k];
+      for (int k = 0; k < 36; ++k)  // H_ of the last residual pass: the level's H (of the finest level run) or the slow path's
+        P.H_out[36 * (size_t)pair + k] = s.h_is_tot ? (UP ? up.Htot[lvl_hi - lvl_lo][k] : s.Htot[k]) : s.Hs[k];
     if (P.stats) {
       svo_b200_sia_stats st;
       st.n_iters = s.n_iters; st.sum_visible = s.sum_vis; st.sum_in_image = s.sum_in;
@@ -1080,8 +1241,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
     if (CS == 1 && P.xg.world > 1) P.xg.peer[P.xg.rank][pair].xseq = s.xg_seq;
 #if SVO_SIA_DEBUG
     if (SVO_SIA_DEBUG && P.debug && (pair == 0 || pair == (int)(gridDim.x / CS) / 2 || pair == (int)(gridDim.x / CS) - 1))
-      printf("[sia dbg] pair %d iters %d cycles: setup %lld pass %lld reduce %lld tail %lld (solve %lld update %lld) total %lld | setup parts: loads+patches %lld hsum %lld factor+wait %lld\n", pair, s.n_iters,
-             s.tk[0], s.tk[1], s.tk[2], s.tk[3], s.tk[5], s.tk[6], (long long)clock64() - s.tk[4], s.tk[7], s.tkx[0], s.tkx[1]);
+      printf("[sia dbg] pair %d iters %d cycles: setup %lld pass %lld reduce %lld tail %lld (solve %lld update %lld) total %lld | setup parts: loads+patches %lld hsum %lld factor+wait %lld upfront %lld\n", pair, s.n_iters,
+             s.tk[0], s.tk[1], s.tk[2], s.tk[3], s.tk[5], s.tk[6], (long long)clock64() - s.tk[4], s.tk[7], s.tkx[0], s.tkx[1], s.tkx[2]);
 #endif
   }
 }
@@ -1102,6 +1263,7 @@ struct SiaBatchState {
   HostBuf h_in, h_out;
   size_t o_T = 0, o_H = 0, o_vis = 0, o_stats = 0, out_bytes = 0;
   int threads = 0, fpt = 1, cluster = 1;
+  bool upfront = false;  // cluster geometry with all levels prepared before the first iteration (SiaUpT)
   size_t smem = 0;
   bool staged = false;
 };
@@ -1136,6 +1298,7 @@ static int g_sia_prefetch = 1;    // SVO_B200_SIA_PREFETCH=0: no bulk L2 prefetc
                                   // (Per-feature L2 prefetches of the next level's footprints were measured and removed: the extra
                                   // uncoalesced requests cost more L1 time than the DRAM latency they hide.)
 static int g_sia_cluster = -1;    // SVO_B200_SIA_CLUSTER: force the CTAs per pair (1, 2, 4, 8); -1 = by batch size
+static int g_sia_upfront = 1;     // SVO_B200_SIA_UPFRONT=0: the cluster geometry prepares each level when it reaches it (round-2a behaviour)
 static int g_sia_plain = 1;       // SVO_B200_SIA_PLAIN=0: the undistorted pinhole runs the general-camera instantiation too
 static int g_sia_fpt2 = 1;        // SVO_B200_SIA_FPT2: <= 320 features per CTA as 160 threads x 2 features: 1 = three CTAs per SM (default,
                                   // measured best for full batches), 2 = two CTAs per SM with windows, 0 = 320 threads x 1 feature
@@ -1151,6 +1314,7 @@ static void read_env_once() {
   if (const char* e = getenv("SVO_B200_SIA_CLUSTER")) g_sia_cluster = atoi(e);
   if (const char* e = getenv("SVO_B200_SIA_FPT2")) g_sia_fpt2 = atoi(e);
   if (const char* e = getenv("SVO_B200_SIA_PLAIN")) g_sia_plain = atoi(e) != 0;
+  if (const char* e = getenv("SVO_B200_SIA_UPFRONT")) g_sia_upfront = atoi(e) != 0;
 }
 
 // Launch geometry for a batch of B pairs with at most max_feat features each.
@@ -1166,8 +1330,14 @@ static size_t sia_shared_bytes(int threads, int cluster) {
   return sizeof(SiaSharedT<16, 1>);
 }
 
-static int pick_launch(svo_b200_ctx* ctx, int B, int max_feat, int& threads, int& fpt, int& cluster, int& stage_cap,
-                       size_t& smem) {
+static size_t sia_upfront_bytes(int cluster) {
+  if (cluster == 2) return sizeof(SiaUpT<3, 2>);
+  if (cluster == 4) return sizeof(SiaUpT<3, 4>);
+  return sizeof(SiaUpT<3, 8>);
+}
+
+static int pick_launch(svo_b200_ctx* ctx, int B, int max_feat, int n_lvl, int& threads, int& fpt, int& cluster, bool& upfront,
+                       int& stage_cap, size_t& smem) {
   read_env_once();
   if (max_feat > 1024)
     return set_err(ctx, SVO_B200_ELIMIT, "sparse_img_align: %d features per pair > 1024 (shared-memory patch cache)", max_feat);
@@ -1200,10 +1370,21 @@ static int pick_launch(svo_b200_ctx* ctx, int B, int max_feat, int& threads, int
     if (fpt2 && max_feat <= 320) { fpt = 2; threads = 160; }
   }
   const int slots = threads * fpt;
-  const size_t base = ((sia_shared_bytes(threads, cluster) + 15) & ~size_t(15)) + (size_t)3 * kPatchArea * slots * sizeof(float);
+  size_t base = ((sia_shared_bytes(threads, cluster) + 15) & ~size_t(15)) + (size_t)3 * kPatchArea * slots * sizeof(float);
+  // cluster geometry with every CTA alone on its SM: one patch array set per level, everything pose independent prepared
+  // before the first iteration (the launch asks for the 4-CTA instantiation; 2 and 8 keep the per-level flow)
+  upfront = false;
+  if (cluster == 4 && g_sia_upfront && ctx->sia_upfront != 0 && B * cluster <= ctx->sm_count && n_lvl >= 1 && n_lvl <= SVO_B200_MAX_LEVELS) {
+    const size_t base_up = ((sia_shared_bytes(threads, cluster) + 15) & ~size_t(15)) + ((sia_upfront_bytes(cluster) + 15) & ~size_t(15)) +
+                           (size_t)n_lvl * 3 * kPatchArea * slots * sizeof(float);
+    if (base_up + (size_t)g_sia_stage_kb * 1024 + 1024 <= (size_t)ctx->max_smem_optin) {
+      upfront = true;
+      base = base_up;
+    }
+  }
   // shared memory one CTA may use so that the intended number of CTAs stays resident per SM (228 KB per SM, 1 KB
   // reserved per CTA)
-  const int resident = cluster > 1 ? 2 : (threads == 160 ? (fpt2 == 2 ? 2 : 3) : threads <= 384 ? 2 : 1);
+  const int resident = upfront ? 1 : cluster > 1 ? 2 : (threads == 160 ? (fpt2 == 2 ? 2 : 3) : threads <= 384 ? 2 : 1);
   size_t budget = (size_t)ctx->max_smem_optin;
   const size_t per_cta = (size_t)(228 * 1024) / resident - 1024;
   if (per_cta < budget) budget = per_cta;
@@ -1221,7 +1402,7 @@ static int pick_launch(svo_b200_ctx* ctx, int B, int max_feat, int& threads, int
 }
 
 template <bool EVAL>
-static int launch_sia(svo_b200_ctx* ctx, const SiaParams& P, int B, int threads, int fpt, int cluster, size_t smem) {
+static int launch_sia(svo_b200_ctx* ctx, const SiaParams& P, int B, int threads, int fpt, int cluster, bool upfront, size_t smem) {
   auto go = [&](auto kern) -> int {
     SVO_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // ask for the full shared-memory carveout so that two CTAs of ~95 KB fit one SM
@@ -1246,21 +1427,25 @@ static int launch_sia(svo_b200_ctx* ctx, const SiaParams& P, int B, int threads,
     SVO_CUDA_CHECK(ctx, cudaGetLastError());
     return 0;
   };
-  // the undistorted pinhole gets its own instantiation of the two geometries that carry the throughput / latency figures
+  // the undistorted pinhole gets its own instantiation of the geometries that carry the throughput / latency figures
   // (the general-camera code also handles it; EVAL and the rarely used geometries are compiled once)
   const bool plain = !EVAL && !P.cam.distorted && P.cam.model == SVO_B200_CAM_PINHOLE && g_sia_plain;
-  if (cluster == 2) return go(sia_kernel<1, EVAL, 96, 2, 2, true>);
-  if (cluster == 4) return plain ? go(sia_kernel<1, EVAL, 96, 2, 4, EVAL>) : go(sia_kernel<1, EVAL, 96, 2, 4, true>);
-  if (cluster == 8) return go(sia_kernel<1, EVAL, 96, 2, 8, true>);
+  if (cluster == 2) return go(sia_kernel<1, EVAL, 96, 2, 2, true, false>);
+  if (cluster == 4) {
+    if (upfront && !EVAL)
+      return plain ? go(sia_kernel<1, EVAL, 96, 1, 4, EVAL, !EVAL>) : go(sia_kernel<1, EVAL, 96, 1, 4, true, !EVAL>);
+    return plain ? go(sia_kernel<1, EVAL, 96, 2, 4, EVAL, false>) : go(sia_kernel<1, EVAL, 96, 2, 4, true, false>);
+  }
+  if (cluster == 8) return go(sia_kernel<1, EVAL, 96, 2, 8, true, false>);
   // <= 384 threads: cap registers so that two CTAs are resident per SM
   if (fpt == 1) {
-    if (threads <= 320 && g_sia_minb == 3) return go(sia_kernel<1, EVAL, 320, 3, 1, true>);
-    if (threads <= 320) return plain ? go(sia_kernel<1, EVAL, 320, 2, 1, EVAL>) : go(sia_kernel<1, EVAL, 320, 2, 1, true>);
-    if (threads <= 384) return go(sia_kernel<1, EVAL, 384, 2, 1, true>);
-    return go(sia_kernel<1, EVAL, 512, 1, 1, true>);
+    if (threads <= 320 && g_sia_minb == 3) return go(sia_kernel<1, EVAL, 320, 3, 1, true, false>);
+    if (threads <= 320) return plain ? go(sia_kernel<1, EVAL, 320, 2, 1, EVAL, false>) : go(sia_kernel<1, EVAL, 320, 2, 1, true, false>);
+    if (threads <= 384) return go(sia_kernel<1, EVAL, 384, 2, 1, true, false>);
+    return go(sia_kernel<1, EVAL, 512, 1, 1, true, false>);
   }
-  if (threads == 160) return plain ? go(sia_kernel<2, EVAL, 160, 3, 1, EVAL>) : go(sia_kernel<2, EVAL, 160, 3, 1, true>);
-  return go(sia_kernel<2, EVAL, 512, 1, 1, true>);
+  if (threads == 160) return plain ? go(sia_kernel<2, EVAL, 160, 3, 1, EVAL, false>) : go(sia_kernel<2, EVAL, 160, 3, 1, true, false>);
+  return go(sia_kernel<2, EVAL, 512, 1, 1, true, false>);
 }
 
 static inline int pad16(int n) { return (n + 15) / 16 * 16; }
@@ -1365,6 +1550,13 @@ int svo_b200_sia_config(svo_b200_ctx* ctx, int ctas_per_pair, int features_per_t
   return 0;
 }
 
+int svo_b200_sia_upfront(svo_b200_ctx* ctx, int mode) {
+  if (!ctx) return SVO_B200_EINVAL;
+  if (mode < -1 || mode > 1) return set_err(ctx, SVO_B200_EINVAL, "sia_upfront: mode must be -1, 0 or 1");
+  ctx->sia_upfront = mode;
+  return 0;
+}
+
 int svo_b200_sia_batch_stage(svo_b200_ctx* ctx, int B, const svo_b200_frame* const* ref,
                              const svo_b200_frame* const* cur, const svo_b200_camera* cam,
                              const svo_b200_sia_options* opt, const double* T, const int* feat_offset,
@@ -1393,7 +1585,8 @@ int svo_b200_sia_batch_stage(svo_b200_ctx* ctx, int B, const svo_b200_frame* con
   int rc = fill_common(ctx, st.P, ref[0], cam, opt);
   if (rc) return rc;
   int stage_cap = 0;
-  rc = pick_launch(ctx, B, st.max_feat, st.threads, st.fpt, st.cluster, stage_cap, st.smem);
+  rc = pick_launch(ctx, B, st.max_feat, opt->max_level - opt->min_level + 1, st.threads, st.fpt, st.cluster, st.upfront, stage_cap,
+                   st.smem);
   if (rc) return rc;
   st.P.stage_cap = stage_cap;
   st.P.slots = st.threads * st.fpt;
@@ -1452,7 +1645,7 @@ int svo_b200_sia_batch_run(svo_b200_ctx* ctx) {
   if (!ctx || !ctx->sia || !ctx->sia->staged) return set_err(ctx, SVO_B200_EINVAL, "sia_batch_run: nothing staged");
   cudaSetDevice(ctx->device);
   SiaBatchState& st = *ctx->sia;
-  return launch_sia<false>(ctx, st.P, st.B, st.threads, st.fpt, st.cluster, st.smem);
+  return launch_sia<false>(ctx, st.P, st.B, st.threads, st.fpt, st.cluster, st.upfront, st.smem);
 }
 
 int svo_b200_sia_batch_fetch(svo_b200_ctx* ctx, double* T_out, uint8_t* visible_out, double* H_out,
@@ -1555,7 +1748,7 @@ int svo_b200_sparse_residuals(svo_b200_ctx* ctx, const svo_b200_frame* ref, cons
   st.P.Jres_out = reinterpret_cast<double*>(ds + o_j);
   st.P.chi2_out = reinterpret_cast<double*>(ds + o_c);
   st.P.n_meas_out = reinterpret_cast<long long*>(ds + o_n);
-  if ((rc = launch_sia<true>(ctx, st.P, 1, st.threads, st.fpt, st.cluster, st.smem))) return rc;
+  if ((rc = launch_sia<true>(ctx, st.P, 1, st.threads, st.fpt, st.cluster, false, st.smem))) return rc;
   double Tdummy[12];
   if ((rc = svo_b200_sia_batch_fetch(ctx, Tdummy, visible_io, H_out, nullptr))) return rc;
   if (ref_patch_out) SVO_CUDA_CHECK(ctx, cudaMemcpy(ref_patch_out, ds + o_rp, sizeof(float) * 16 * (size_t)N, cudaMemcpyDeviceToHost));

@@ -18,14 +18,20 @@ RES_TOL = 1e-4
 #   cta-1fpt    one CTA per pair, one feature per thread (320 / 384 / 512 threads)
 #   cta-2fpt    one CTA per pair, two features per thread (160 threads for <= 320 features: the full-batch kernel)
 #   cluster-4/8 the pair's features split over a thread-block cluster, partial sums exchanged through DSMEM
-GEOMETRIES = {"auto": (-1, 0), "cta-1fpt": (1, 1), "cta-2fpt": (1, 2), "cluster-4": (4, 0), "cluster-8": (8, 0)}
+# third entry: svo_b200_sia_upfront mode (-1 = all levels prepared before the first iteration where the geometry allows it,
+# 0 = every level prepared when it is reached)
+GEOMETRIES = {"auto": (-1, 0, -1), "cta-1fpt": (1, 1, -1), "cta-2fpt": (1, 2, -1), "cluster-4": (4, 0, -1),
+              "cluster-4-per-level": (4, 0, 0), "cluster-8": (8, 0, -1)}
 
 
 @pytest.fixture(params=list(GEOMETRIES), autouse=True)
 def geometry(request, ctx):
-    ctx.sia_config(*GEOMETRIES[request.param])
+    g = GEOMETRIES[request.param]
+    ctx.sia_config(g[0], g[1])
+    ctx.sia_upfront(g[2])
     yield request.param
     ctx.sia_config(-1, 0)
+    ctx.sia_upfront(-1)
 
 
 def _run_both(ctx, oracle, d, max_level, min_level, n_iter=30, T0=None, trace=True):
