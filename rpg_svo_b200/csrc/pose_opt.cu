@@ -56,6 +56,7 @@ struct PoseOptShared {
   double sums[kPoK];
   double R[9], t[3];
   double A[36];
+  double cov[36];
   double med[2];
   Pose T, T_old;   // frame->T_f_w_ and the roll-back copy (warp 0)
   double chi2;
@@ -238,18 +239,38 @@ __global__ void __launch_bounds__(kPoThreads) pose_opt_kernel(PoseOptParams P) {
   PO_DBG(long long tc[8]; tc[0] = clock64();)
 
   // ---- per-observation constants, once ------------------------------------------------------------
+  // (the loads of an observation do not wait for its has_point flag, and two observations per thread are in flight
+  // together: the phase is a chain of first-touch global loads, not arithmetic)
   double cnt[1] = {0.0};
-  for (int i = tid; i < N; i += kPoThreads) {
-    const uint8_t hp = has_point[i];
-    o.valid[i] = hp;
-    if (!hp) continue;
-    const size_t g = (size_t)(o0 + i);
-    o.px[i] = P.pos[3 * g]; o.py[i] = P.pos[3 * g + 1]; o.pz[i] = P.pos[3 * g + 2];
-    const double f2 = P.f[3 * g + 2];
-    o.fxn[i] = P.f[3 * g] / f2;  // vk::project2d(f)
-    o.fyn[i] = P.f[3 * g + 1] / f2;
-    o.sic[i] = 1.0 / (double)(1 << P.level[g]);
-    cnt[0] += 1.0;
+  for (int i0 = tid; i0 < N; i0 += 2 * kPoThreads) {
+    const int i1 = i0 + kPoThreads;
+    const bool in1 = i1 < N;
+    const size_t g0 = (size_t)(o0 + i0), g1 = (size_t)(o0 + (in1 ? i1 : i0));
+    const uint8_t hp0 = has_point[i0], hp1 = in1 ? has_point[i1] : (uint8_t)0;
+    const double a0 = P.pos[3 * g0], a1 = P.pos[3 * g0 + 1], a2 = P.pos[3 * g0 + 2];
+    const double f00 = P.f[3 * g0], f01 = P.f[3 * g0 + 1], f02 = P.f[3 * g0 + 2];
+    const int l0 = P.level[g0];
+    const double b0 = P.pos[3 * g1], b1 = P.pos[3 * g1 + 1], b2 = P.pos[3 * g1 + 2];
+    const double f10 = P.f[3 * g1], f11 = P.f[3 * g1 + 1], f12 = P.f[3 * g1 + 2];
+    const int l1 = P.level[g1];
+    o.valid[i0] = hp0;
+    if (hp0) {
+      o.px[i0] = a0; o.py[i0] = a1; o.pz[i0] = a2;
+      o.fxn[i0] = f00 / f02;  // vk::project2d(f)
+      o.fyn[i0] = f01 / f02;
+      o.sic[i0] = 1.0 / (double)(1 << l0);
+      cnt[0] += 1.0;
+    }
+    if (in1) {
+      o.valid[i1] = hp1;
+      if (hp1) {
+        o.px[i1] = b0; o.py[i1] = b1; o.pz[i1] = b2;
+        o.fxn[i1] = f10 / f12;
+        o.fyn[i1] = f11 / f12;
+        o.sic[i1] = 1.0 / (double)(1 << l1);
+        cnt[0] += 1.0;
+      }
+    }
   }
   // pose: every thread derives R, t from the input itself (same arithmetic everywhere)
   double R[9], t[3];
@@ -413,30 +434,57 @@ __global__ void __launch_bounds__(kPoThreads) pose_opt_kernel(PoseOptParams P) {
   for (int i = tid; i < N; i += kPoThreads)
     if (o.valid[i] && sqrt(o.work[i]) > thresh) has_point[i] = 0;  // point = NULL
 
+  // Cov_ = (A * fx^2)^-1  (:125-126).  Warp 0: every lane factorises A fx^2 (register LDL^T, redundantly), lane j < 6
+  // solves for the unit vector e_j = column j of the inverse -- ~0.8 K cycles instead of a one-thread elimination
+  // with 36 dependent divisions (9.5 K).  A degenerate A falls back to Gauss-Jordan with partial pivoting.
+  if (warp == 0) {
+    const double f2 = fx * fx;
+    double h[21];
+    {
+      int idx = 0;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+#pragma unroll
+        for (int c = r; c < 6; ++c, ++idx) h[idx] = s.A[r * 6 + c] * f2;
+    }
+    Fact6 F;
+    const bool ok = fact6_compute_upper(h, F);
+    if (ok) {
+      double e[6], x[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) e[k] = (k == lane) ? 1.0 : 0.0;
+      fact6_solve(F, e, x);
+      if (lane < 6) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s.cov[k * 6 + lane] = x[k];
+      }
+    } else if (lane == 0) {
+      double M[6][12];
+      for (int a = 0; a < 6; ++a)
+        for (int b = 0; b < 6; ++b) { M[a][b] = s.A[a * 6 + b] * f2; M[a][6 + b] = (a == b) ? 1.0 : 0.0; }
+      for (int c = 0; c < 6; ++c) {
+        int p = c;
+        for (int rr = c + 1; rr < 6; ++rr)
+          if (fabs(M[rr][c]) > fabs(M[p][c])) p = rr;
+        if (p != c)
+          for (int j = 0; j < 12; ++j) { const double tmp = M[c][j]; M[c][j] = M[p][j]; M[p][j] = tmp; }
+        const double d = 1.0 / M[c][c];
+        for (int j = 0; j < 12; ++j) M[c][j] *= d;
+        for (int rr = 0; rr < 6; ++rr)
+          if (rr != c) {
+            const double fct = M[rr][c];
+            for (int j = 0; j < 12; ++j) M[rr][j] -= fct * M[c][j];
+          }
+      }
+      for (int a = 0; a < 6; ++a)
+        for (int b = 0; b < 6; ++b) s.cov[a * 6 + b] = M[a][6 + b];
+    }
+    __syncwarp();
+  }
   if (tid == 0) {
     svo_b200_pose_opt_result r;
     memset(&r, 0, sizeof(r));
-    // Cov_ = (A * fx^2)^-1  (:125-126), Gauss-Jordan with partial pivoting on [A|I]
-    double M[6][12];
-    const double f2 = fx * fx;
-    for (int a = 0; a < 6; ++a)
-      for (int b = 0; b < 6; ++b) { M[a][b] = s.A[a * 6 + b] * f2; M[a][6 + b] = (a == b) ? 1.0 : 0.0; }
-    for (int c = 0; c < 6; ++c) {
-      int p = c;
-      for (int rr = c + 1; rr < 6; ++rr)
-        if (fabs(M[rr][c]) > fabs(M[p][c])) p = rr;
-      if (p != c)
-        for (int j = 0; j < 12; ++j) { const double tmp = M[c][j]; M[c][j] = M[p][j]; M[p][j] = tmp; }
-      const double d = 1.0 / M[c][c];
-      for (int j = 0; j < 12; ++j) M[c][j] *= d;
-      for (int rr = 0; rr < 6; ++rr)
-        if (rr != c) {
-          const double fct = M[rr][c];
-          for (int j = 0; j < 12; ++j) M[rr][j] -= fct * M[c][j];
-        }
-    }
-    for (int a = 0; a < 6; ++a)
-      for (int b = 0; b < 6; ++b) r.cov[a * 6 + b] = M[a][6 + b];
+    for (int k = 0; k < 36; ++k) r.cov[k] = s.cov[k];
     r.estimated_scale = estimated_scale * fx;
     r.error_init = sqrt(med_init) * fx;
     r.error_final = sqrt(med_final) * fx;

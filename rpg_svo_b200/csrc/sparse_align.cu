@@ -97,6 +97,7 @@ struct SiaParams {
   int stage_cap;  // bytes of the staging region in shared memory (TMA image / cp.async windows)
   int slots;      // blockDim * FPT feature slots per CTA (patch arrays are [3][16][slots])
   int use_windows, use_prefetch;
+  int async_xchg;  // upfront cluster variant: per-iteration sums by st.async + mbarrier instead of DSMEM stores + barrier.cluster
   double* T_out;
   double* H_out;
   uint8_t* visible_out;
@@ -125,6 +126,7 @@ template <int NWC, int CS>
 struct SiaSharedT {
   static constexpr int kPairWarps = NWC * CS;
   uint64_t mbar;
+  uint64_t xbar[2];  // cluster geometry, asynchronous exchange: one mbarrier per parity of the running iteration counter
   // per-warp partial sums of one residual pass (6 Jres + chi2, slot 7 unused) for every warp of the
   // pair (all CTAs of the cluster), double-buffered by the parity of the running iteration counter
   double part[2][kPairWarps][8];
@@ -251,6 +253,23 @@ __device__ __forceinline__ void st_cluster_v2s32(int* local_ptr, unsigned rank, 
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(rank));
   asm volatile("st.shared::cluster.v2.s32 [%0], {%1, %2};" ::"r"(remote), "r"(a), "r"(b) : "memory");
+}
+
+// asynchronous remote store that also counts its bytes on an mbarrier of the SAME remote CTA (st.async + complete_tx): data
+// and "it has arrived" travel together, one DSMEM hop, and the receiver sleeps on its own mbarrier instead of a cluster barrier
+__device__ __forceinline__ uint32_t cluster_addr(const void* local_ptr, unsigned rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(rank));
+  return remote;
+}
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];" ::"r"(remote_addr), "d"(v), "r"(remote_mbar)
+               : "memory");
+}
+__device__ __forceinline__ void st_async_v2s32(uint32_t remote_addr, int a, int b, uint32_t remote_mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.s32 [%0], {%1, %2}, [%3];" ::"r"(remote_addr), "r"(a), "r"(b),
+               "r"(remote_mbar)
+               : "memory");
 }
 
 // ---- system-scope accesses to (peer) global memory
@@ -594,22 +613,13 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
 
   if (tid == 0) {
     mbar_init(&s.mbar, 1);
+    mbar_init(&s.xbar[0], 1);
+    mbar_init(&s.xbar[1], 1);
     fence_mbar_init();
     s.mbar_phase = 0;  // use k of the barrier completes phase parity k&1; the blob copy is use 0
-    s.st[0].model = pose_from_rt12(job.T);
-    s.st[0].old_model = s.st[0].model;
-    s.h_is_tot = 0; s.n_in_last = 0;
-    s.n_iters = 0; s.sum_vis = 0; s.sum_in = 0; s.n_trace = 0;
-    s.xg_seq = (CS == 1 && P.xg.world > 1) ? P.xg.peer[P.xg.rank][pair].xseq : 0u;
-    s.xg_failed = 0u;
-#if SVO_SIA_DEBUG
-    for (int k = 0; k < 8; ++k) s.tk[k] = 0;
-    for (int k = 0; k < 4; ++k) s.tkx[k] = 0;
-    s.tk[4] = clock64();
-#endif
-    for (int k = 0; k < 36; ++k) s.Hs[k] = 0.0;
     // ---- TMA: the packed feature records of this CTA's features, four bulk copies (px, f, pos, has_point
-    //      sections of the pair's blob) into the (idle) patch arrays
+    //      sections of the pair's blob) into the (idle) patch arrays -- issued first, everything else this thread
+    //      initialises runs in the shadow of that copy
     fence_proxy_async();
     if (np_loc > 0) {
       const uint32_t bytes = (uint32_t)np_loc * 65u;
@@ -623,6 +633,18 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
     } else {
       mbar_arrive(&s.mbar);  // a CTA without features still completes use 0 of the barrier: the phase parities of the image copies stay in step
     }
+    s.st[0].model = pose_from_rt12(job.T);
+    s.st[0].old_model = s.st[0].model;
+    s.h_is_tot = 0; s.n_in_last = 0;
+    s.n_iters = 0; s.sum_vis = 0; s.sum_in = 0; s.n_trace = 0;
+    s.xg_seq = (CS == 1 && P.xg.world > 1) ? P.xg.peer[P.xg.rank][pair].xseq : 0u;
+    s.xg_failed = 0u;
+#if SVO_SIA_DEBUG
+    for (int k = 0; k < 8; ++k) s.tk[k] = 0;
+    for (int k = 0; k < 4; ++k) s.tkx[k] = 0;
+    s.tk[4] = clock64();
+#endif
+    for (int k = 0; k < 36; ++k) s.Hs[k] = 0.0;
   }
   __syncthreads();
   mbar_wait(&s.mbar, 0);
@@ -708,6 +730,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
   }
   pair_sync<CS>();  // everyone is done with the staged blob (the patch arrays may be written) and, in the cluster
                     // variant, every CTA's shared memory is initialised before remote stores arrive
+    SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) s.tkx[3] = clock64() - s.tk[4];)
 
   // ---- one feature's window of the current image at this level (kModeWindow): 16 columns x 8 rows around the projection
   //      with the pose the level starts from, requested with cp.async (completion: cp_async_wait_all by the same thread)
@@ -1052,6 +1075,22 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       if constexpr (CS == 1) {
         if ((lane & 3) == 0) s.part[buf][gw][lane >> 2] = acc[0];
         if (lane == 0) { s.cnt[buf][gw][0] = w_in; s.cnt[buf][gw][1] = w_out; }
+      } else if (UP && P.async_xchg) {
+        // every CTA of the cluster receives every warp's partials by st.async: each store completes its 8 bytes on the
+        // receiver's mbarrier of this parity, which one local thread arms with the byte count of all warps of the pair; the
+        // receiver wakes when the last byte has landed -- one DSMEM hop, no cluster barrier.  (Two barriers: traffic of
+        // iteration g+1 goes to the other one, and nobody can send g+2 before everybody has consumed g.)
+        uint64_t* xb = &s.xbar[buf];
+        if (tid == 0) mbar_expect_tx(xb, 72u * (uint32_t)(nwarps * CS));
+        if ((lane & 3) == 0) {
+#pragma unroll
+          for (int r = 0; r < CS; ++r) st_async_f64(cluster_addr(&s.part[buf][gw][lane >> 2], (unsigned)r), acc[0], cluster_addr(xb, (unsigned)r));
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int r = 0; r < CS; ++r) st_async_v2s32(cluster_addr(&s.cnt[buf][gw][0], (unsigned)r), w_in, w_out, cluster_addr(xb, (unsigned)r));
+        }
+        mbar_wait(xb, (g >> 1) & 1u);
       } else {
         // every CTA of the cluster receives every warp's partials (distributed shared memory stores)
         if ((lane & 3) == 0) {
@@ -1063,7 +1102,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           for (int r = 0; r < CS; ++r) st_cluster_v2s32(&s.cnt[buf][gw][0], (unsigned)r, w_in, w_out);
         }
       }
-      pair_sync<CS>();  // barrier A: every warp's partial sums are in place
+      if (!(CS > 1 && UP && P.async_xchg)) pair_sync<CS>();  // barrier A: every warp's partial sums are in place
       const int nw_pair = nwarps * CS;
       double tot[7];
       int n_in = 0, n_out = 0, done = 0;
@@ -1217,8 +1256,13 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) s.tk[3] += clock64() - ti2;)
       if (done) break;
     }
-    pair_sync<CS>();  // stage region / patches are rewritten by the next level; the leader's state writes are visible
+    // stage region / patches are rewritten by the next level; the leader's state writes are visible.  Upfront variant: only
+    // CTA-local buffers are reused between levels (every level has its own patch arrays, the exchange buffers alternate by
+    // the parity of the running iteration counter), so the CTAs of the pair need not meet here
+    if constexpr (UP) __syncthreads();
+    else pair_sync<CS>();
   }
+  if constexpr (UP) pair_sync<CS>();  // no CTA of the cluster exits while another may still write into its shared memory
 
   // ---- outputs ---------------------------------------------------------------------------------
 #pragma unroll
@@ -1241,8 +1285,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
     if (CS == 1 && P.xg.world > 1) P.xg.peer[P.xg.rank][pair].xseq = s.xg_seq;
 #if SVO_SIA_DEBUG
     if (SVO_SIA_DEBUG && P.debug && (pair == 0 || pair == (int)(gridDim.x / CS) / 2 || pair == (int)(gridDim.x / CS) - 1))
-      printf("[sia dbg] pair %d iters %d cycles: setup %lld pass %lld reduce %lld tail %lld (solve %lld update %lld) total %lld | setup parts: loads+patches %lld hsum %lld factor+wait %lld upfront %lld\n", pair, s.n_iters,
-             s.tk[0], s.tk[1], s.tk[2], s.tk[3], s.tk[5], s.tk[6], (long long)clock64() - s.tk[4], s.tk[7], s.tkx[0], s.tkx[1], s.tkx[2]);
+      printf("[sia dbg] pair %d iters %d cycles: setup %lld pass %lld reduce %lld tail %lld (solve %lld update %lld) total %lld | setup parts: loads+patches %lld hsum %lld factor+wait %lld upfront %lld prologue %lld\n", pair, s.n_iters,
+             s.tk[0], s.tk[1], s.tk[2], s.tk[3], s.tk[5], s.tk[6], (long long)clock64() - s.tk[4], s.tk[7], s.tkx[0], s.tkx[1], s.tkx[2], s.tkx[3]);
 #endif
   }
 }
@@ -1299,6 +1343,7 @@ static int g_sia_prefetch = 1;    // SVO_B200_SIA_PREFETCH=0: no bulk L2 prefetc
                                   // uncoalesced requests cost more L1 time than the DRAM latency they hide.)
 static int g_sia_cluster = -1;    // SVO_B200_SIA_CLUSTER: force the CTAs per pair (1, 2, 4, 8); -1 = by batch size
 static int g_sia_upfront = 1;     // SVO_B200_SIA_UPFRONT=0: the cluster geometry prepares each level when it reaches it (round-2a behaviour)
+static int g_sia_async = 1;       // SVO_B200_SIA_ASYNC=0: the upfront variant exchanges its sums through barrier.cluster like the others
 static int g_sia_plain = 1;       // SVO_B200_SIA_PLAIN=0: the undistorted pinhole runs the general-camera instantiation too
 static int g_sia_fpt2 = 1;        // SVO_B200_SIA_FPT2: <= 320 features per CTA as 160 threads x 2 features: 1 = three CTAs per SM (default,
                                   // measured best for full batches), 2 = two CTAs per SM with windows, 0 = 320 threads x 1 feature
@@ -1315,6 +1360,7 @@ static void read_env_once() {
   if (const char* e = getenv("SVO_B200_SIA_FPT2")) g_sia_fpt2 = atoi(e);
   if (const char* e = getenv("SVO_B200_SIA_PLAIN")) g_sia_plain = atoi(e) != 0;
   if (const char* e = getenv("SVO_B200_SIA_UPFRONT")) g_sia_upfront = atoi(e) != 0;
+  if (const char* e = getenv("SVO_B200_SIA_ASYNC")) g_sia_async = atoi(e) != 0;
 }
 
 // Launch geometry for a batch of B pairs with at most max_feat features each.
@@ -1475,6 +1521,7 @@ static int fill_common(svo_b200_ctx* ctx, SiaParams& P, const svo_b200_frame* fr
   read_env_once();
   P.use_windows = g_sia_windows;
   P.use_prefetch = g_sia_prefetch;
+  P.async_xchg = g_sia_async;
   P.xg.rank = 0; P.xg.world = 1;
   if (ctx->xg_connected) {
     P.xg.rank = ctx->xg_rank; P.xg.world = ctx->xg_world;
