@@ -366,13 +366,15 @@ __device__ __forceinline__ void warp_h_partials(Get get, double* dst) {
 // (and in the rare "slow path"): per-warp partials, one shared-memory hop, warp 0 adds the per-warp partials (and, in the
 // cluster variant, the per-CTA sums every CTA received through DSMEM, after a cluster barrier).  On return the totals are in
 // s.sums[0..23] of EVERY CTA of the pair, visible to warp 0 only (callers that need them elsewhere synchronise).
+// (`sum_warp`: the warp that adds the per-warp partials and afterwards sees s.sums -- warp 0, or, one CTA per pair, another
+// warp of the caller's choice.)
 template <int FPT, int CS, class SH, class Get>
-__device__ __forceinline__ void pair_sum_h_to_warp0(Get get, SH& s, int nwarps, const XgParams& xg, int xg_pair) {
+__device__ __forceinline__ void pair_sum_h_to_warp0(Get get, SH& s, int nwarps, const XgParams& xg, int xg_pair, int sum_warp = 0) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   warp_h_partials<FPT>(get, &s.hpart[warp * kPartK]);
   __syncthreads();
   if constexpr (CS == 1) {
-    if (warp == 0) {
+    if (warp == sum_warp) {
       double acc = 0.0;
       if (lane < kPartK)
         for (int wv = 0; wv < nwarps; ++wv) acc += s.hpart[wv * kPartK + lane];
@@ -586,16 +588,24 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
   using UPT = SiaUpT<MAXT / 32, CS>;
   SH& s = *reinterpret_cast<SH*>(smem_raw);
   constexpr int S = MAXT * FPT;  // feature slots of this CTA (== P.slots, checked on the host)
+  // Throughput geometry (160 threads x 2 features, three CTAs per SM): the shared arrays are allocated for SA = 304 slots
+  // (the host selects it for <= 304 features only), which leaves room for the per-feature state xyz_ref in shared memory
+  // next to the two coarsest current images.  Kept in registers that state was spilled at 128 registers per thread, and local
+  // memory misses the small L1 left beside 3 x 75 KB of shared memory (ncu r02c: 15 M local loads per launch, 17 % L1 hits,
+  // each at the head of a feature's projection chain).
+  constexpr bool SS = (FPT == 2 && MAXT == 160 && CS == 1);
+  constexpr int SA = SS ? 304 : S;  // stride of the per-slot shared arrays
   constexpr size_t kCtlBytes = ((sizeof(SH) + 15) & ~size_t(15)) + (UP ? ((sizeof(UPT) + 15) & ~size_t(15)) : 0);
   UPT& up = *reinterpret_cast<UPT*>(smem_raw + ((sizeof(SH) + 15) & ~size_t(15)));  // only touched when UP
   const int n_lvl_bufs = UP ? (P.max_level - P.min_level + 1) : 1;  // patch array sets (one per level when UP)
   float* const pat_base = reinterpret_cast<float*>(smem_raw + kCtlBytes);
   // set li (0 = coarsest level) : [16][S] f32 reference patch, then [16][S] float2 gradients
-  auto pat_ref_of = [&](int li) -> float* { return pat_base + (size_t)li * 3 * kPatchArea * S; };
-  auto pat_dxy_of = [&](int li) -> float2* { return reinterpret_cast<float2*>(pat_ref_of(li) + kPatchArea * S); };
+  auto pat_ref_of = [&](int li) -> float* { return pat_base + (size_t)li * 3 * kPatchArea * SA; };
+  auto pat_dxy_of = [&](int li) -> float2* { return reinterpret_cast<float2*>(pat_ref_of(li) + kPatchArea * SA); };
   float* pat_ref = pat_ref_of(0);
   float2* pat_dxy = pat_dxy_of(0);
-  uint8_t* stage = reinterpret_cast<uint8_t*>(pat_base + (size_t)n_lvl_bufs * 3 * kPatchArea * S);  // 16-byte aligned
+  double* const st_xyz = reinterpret_cast<double*>(pat_base + (size_t)n_lvl_bufs * 3 * kPatchArea * SA);  // SS: [3][SA] xyz_ref
+  uint8_t* stage = reinterpret_cast<uint8_t*>(st_xyz + (SS ? 3 * SA : 0));  // 16-byte aligned
   uint4* win = reinterpret_cast<uint4*>(stage);                                                      // [kWinRows][S] 16-byte window rows
 
   const unsigned crank = CS == 1 ? 0u : cluster_rank();
@@ -655,6 +665,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
 
   // per-feature register state
   double fx_[FPT], fy_[FPT], fz_[FPT], fzi_[FPT];
+  double fxs[FPT], fys[FPT], fzs[FPT];  // SS: copies that go to shared memory once the staged blob has been consumed
   int wx_[FPT], wy_[FPT];  // origin of the feature's current-image window (kModeWindow)
   unsigned hp_mask = 0, vis_mask = 0, in_mask = 0;
 #pragma unroll
@@ -670,6 +681,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       fy_[k] = b_f[3 * i + 1] * depth;
       fz_[k] = b_f[3 * i + 2] * depth;
       fzi_[k] = 1.0 / fz_[k];
+      if constexpr (SS) { fxs[k] = fx_[k]; fys[k] = fy_[k]; fzs[k] = fz_[k]; }
       if (b_hp[i]) hp_mask |= 1u << k;
       if (EVAL && P.visible_in[fbase + i]) vis_mask |= 1u << k;
     }
@@ -731,11 +743,32 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
   pair_sync<CS>();  // everyone is done with the staged blob (the patch arrays may be written) and, in the cluster
                     // variant, every CTA's shared memory is initialised before remote stores arrive
     SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) s.tkx[3] = clock64() - s.tk[4];)
+  if constexpr (SS) {
+#pragma unroll
+    for (int k = 0; k < FPT; ++k) {
+      const int slot = tid + k * T;
+      if (slot < n_loc) { st_xyz[slot] = fxs[k]; st_xyz[SA + slot] = fys[k]; st_xyz[2 * SA + slot] = fzs[k]; }
+    }
+  }
+  // xyz_ref of feature k of this thread, and 1/z (SS: re-read from shared memory / recomputed, correctly rounded like the division)
+  auto feat_xyz = [&](const int k, const int slot, double& x, double& y, double& z) {
+    if constexpr (SS) {
+      // slots without a feature (and the slots >= SA the last half-warp maps to) yield the neutral (0, 0, 1) the register
+      // variant initialises: the H reduction multiplies their Jacobian rows by zero moments, which must stay finite
+      x = 0.0; y = 0.0; z = 1.0;
+      if (slot < n_loc) { x = st_xyz[slot]; y = st_xyz[SA + slot]; z = st_xyz[2 * SA + slot]; }
+    } else { x = fx_[k]; y = fy_[k]; z = fz_[k]; }
+  };
+  auto feat_zi = [&](const int k, const double z) -> double {
+    if constexpr (SS) return rcp_rn(z);
+    else return fzi_[k];
+  };
 
   // ---- one feature's window of the current image at this level (kModeWindow): 16 columns x 8 rows around the projection
   //      with the pose the level starts from, requested with cp.async (completion: cp_async_wait_all by the same thread)
   auto stage_window = [&](const int k, const int slot, const int W, const int Hh, const float scale, const uint8_t* cur_img) {
-    const double x = fx_[k], y = fy_[k], z = fz_[k];
+    double x, y, z;
+    feat_xyz(k, slot, x, y, z);
     double xc, yc, zc;
     sia_transform<CS>(s.pub, R, t, x, y, z, xc, yc, zc);
     const double rz = fast_rcp(zc);
@@ -757,12 +790,12 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           const uint8_t* src = cur_img + (size_t)wy * W + wx;
           if (one) {
 #pragma unroll
-            for (int r = 0; r < kWinRows; ++r) cp_async16(win + r * S + slot, src + (size_t)r * W);
+            for (int r = 0; r < kWinRows; ++r) cp_async16(win + r * SA + slot, src + (size_t)r * W);
           } else {
 #pragma unroll
             for (int r = 0; r < kWinRows; ++r) {
-              cp_async8(reinterpret_cast<uint8_t*>(win + r * S + slot), src + (size_t)r * W);
-              cp_async8(reinterpret_cast<uint8_t*>(win + r * S + slot) + 8, src + (size_t)r * W + 8);
+              cp_async8(reinterpret_cast<uint8_t*>(win + r * SA + slot), src + (size_t)r * W);
+              cp_async8(reinterpret_cast<uint8_t*>(win + r * SA + slot) + 8, src + (size_t)r * W + 8);
             }
           }
         }
@@ -830,8 +863,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
               const float val = b1[x + 1];
               const float dx = __fmul_rn(0.5f, __fsub_rn(b1[x + 2], b1[x]));
               const float dy = __fmul_rn(0.5f, __fsub_rn(b2[x + 1], b0[x + 1]));
-              pr[p * S + slot] = val;
-              pd[p * S + slot] = make_float2(dx, dy);
+              pr[p * SA + slot] = val;
+              pd[p * SA + slot] = make_float2(dx, dy);
               sxx = fma((double)dx, (double)dx, sxx);
               sxy = fma((double)dx, (double)dy, sxy);
               syy = fma((double)dy, (double)dy, syy);
@@ -848,9 +881,9 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         // and a zeroed Jacobian (jacobian_cache_.setZero() per level, :64).  Unreachable for
         // dyadic pyramids but kept bit-faithful.
 #pragma unroll
-        for (int p = 0; p < kPatchArea; ++p) pd[p * S + slot] = make_float2(0.f, 0.f);
+        for (int p = 0; p < kPatchArea; ++p) pd[p * SA + slot] = make_float2(0.f, 0.f);
         if (pr_stale)  // per-level arrays (upfront variant): the stale patch is the previous level's
-          for (int p = 0; p < kPatchArea; ++p) pr[p * S + slot] = pr_stale[p * S + slot];
+          for (int p = 0; p < kPatchArea; ++p) pr[p * SA + slot] = pr_stale[p * SA + slot];
         m_cnt[k] = 1.0;
       }
     }
@@ -871,7 +904,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       vis_levels |= (vis_mask & 1u) << li;
       warp_h_partials<FPT>(
           [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
-            x = fx_[k]; y = fy_[k]; zi = fzi_[k]; sxx = m_sxx[k]; sxy = m_sxy[k]; syy = m_syy[k]; cnt = m_cnt[k];
+            { double z_; feat_xyz(k, (int)threadIdx.x + k * (int)blockDim.x, x, y, z_); zi = feat_zi(k, z_); } sxx = m_sxx[k]; sxy = m_sxy[k]; syy = m_syy[k]; cnt = m_cnt[k];
           },
           &up.hpart[li][warp * kPartK]);
     }
@@ -911,7 +944,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
     const uint32_t img_bytes = ((uint32_t)(W * Hh) + 15u) & ~15u;
     int mode = kModeGlobal;
     if (img_bytes + 16u <= (uint32_t)P.stage_cap) mode = kModeImage;
-    else if (P.use_windows && (W & 7) == 0 && kWinBytes * S <= P.stage_cap) mode = kModeWindow;
+    else if (P.use_windows && (W & 7) == 0 && kWinBytes * SA <= P.stage_cap) mode = kModeWindow;
     if (mode == kModeImage && tid == 0) {
       s.mbar_phase ^= 1u;
       fence_proxy_async();
@@ -930,6 +963,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
     SIA_DBG(long long tq1 = 0;)
     SIA_DBG(long long tq2 = 0;)
     const Solver6* sol_level = &s.sol_tot;  // factorisation of this level's H over its visible set
+    const int fwarp = SS ? nwarps - 1 : 0;  // the warp that sums and factorises this level's H
     if constexpr (!UP) {
       // ---- precomputeReferencePatches (:84-145), one feature per thread; the windows of the current image are requested
       //      between the footprint loads and the patch arithmetic
@@ -938,18 +972,19 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { tq1 = clock64(); s.tk[7] += tq1 - tq0; })
       pair_sum_h_to_warp0<FPT, CS, SH>(
           [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
-            x = fx_[k]; y = fy_[k]; zi = fzi_[k]; sxx = m_sxx[k]; sxy = m_sxy[k]; syy = m_syy[k]; cnt = m_cnt[k];
+            { double z_; feat_xyz(k, (int)threadIdx.x + k * (int)blockDim.x, x, y, z_); zi = feat_zi(k, z_); } sxx = m_sxx[k]; sxy = m_sxy[k]; syy = m_syy[k]; cnt = m_cnt[k];
             // opaque to the optimiser: otherwise the level-invariant Jacobian rows are hoisted out of the level loop and
             // parked in local memory (17 doubles per thread, written once and re-read every level)
             asm volatile("" : "+d"(x), "+d"(y), "+d"(zi));
           },
-          s, nwarps, P.xg, pair);
-      // The scaling and LDL^T factorisation of this level's H is serial work nobody needs before the first solve: warp 0
-      // does it while the other warps already run the first residual pass; its results (s.sol_tot, s.Htot) become
-      // visible to everybody through the barrier of that pass.
+          s, nwarps, P.xg, pair, fwarp);
+      // The scaling and LDL^T factorisation of this level's H is serial work nobody needs before the first solve: one warp
+      // does it while the others already run the first residual pass; its results (s.sol_tot, s.Htot) become visible to
+      // everybody through the barrier of that pass.  Throughput geometry: the LAST warp, which owns fewer features than the
+      // others (44 of 300 against 64) and would reach that barrier early -- not warp 0, which runs the Gauss-Newton tail.
       SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { tq2 = clock64(); s.tkx[0] += tq2 - tq1; })
-      if (warp == 0) {
-        if (leader) s.sum_vis += (int)s.sums[21];
+      if (warp == fwarp) {
+        if (lane == 0) s.sum_vis += (int)s.sums[21];
         warp_scale_and_factor(s.sums, jscale * jscale, s.Htot, s.sol_tot);
       }
     } else {
@@ -985,7 +1020,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       for (int k = 0; k < FPT; ++k) {
         if (!((vis_mask >> k) & 1u)) continue;
         const int slot = tid + k * T;
-        const double x = fx_[k], y = fy_[k], z = fz_[k];
+        double x, y, z;
+        feat_xyz(k, slot, x, y, z);
         double xc, yc, zc;
         sia_transform<CS>(s.pub, R, t, x, y, z, xc, yc, zc);
         const double rz = fast_rcp(zc);
@@ -1017,12 +1053,12 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         } else {
           const int c0 = (ui - 2) - wx_[k], r0 = (vi - 2) - wy_[k];
           if (mode == kModeWindow && (unsigned)c0 <= 11u && (unsigned)r0 <= (unsigned)(kWinRows - 5)) {
-            const uint4* wp = win + r0 * S + slot;
+            const uint4* wp = win + r0 * SA + slot;
             const int kw = c0 >> 2;  // 0..2: the footprint row starts in word kw of the 16-byte window row
             const unsigned sh = (unsigned)(c0 & 3) * 8u;
 #pragma unroll
             for (int r = 0; r < 5; ++r) {
-              const uint4 q = wp[r * S];
+              const uint4 q = wp[r * SA];
               const uint32_t w0 = kw == 0 ? q.x : kw == 1 ? q.y : q.z, w1 = kw == 0 ? q.y : kw == 1 ? q.z : q.w;
               lo[r] = __funnelshift_r(w0, w1, sh);
               hi[r] = w1 >> sh;
@@ -1044,8 +1080,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           for (int xx = 0; xx < 4; ++xx) {
             const int p = yy * 4 + xx;
             const float I = bilin(wtl, wtr, wbl, wbr, q0[xx], q0[xx + 1], q1[xx], q1[xx + 1]);
-            const float res = __fsub_rn(I, pat_ref[p * S + slot]);
-            const float2 gr = pat_dxy[p * S + slot];
+            const float res = __fsub_rn(I, pat_ref[p * SA + slot]);
+            const float2 gr = pat_dxy[p * SA + slot];
             c2 = fmaf(res, res, c2);  // chi2 += res*res*weight, weight == 1 (:222); order differs from the serial sum anyway
             gx = fmaf(gr.x, res, gx);
             gy = fmaf(gr.y, res, gy);
@@ -1054,7 +1090,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
 #pragma unroll
           for (int c = 0; c < 5; ++c) q0[c] = q1[c];
         }
-        const double zi = fzi_[k], X = x * zi, Y = y * zi, dgx = (double)gx, dgy = (double)gy;
+        const double zi = feat_zi(k, z), X = x * zi, Y = y * zi, dgx = (double)gx, dgy = (double)gy;
         acc[0] = fma(-zi, dgx, acc[0]);
         acc[1] = fma(-zi, dgy, acc[1]);
         acc[2] = fma(zi, fma(X, dgx, Y * dgy), acc[2]);
@@ -1130,7 +1166,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           const int slot = tid + k * T;
 #pragma unroll
           for (int p = 0; p < kPatchArea; ++p) {
-            const float2 gr = pat_dxy[p * S + slot];
+            const float2 gr = pat_dxy[p * SA + slot];
             const double dx = (double)gr.x, dy = (double)gr.y;
             q_sxx[k] = fma(dx, dx, q_sxx[k]);
             q_sxy[k] = fma(dx, dy, q_sxy[k]);
@@ -1139,7 +1175,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         }
         pair_sum_h_to_warp0<FPT, CS, SH>(
             [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
-              x = fx_[k]; y = fy_[k]; zi = fzi_[k]; sxx = q_sxx[k]; sxy = q_sxy[k]; syy = q_syy[k]; cnt = 0.0;
+              { double z_; feat_xyz(k, (int)threadIdx.x + k * (int)blockDim.x, x, y, z_); zi = feat_zi(k, z_); } sxx = q_sxx[k]; sxy = q_sxy[k]; syy = q_syy[k]; cnt = 0.0;
               asm volatile("" : "+d"(x), "+d"(y), "+d"(zi));  // see the per-level call: no hoisting into local memory
             },
             s, nwarps, P.xg, pair);
@@ -1247,7 +1283,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
               for (int p = 0; p < kPatchArea; ++p)
                 P.residuals_out[(size_t)(fbase + i) * kPatchArea + p] = __int_as_float(0x7fc00000);
             for (int p = 0; p < kPatchArea; ++p)
-              P.ref_patch_out[(size_t)(fbase + i) * kPatchArea + p] = pat_ref[p * S + i];
+              P.ref_patch_out[(size_t)(fbase + i) * kPatchArea + p] = pat_ref[p * SA + i];
           }
         }
         break;
@@ -1413,10 +1449,12 @@ static int pick_launch(svo_b200_ctx* ctx, int B, int max_feat, int n_lvl, int& t
     // the kernels are instantiated for MAXT in {320, 384, 512}; launching exactly MAXT threads makes the
     // slot count S = MAXT*FPT a compile-time constant (immediate shared-memory offsets)
     threads = fpt == 1 ? (threads <= 320 ? 320 : threads <= 384 ? 384 : 512) : 512;
-    if (fpt2 && max_feat <= 320) { fpt = 2; threads = 160; }
+    if (fpt2 && max_feat <= 304) { fpt = 2; threads = 160; }  // its shared arrays are allocated for 304 slots (kernel: SA)
   }
-  const int slots = threads * fpt;
+  const bool throughput_geom = cluster == 1 && fpt == 2 && threads == 160;
+  const int slots = throughput_geom ? 304 : threads * fpt;
   size_t base = ((sia_shared_bytes(threads, cluster) + 15) & ~size_t(15)) + (size_t)3 * kPatchArea * slots * sizeof(float);
+  if (throughput_geom) base += (size_t)3 * slots * sizeof(double);  // xyz_ref of every feature (kernel: st_xyz)
   // cluster geometry with every CTA alone on its SM: one patch array set per level, everything pose independent prepared
   // before the first iteration (the launch asks for the 4-CTA instantiation; 2 and 8 keep the per-level flow)
   upfront = false;
