@@ -273,7 +273,7 @@ def measure_latency_and_c4(ctx, capi, torch, stream, inp, host_l0, pool) -> dict
                          "e2e_us_per_frame": 1e6 * (t1 - t0) / nlive,
                          "e2e_includes": "pinned-host level-0 upload (307 KB) + device pyramid + feature H2D + kernel + pose/mask D2H, via python ctypes",
                          "frames_per_s_e2e": nlive / (t1 - t0),
-                         "launch_geometry": "4-CTA thread-block cluster per pair (DSMEM partial sums)"}
+                         "launch_geometry": "4-CTA thread-block cluster per pair, all levels prepared before the first iteration, sums exchanged by st.async + mbarrier"}
     for f_ in ping:
         f_.destroy()
     # ---- configs[4]: 32 pairs per GPU per launch
@@ -297,7 +297,7 @@ def measure_latency_and_c4(ctx, capi, torch, stream, inp, host_l0, pool) -> dict
     out["c4_32_per_gpu"] = {"config": "configs[4]: 256 pairs over 8 GPUs = 32 pairs per GPU per launch",
                             "device_us_per_launch": us32, "frames_per_s_device": 32 / (us32 * 1e-6),
                             "e2e_us_per_launch": 1e6 * t32, "frames_per_s_e2e": 32 / t32,
-                            "launch_geometry": "4-CTA cluster per pair, 128 CTAs"}
+                            "launch_geometry": "4-CTA cluster per pair (upfront variant, st.async exchange), 128 CTAs"}
     return out
 
 
@@ -639,10 +639,10 @@ def main():
                 "data": "synthetic", "config": cfg,
                 "pose_rmse_vs_ref": rmse,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": peak_src, "kernel": "svo::sia_kernel<2,false,160,3,1>",
+                             "traffic": traffic, "peak_source": peak_src, "kernel": "svo::sia_kernel<FPT=2,EVAL=false,MAXT=160,MINB=3,CS=1,CG=false,UP=false>",
                              "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
                              "mean_gn_iterations_per_pair": float(np.mean(stats["n_iters"])),
-                             "note": "latency-bound sparse gather kernel: see DESIGN.md 4.1 for the sector-granular DRAM floor"},
+                             "note": "latency-bound sparse gather kernel (ncu r02h: see profiles/ and DESIGN.md 4.1 for the stall breakdown and the sector-granular DRAM floor)"},
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "numa": numa}
         line.update(extras)
         print(json.dumps(line), flush=True)

@@ -368,7 +368,7 @@ __device__ __forceinline__ void warp_h_partials(Get get, double* dst) {
 // s.sums[0..23] of EVERY CTA of the pair, visible to warp 0 only (callers that need them elsewhere synchronise).
 // (`sum_warp`: the warp that adds the per-warp partials and afterwards sees s.sums -- warp 0, or, one CTA per pair, another
 // warp of the caller's choice.)
-template <int FPT, int CS, class SH, class Get>
+template <int FPT, int CS, bool XG, class SH, class Get>
 __device__ __forceinline__ void pair_sum_h_to_warp0(Get get, SH& s, int nwarps, const XgParams& xg, int xg_pair, int sum_warp = 0) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   warp_h_partials<FPT>(get, &s.hpart[warp * kPartK]);
@@ -378,7 +378,7 @@ __device__ __forceinline__ void pair_sum_h_to_warp0(Get get, SH& s, int nwarps, 
       double acc = 0.0;
       if (lane < kPartK)
         for (int wv = 0; wv < nwarps; ++wv) acc += s.hpart[wv * kPartK + lane];
-      if (xg.world > 1) {  // feature split over GPUs: the other ranks' partial sums arrive through peer memory
+      if (XG && xg.world > 1) {  // feature split over GPUs: the other ranks' partial sums arrive through peer memory
         int z0 = 0, z1 = 0;
         xg_allreduce<kPartK>(xg, xg_pair, &s.xg_seq, acc, z0, z1);
       }
@@ -595,6 +595,13 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
   // each at the head of a feature's projection chain).
   constexpr bool SS = (FPT == 2 && MAXT == 160 && CS == 1);
   constexpr int SA = SS ? 304 : S;  // stride of the per-slot shared arrays
+  // The throughput geometry has no room for windows (its staging region holds the two coarsest current images) and is never
+  // used for the multi-GPU feature split: both code paths are compiled out of it, and its residual pass loops over the
+  // thread's features instead of being unrolled -- the instruction stream of one Gauss-Newton iteration shrinks from ~27 KB to
+  // ~20 KB, which matters with three CTAs in different phases sharing one instruction cache (ncu r02h: 16 % of the stall
+  // samples are instruction-fetch stalls).
+  constexpr bool WIN = !SS;  // per-feature cp.async windows of the current image exist in this instantiation
+  constexpr bool XG = (CS == 1) && !SS;  // multi-GPU feature split (svo_b200_sia_split_*) compiled in
   constexpr size_t kCtlBytes = ((sizeof(SH) + 15) & ~size_t(15)) + (UP ? ((sizeof(UPT) + 15) & ~size_t(15)) : 0);
   UPT& up = *reinterpret_cast<UPT*>(smem_raw + ((sizeof(SH) + 15) & ~size_t(15)));  // only touched when UP
   const int n_lvl_bufs = UP ? (P.max_level - P.min_level + 1) : 1;  // patch array sets (one per level when UP)
@@ -831,9 +838,11 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         for (int r = 0; r < 7; ++r) fetch7_g64(ref_img, (vi - 3 + r) * W + (ui - 3), rlo[r], rhi[r]);
       }
       // ---- current-image window of this feature (fine levels): projected with the pose the level starts from
-      if (with_windows) {
-        wx_[k] = wy_[k] = -(1 << 20);
-        if (((vis_mask >> k) & 1u) && mode == kModeWindow) stage_window(k, slot, W, Hh, scale, cur_img);
+      if constexpr (WIN) {
+        if (with_windows) {
+          wx_[k] = wy_[k] = -(1 << 20);
+          if (((vis_mask >> k) & 1u) && mode == kModeWindow) stage_window(k, slot, W, Hh, scale, cur_img);
+        }
       }
       if (ok) {
         float wtl, wtr, wbl, wbr;
@@ -944,7 +953,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
     const uint32_t img_bytes = ((uint32_t)(W * Hh) + 15u) & ~15u;
     int mode = kModeGlobal;
     if (img_bytes + 16u <= (uint32_t)P.stage_cap) mode = kModeImage;
-    else if (P.use_windows && (W & 7) == 0 && kWinBytes * SA <= P.stage_cap) mode = kModeWindow;
+    else if (WIN && P.use_windows && (W & 7) == 0 && kWinBytes * SA <= P.stage_cap) mode = kModeWindow;
     if (mode == kModeImage && tid == 0) {
       s.mbar_phase ^= 1u;
       fence_proxy_async();
@@ -970,7 +979,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       double m_sxx[FPT], m_sxy[FPT], m_syy[FPT], m_cnt[FPT];
       level_patches(level, pat_ref, pat_dxy, (const float*)nullptr, mode, true, m_sxx, m_sxy, m_syy, m_cnt);
       SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { tq1 = clock64(); s.tk[7] += tq1 - tq0; })
-      pair_sum_h_to_warp0<FPT, CS, SH>(
+      pair_sum_h_to_warp0<FPT, CS, XG, SH>(
           [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
             { double z_; feat_xyz(k, (int)threadIdx.x + k * (int)blockDim.x, x, y, z_); zi = feat_zi(k, z_); } sxx = m_sxx[k]; sxy = m_sxy[k]; syy = m_syy[k]; cnt = m_cnt[k];
             // opaque to the optimiser: otherwise the level-invariant Jacobian rows are hoisted out of the level loop and
@@ -1016,7 +1025,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       for (int k = 0; k < 8; ++k) acc[k] = 0.0;
       int n_in_t = 0, n_out_t = 0;
       in_mask = 0;
-#pragma unroll
+#pragma unroll(SS ? 1 : FPT)
       for (int k = 0; k < FPT; ++k) {
         if (!((vis_mask >> k) & 1u)) continue;
         const int slot = tid + k * T;
@@ -1051,8 +1060,8 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
 #pragma unroll
           for (int r = 0; r < 5; ++r) fetch8<true>(stage, (vi - 2 + r) * W + (ui - 2), lo[r], hi[r]);
         } else {
-          const int c0 = (ui - 2) - wx_[k], r0 = (vi - 2) - wy_[k];
-          if (mode == kModeWindow && (unsigned)c0 <= 11u && (unsigned)r0 <= (unsigned)(kWinRows - 5)) {
+          const int c0 = WIN ? (ui - 2) - wx_[SS ? 0 : k] : -1, r0 = WIN ? (vi - 2) - wy_[SS ? 0 : k] : -1;
+          if (WIN && mode == kModeWindow && (unsigned)c0 <= 11u && (unsigned)r0 <= (unsigned)(kWinRows - 5)) {
             const uint4* wp = win + r0 * SA + slot;
             const int kw = c0 >> 2;  // 0..2: the footprint row starts in word kw of the 16-byte window row
             const unsigned sh = (unsigned)(c0 & 3) * 8u;
@@ -1173,7 +1182,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
             q_syy[k] = fma(dy, dy, q_syy[k]);
           }
         }
-        pair_sum_h_to_warp0<FPT, CS, SH>(
+        pair_sum_h_to_warp0<FPT, CS, XG, SH>(
             [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
               { double z_; feat_xyz(k, (int)threadIdx.x + k * (int)blockDim.x, x, y, z_); zi = feat_zi(k, z_); } sxx = q_sxx[k]; sxy = q_sxy[k]; syy = q_syy[k]; cnt = 0.0;
               asm volatile("" : "+d"(x), "+d"(y), "+d"(zi));  // see the per-level call: no hoisting into local memory
@@ -1205,7 +1214,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         bool slow = false;
         if (warp == 0) {
           compute_totals();
-          if (P.xg.world > 1) {  // feature split over GPUs: sum the 7 doubles + 2 counts of this pass over the ranks
+          if (XG && P.xg.world > 1) {  // feature split over GPUs: sum the 7 doubles + 2 counts of this pass over the ranks
             double v = 0.0;
 #pragma unroll
             for (int e = 0; e < 7; ++e) v = lane == e ? tot[e] : v;
