@@ -331,7 +331,7 @@ __device__ __forceinline__ void xg_allreduce(const XgParams& X, int pair, unsign
 // feature count, two pads) of this warp's features, into dst[0..23] (shared memory): three transposed 8-value warp
 // reductions computed chunk by chunk so that only ~8 accumulators are live at a time.
 // `get(k, x, y, zi, sxx, sxy, syy, cnt)` yields feature k's data.
-template <int FPT, class Get>
+template <int FPT, bool ROLL, class Get>
 __device__ __forceinline__ void warp_h_partials(Get get, double* dst) {
   const int lane = threadIdx.x & 31;
   auto do_chunk = [&](auto chunk_tag) {
@@ -339,8 +339,8 @@ __device__ __forceinline__ void warp_h_partials(Get get, double* dst) {
     double v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = 0.0;
-#pragma unroll
-    for (int k = 0; k < FPT; ++k) {
+#pragma unroll(ROLL ? 1 : FPT)
+    for (int k = 0; k < FPT; ++k) {  // ROLL: a loop, not FPT copies (instruction-cache footprint of the throughput geometry)
       double x, y, zi, sxx, sxy, syy, cnt;
       get(k, x, y, zi, sxx, sxy, syy, cnt);
       double a[6], b[6];
@@ -368,10 +368,10 @@ __device__ __forceinline__ void warp_h_partials(Get get, double* dst) {
 // s.sums[0..23] of EVERY CTA of the pair, visible to warp 0 only (callers that need them elsewhere synchronise).
 // (`sum_warp`: the warp that adds the per-warp partials and afterwards sees s.sums -- warp 0, or, one CTA per pair, another
 // warp of the caller's choice.)
-template <int FPT, int CS, bool XG, class SH, class Get>
+template <int FPT, int CS, bool XG, bool ROLL, class SH, class Get>
 __device__ __forceinline__ void pair_sum_h_to_warp0(Get get, SH& s, int nwarps, const XgParams& xg, int xg_pair, int sum_warp = 0) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  warp_h_partials<FPT>(get, &s.hpart[warp * kPartK]);
+  warp_h_partials<FPT, ROLL>(get, &s.hpart[warp * kPartK]);
   __syncthreads();
   if constexpr (CS == 1) {
     if (warp == sum_warp) {
@@ -818,7 +818,10 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
     const float scale = 1.0f / (float)(1 << level);
     const uint8_t* ref_img = job.ref_lvl[level];
     const uint8_t* cur_img = job.cur_lvl[level];
-#pragma unroll
+    // (throughput geometry: a loop over the thread's features -- the per-feature moments m_* are then indexed dynamically and
+    // live in local memory, eight values per level, which is cheaper than a second copy of the patch arithmetic in the
+    // instruction stream)
+#pragma unroll(SS ? 1 : FPT)
     for (int k = 0; k < FPT; ++k) {
       m_sxx[k] = m_sxy[k] = m_syy[k] = m_cnt[k] = 0.0;
       const int slot = tid + k * T;
@@ -911,7 +914,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       level_patches(level, pat_ref_of(li), pat_dxy_of(li), li > 0 ? pat_ref_of(li - 1) : (const float*)nullptr, kModeGlobal, false,
                     m_sxx, m_sxy, m_syy, m_cnt);
       vis_levels |= (vis_mask & 1u) << li;
-      warp_h_partials<FPT>(
+      warp_h_partials<FPT, false>(
           [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
             { double z_; feat_xyz(k, (int)threadIdx.x + k * (int)blockDim.x, x, y, z_); zi = feat_zi(k, z_); } sxx = m_sxx[k]; sxy = m_sxy[k]; syy = m_syy[k]; cnt = m_cnt[k];
           },
@@ -979,7 +982,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       double m_sxx[FPT], m_sxy[FPT], m_syy[FPT], m_cnt[FPT];
       level_patches(level, pat_ref, pat_dxy, (const float*)nullptr, mode, true, m_sxx, m_sxy, m_syy, m_cnt);
       SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { tq1 = clock64(); s.tk[7] += tq1 - tq0; })
-      pair_sum_h_to_warp0<FPT, CS, XG, SH>(
+      pair_sum_h_to_warp0<FPT, CS, XG, SS, SH>(
           [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
             { double z_; feat_xyz(k, (int)threadIdx.x + k * (int)blockDim.x, x, y, z_); zi = feat_zi(k, z_); } sxx = m_sxx[k]; sxy = m_sxy[k]; syy = m_syy[k]; cnt = m_cnt[k];
             // opaque to the optimiser: otherwise the level-invariant Jacobian rows are hoisted out of the level loop and
@@ -1182,7 +1185,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
             q_syy[k] = fma(dy, dy, q_syy[k]);
           }
         }
-        pair_sum_h_to_warp0<FPT, CS, XG, SH>(
+        pair_sum_h_to_warp0<FPT, CS, XG, SS, SH>(
             [&](int k, double& x, double& y, double& zi, double& sxx, double& sxy, double& syy, double& cnt) {
               { double z_; feat_xyz(k, (int)threadIdx.x + k * (int)blockDim.x, x, y, z_); zi = feat_zi(k, z_); } sxx = q_sxx[k]; sxy = q_sxy[k]; syy = q_syy[k]; cnt = 0.0;
               asm volatile("" : "+d"(x), "+d"(y), "+d"(zi));  // see the per-level call: no hoisting into local memory
