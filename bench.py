@@ -5,7 +5,7 @@ Workload (`config`, identical in both arms): one synthetic 640x480 camera stream
 pyramid levels 4..0, <=30 Gauss-Newton iterations per level (BASELINE.json configs[1]).  One *pass* = svo::SparseImgAlign::run
 over a window of `pairs_per_step_per_gpu` consecutive frame pairs of the stream (frame k is the reference of pair k and the
 current frame of pair k-1); every pair starts from the identity relative pose, so the pairs of a window are independent.  A
-*step* = `passes_per_step` = ceil(300 / steps) passes, so that the timed region of EXACTLY `steps` steps spans >= 0.5 s.
+*step* = `passes_per_step` = ceil(500 / steps) passes, so that the timed region of EXACTLY `steps` steps spans >= 0.5 s.
 
 Legs of a run (CUDA events on the library's stream, barrier + sync on both sides, max over ranks):
   value          pyramids + feature records resident in HBM; steps x passes launches of the alignment kernel.
@@ -71,7 +71,7 @@ def make_config(args) -> dict:
 
 
 def passes_per_step(steps: int) -> int:
-    return max(1, math.ceil(300 / max(steps, 1)))
+    return max(1, math.ceil(500 / max(steps, 1)))  # 500 launches of ~1.3 ms: >= 0.5 s on the device
 
 
 class ClockSampler:
