@@ -532,6 +532,9 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, uint32_t bytes) 
 
 enum { kModeGlobal = 0, kModeImage = 1, kModeWindow = 2 };
 
+// slot of Bq[r][c] in the 32-value patch cache (BQ): row 0 cols 1..4 -> 0..3, rows 1..4 cols 0..5 -> 4..27, row 5 cols 1..4 -> 28..31
+__host__ __device__ constexpr int bq_idx(int r, int c) { return r == 0 ? c - 1 : r == 5 ? 28 + c - 1 : 4 + (r - 1) * 6 + c; }
+
 // xyz_cur = T_cur_from_ref * xyz_ref.  One CTA per pair (CS == 1): the pose is read from shared memory (s.pub, published by
 // warp 0's Gauss-Newton tail) at the point of use -- six 128-bit shared loads per feature instead of 24 registers that stay
 // live across the residual loops (at 128 registers per thread those were spilled to local memory, which misses the small L1
@@ -600,6 +603,13 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
   // thread's features instead of being unrolled -- the instruction stream of one Gauss-Newton iteration shrinks from ~27 KB to
   // ~20 KB, which matters with three CTAs in different phases sharing one instruction cache (ncu r02h: 16 % of the stall
   // samples are instruction-fetch stalls).
+  // BQ (throughput geometry compiled for FOUR CTAs per SM): the patch cache holds the 32 values of the bilinear reference
+  // array the patch and both gradients are made of (rows 1..4 x cols 0..5 and cols 1..4 of rows 0 and 5 of the 6x6 array Bq)
+  // instead of 16 values + 16 gradient pairs -- 128 instead of 192 bytes per feature; dx = (Bq[y][x+1] - Bq[y][x-1]) / 2 and
+  // dy likewise are formed in the residual pass with the same two roundings precomputeReferencePatches uses.  That brings a
+  // CTA to ~55 KB of shared memory: four pairs per SM instead of three interleave their serial phases.
+  constexpr bool BQ = SS && MINB == 4;
+  constexpr int kPatFloats = BQ ? 32 : 3 * kPatchArea;  // floats per feature slot in one patch array set
   constexpr bool WIN = !SS;  // per-feature cp.async windows of the current image exist in this instantiation
   constexpr bool XG = (CS == 1) && !SS;  // multi-GPU feature split (svo_b200_sia_split_*) compiled in
   constexpr size_t kCtlBytes = ((sizeof(SH) + 15) & ~size_t(15)) + (UP ? ((sizeof(UPT) + 15) & ~size_t(15)) : 0);
@@ -607,11 +617,11 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
   const int n_lvl_bufs = UP ? (P.max_level - P.min_level + 1) : 1;  // patch array sets (one per level when UP)
   float* const pat_base = reinterpret_cast<float*>(smem_raw + kCtlBytes);
   // set li (0 = coarsest level) : [16][S] f32 reference patch, then [16][S] float2 gradients
-  auto pat_ref_of = [&](int li) -> float* { return pat_base + (size_t)li * 3 * kPatchArea * SA; };
+  auto pat_ref_of = [&](int li) -> float* { return pat_base + (size_t)li * kPatFloats * SA; };
   auto pat_dxy_of = [&](int li) -> float2* { return reinterpret_cast<float2*>(pat_ref_of(li) + kPatchArea * SA); };
   float* pat_ref = pat_ref_of(0);
   float2* pat_dxy = pat_dxy_of(0);
-  double* const st_xyz = reinterpret_cast<double*>(pat_base + (size_t)n_lvl_bufs * 3 * kPatchArea * SA);  // SS: [3][SA] xyz_ref
+  double* const st_xyz = reinterpret_cast<double*>(pat_base + (size_t)n_lvl_bufs * kPatFloats * SA);  // SS: [3][SA] xyz_ref
   uint8_t* stage = reinterpret_cast<uint8_t*>(st_xyz + (SS ? 3 * SA : 0));  // 16-byte aligned
   uint4* win = reinterpret_cast<uint4*>(stage);                                                      // [kWinRows][S] 16-byte window rows
 
@@ -674,7 +684,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
   double fx_[FPT], fy_[FPT], fz_[FPT], fzi_[FPT];
   double fxs[FPT], fys[FPT], fzs[FPT];  // SS: copies that go to shared memory once the staged blob has been consumed
   int wx_[FPT], wy_[FPT];  // origin of the feature's current-image window (kModeWindow)
-  unsigned hp_mask = 0, vis_mask = 0, in_mask = 0;
+  unsigned hp_mask = 0, vis_mask = 0, in_mask = 0, stale_mask = 0;
 #pragma unroll
   for (int k = 0; k < FPT; ++k) {
     const int i = tid + k * T;
@@ -824,6 +834,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
 #pragma unroll(SS ? 1 : FPT)
     for (int k = 0; k < FPT; ++k) {
       m_sxx[k] = m_sxy[k] = m_syy[k] = m_cnt[k] = 0.0;
+      stale_mask &= ~(1u << k);
       const int slot = tid + k * T;
       // px is re-read from the pair's blob in global memory (L2) once per level instead of living in registers
       const double2 pxy = slot < n_loc ? __ldg(reinterpret_cast<const double2*>(job.blob) + fbase + slot) : make_double2(-1e6, -1e6);
@@ -867,6 +878,10 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           load_row(r + 1, pr1);
 #pragma unroll
           for (int c = 0; c < 6; ++c) b2[c] = bilin(wtl, wtr, wbl, wbr, pr0[c], pr0[c + 1], pr1[c], pr1[c + 1]);
+          if constexpr (BQ) {  // b2 is row r of Bq: cache it (corner columns of rows 0 and 5 are never used)
+#pragma unroll
+            for (int c = (r == 0 || r == 5) ? 1 : 0; c < ((r == 0 || r == 5) ? 5 : 6); ++c) pr[bq_idx(r, c) * SA + slot] = b2[c];
+          }
           if (r >= 2) {  // rows b0 (= Bq[y]), b1 (= Bq[y+1]), b2 (= Bq[y+2]) with y = r-2 are complete
             const int y = r - 2;
 #pragma unroll
@@ -875,8 +890,10 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
               const float val = b1[x + 1];
               const float dx = __fmul_rn(0.5f, __fsub_rn(b1[x + 2], b1[x]));
               const float dy = __fmul_rn(0.5f, __fsub_rn(b2[x + 1], b0[x + 1]));
-              pr[p * SA + slot] = val;
-              pd[p * SA + slot] = make_float2(dx, dy);
+              if constexpr (!BQ) {
+                pr[p * SA + slot] = val;
+                pd[p * SA + slot] = make_float2(dx, dy);
+              }
               sxx = fma((double)dx, (double)dx, sxx);
               sxy = fma((double)dx, (double)dy, sxy);
               syy = fma((double)dy, (double)dy, syy);
@@ -892,10 +909,14 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         // visible from a coarser level but failing here: the reference would keep the stale patch
         // and a zeroed Jacobian (jacobian_cache_.setZero() per level, :64).  Unreachable for
         // dyadic pyramids but kept bit-faithful.
+        if constexpr (BQ) {
+          stale_mask |= 1u << k;  // the cache keeps the previous level's Bq: stale values, gradients scaled by zero
+        } else {
 #pragma unroll
-        for (int p = 0; p < kPatchArea; ++p) pd[p * SA + slot] = make_float2(0.f, 0.f);
-        if (pr_stale)  // per-level arrays (upfront variant): the stale patch is the previous level's
-          for (int p = 0; p < kPatchArea; ++p) pr[p * SA + slot] = pr_stale[p * SA + slot];
+          for (int p = 0; p < kPatchArea; ++p) pd[p * SA + slot] = make_float2(0.f, 0.f);
+          if (pr_stale)  // per-level arrays (upfront variant): the stale patch is the previous level's
+            for (int p = 0; p < kPatchArea; ++p) pr[p * SA + slot] = pr_stale[p * SA + slot];
+        }
         m_cnt[k] = 1.0;
       }
     }
@@ -1084,23 +1105,51 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
         float q0[5], q1[5];
         q0[0] = byte_to_float<0>(lo[0]); q0[1] = byte_to_float<1>(lo[0]); q0[2] = byte_to_float<2>(lo[0]);
         q0[3] = byte_to_float<3>(lo[0]); q0[4] = byte_to_float<0>(hi[0]);
+        // BQ: three rows of the cached bilinear reference array rotate through registers (row yy cols 1..4, rows yy+1 and yy+2)
+        const float ghalf = ((stale_mask >> k) & 1u) ? 0.f : 0.5f;
+        float bprev[4], bmid[6], bnext[6];
+        if constexpr (BQ) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) bprev[c] = pat_ref[bq_idx(0, c + 1) * SA + slot];
+#pragma unroll
+          for (int c = 0; c < 6; ++c) bmid[c] = pat_ref[bq_idx(1, c) * SA + slot];
+        }
 #pragma unroll
         for (int yy = 0; yy < 4; ++yy) {
           q1[0] = byte_to_float<0>(lo[yy + 1]); q1[1] = byte_to_float<1>(lo[yy + 1]); q1[2] = byte_to_float<2>(lo[yy + 1]);
           q1[3] = byte_to_float<3>(lo[yy + 1]); q1[4] = byte_to_float<0>(hi[yy + 1]);
+          if constexpr (BQ) {
+#pragma unroll
+            for (int c = (yy == 3) ? 1 : 0; c < ((yy == 3) ? 5 : 6); ++c) bnext[c] = pat_ref[bq_idx(yy + 2, c) * SA + slot];
+          }
 #pragma unroll
           for (int xx = 0; xx < 4; ++xx) {
             const int p = yy * 4 + xx;
             const float I = bilin(wtl, wtr, wbl, wbr, q0[xx], q0[xx + 1], q1[xx], q1[xx + 1]);
-            const float res = __fsub_rn(I, pat_ref[p * SA + slot]);
-            const float2 gr = pat_dxy[p * SA + slot];
+            float val, dx, dy;
+            if constexpr (BQ) {
+              val = bmid[xx + 1];
+              dx = __fmul_rn(ghalf, __fsub_rn(bmid[xx + 2], bmid[xx]));          // as precomputeReferencePatches forms them (:121-126)
+              dy = __fmul_rn(ghalf, __fsub_rn(bnext[xx + 1], bprev[xx]));
+            } else {
+              val = pat_ref[p * SA + slot];
+              const float2 gr = pat_dxy[p * SA + slot];
+              dx = gr.x; dy = gr.y;
+            }
+            const float res = __fsub_rn(I, val);
             c2 = fmaf(res, res, c2);  // chi2 += res*res*weight, weight == 1 (:222); order differs from the serial sum anyway
-            gx = fmaf(gr.x, res, gx);
-            gy = fmaf(gr.y, res, gy);
+            gx = fmaf(dx, res, gx);
+            gy = fmaf(dy, res, gy);
             if (EVAL) P.residuals_out[(size_t)(fbase + slot) * kPatchArea + p] = res;
           }
 #pragma unroll
           for (int c = 0; c < 5; ++c) q0[c] = q1[c];
+          if constexpr (BQ) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) bprev[c] = bmid[c + 1];
+#pragma unroll
+            for (int c = 0; c < 6; ++c) bmid[c] = bnext[c];
+          }
         }
         const double zi = feat_zi(k, z), X = x * zi, Y = y * zi, dgx = (double)gx, dgy = (double)gy;
         acc[0] = fma(-zi, dgx, acc[0]);
@@ -1178,7 +1227,15 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
           const int slot = tid + k * T;
 #pragma unroll
           for (int p = 0; p < kPatchArea; ++p) {
-            const float2 gr = pat_dxy[p * SA + slot];
+            float2 gr;
+            if constexpr (BQ) {
+              const int yy = p >> 2, xx = p & 3;
+              const float gh = ((stale_mask >> k) & 1u) ? 0.f : 0.5f;
+              gr.x = __fmul_rn(gh, __fsub_rn(pat_ref[bq_idx(yy + 1, xx + 2) * SA + slot], pat_ref[bq_idx(yy + 1, xx) * SA + slot]));
+              gr.y = __fmul_rn(gh, __fsub_rn(pat_ref[bq_idx(yy + 2, xx + 1) * SA + slot], pat_ref[bq_idx(yy, xx + 1) * SA + slot]));
+            } else {
+              gr = pat_dxy[p * SA + slot];
+            }
             const double dx = (double)gr.x, dy = (double)gr.y;
             q_sxx[k] = fma(dx, dx, q_sxx[k]);
             q_sxy[k] = fma(dx, dy, q_sxy[k]);
@@ -1295,7 +1352,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
               for (int p = 0; p < kPatchArea; ++p)
                 P.residuals_out[(size_t)(fbase + i) * kPatchArea + p] = __int_as_float(0x7fc00000);
             for (int p = 0; p < kPatchArea; ++p)
-              P.ref_patch_out[(size_t)(fbase + i) * kPatchArea + p] = pat_ref[p * SA + i];
+              P.ref_patch_out[(size_t)(fbase + i) * kPatchArea + p] = BQ ? pat_ref[bq_idx((p >> 2) + 1, (p & 3) + 1) * SA + i] : pat_ref[p * SA + i];
           }
         }
         break;
@@ -1356,6 +1413,7 @@ struct SiaBatchState {
   size_t o_T = 0, o_H = 0, o_vis = 0, o_stats = 0, out_bytes = 0;
   int threads = 0, fpt = 1, cluster = 1;
   bool upfront = false;  // cluster geometry with all levels prepared before the first iteration (SiaUpT)
+  bool bq = false;       // throughput geometry with the 32-value patch cache, four CTAs per SM
   size_t smem = 0;
   bool staged = false;
 };
@@ -1391,6 +1449,7 @@ static int g_sia_prefetch = 1;    // SVO_B200_SIA_PREFETCH=0: no bulk L2 prefetc
                                   // uncoalesced requests cost more L1 time than the DRAM latency they hide.)
 static int g_sia_cluster = -1;    // SVO_B200_SIA_CLUSTER: force the CTAs per pair (1, 2, 4, 8); -1 = by batch size
 static int g_sia_upfront = 1;     // SVO_B200_SIA_UPFRONT=0: the cluster geometry prepares each level when it reaches it (round-2a behaviour)
+static int g_sia_bq = 0;          // SVO_B200_SIA_BQ=1: throughput geometry with the 128-byte patch cache at four CTAs per SM
 static int g_sia_async = 1;       // SVO_B200_SIA_ASYNC=0: the upfront variant exchanges its sums through barrier.cluster like the others
 static int g_sia_plain = 1;       // SVO_B200_SIA_PLAIN=0: the undistorted pinhole runs the general-camera instantiation too
 static int g_sia_fpt2 = 1;        // SVO_B200_SIA_FPT2: <= 320 features per CTA as 160 threads x 2 features: 1 = three CTAs per SM (default,
@@ -1409,6 +1468,7 @@ static void read_env_once() {
   if (const char* e = getenv("SVO_B200_SIA_PLAIN")) g_sia_plain = atoi(e) != 0;
   if (const char* e = getenv("SVO_B200_SIA_UPFRONT")) g_sia_upfront = atoi(e) != 0;
   if (const char* e = getenv("SVO_B200_SIA_ASYNC")) g_sia_async = atoi(e) != 0;
+  if (const char* e = getenv("SVO_B200_SIA_BQ")) g_sia_bq = atoi(e) != 0;
 }
 
 // Launch geometry for a batch of B pairs with at most max_feat features each.
@@ -1431,7 +1491,7 @@ static size_t sia_upfront_bytes(int cluster) {
 }
 
 static int pick_launch(svo_b200_ctx* ctx, int B, int max_feat, int n_lvl, int& threads, int& fpt, int& cluster, bool& upfront,
-                       int& stage_cap, size_t& smem) {
+                       bool& bq, int& stage_cap, size_t& smem) {
   read_env_once();
   if (max_feat > 1024)
     return set_err(ctx, SVO_B200_ELIMIT, "sparse_img_align: %d features per pair > 1024 (shared-memory patch cache)", max_feat);
@@ -1449,7 +1509,9 @@ static int pick_launch(svo_b200_ctx* ctx, int B, int max_feat, int n_lvl, int& t
   if (want < 0) want = (B * 4 <= ctx->sm_count) ? 4 : 1;
   // full batches (more pairs than 2 per SM): 160 threads x 2 features, three CTAs per SM; in between, 320 x 1 with windows
   int fpt2 = ctx->sia_fpt > 0 ? (ctx->sia_fpt == 2 ? 1 : 0) : g_sia_fpt2;
-  if (ctx->sia_fpt == 0 && B <= 2 * ctx->sm_count) fpt2 = 0;
+  // (round 2b: with its state in shared memory and its loops rolled the 160 x 2 geometry also wins below two CTAs per SM --
+  // 148 pairs 117 vs 131 us, 296 pairs 145 vs 165 us, 444 pairs 178 vs 304 us, profiles/r02l -- so the 320 x 1 geometry is
+  // left for > 304 features per pair, the multi-GPU split and explicit requests)
   if (ctx->xg_connected) fpt2 = 0;
   if (want > 1 && max_feat <= 96 * want && (want == 2 || want == 4 || want == 8)) cluster = want;
   if (cluster > 1) {
@@ -1464,8 +1526,9 @@ static int pick_launch(svo_b200_ctx* ctx, int B, int max_feat, int n_lvl, int& t
     if (fpt2 && max_feat <= 304) { fpt = 2; threads = 160; }  // its shared arrays are allocated for 304 slots (kernel: SA)
   }
   const bool throughput_geom = cluster == 1 && fpt == 2 && threads == 160;
+  bq = throughput_geom && g_sia_bq && fpt2 != 2;
   const int slots = throughput_geom ? 304 : threads * fpt;
-  size_t base = ((sia_shared_bytes(threads, cluster) + 15) & ~size_t(15)) + (size_t)3 * kPatchArea * slots * sizeof(float);
+  size_t base = ((sia_shared_bytes(threads, cluster) + 15) & ~size_t(15)) + (size_t)(bq ? 32 : 3 * kPatchArea) * slots * sizeof(float);
   if (throughput_geom) base += (size_t)3 * slots * sizeof(double);  // xyz_ref of every feature (kernel: st_xyz)
   // cluster geometry with every CTA alone on its SM: one patch array set per level, everything pose independent prepared
   // before the first iteration (the launch asks for the 4-CTA instantiation; 2 and 8 keep the per-level flow)
@@ -1480,7 +1543,7 @@ static int pick_launch(svo_b200_ctx* ctx, int B, int max_feat, int n_lvl, int& t
   }
   // shared memory one CTA may use so that the intended number of CTAs stays resident per SM (228 KB per SM, 1 KB
   // reserved per CTA)
-  const int resident = upfront ? 1 : cluster > 1 ? 2 : (threads == 160 ? (fpt2 == 2 ? 2 : 3) : threads <= 384 ? 2 : 1);
+  const int resident = upfront ? 1 : cluster > 1 ? 2 : (threads == 160 ? (bq ? 4 : fpt2 == 2 ? 2 : 3) : threads <= 384 ? 2 : 1);
   size_t budget = (size_t)ctx->max_smem_optin;
   const size_t per_cta = (size_t)(228 * 1024) / resident - 1024;
   if (per_cta < budget) budget = per_cta;
@@ -1498,7 +1561,7 @@ static int pick_launch(svo_b200_ctx* ctx, int B, int max_feat, int n_lvl, int& t
 }
 
 template <bool EVAL>
-static int launch_sia(svo_b200_ctx* ctx, const SiaParams& P, int B, int threads, int fpt, int cluster, bool upfront, size_t smem) {
+static int launch_sia(svo_b200_ctx* ctx, const SiaParams& P, int B, int threads, int fpt, int cluster, bool upfront, bool bq, size_t smem) {
   auto go = [&](auto kern) -> int {
     SVO_CUDA_CHECK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // ask for the full shared-memory carveout so that two CTAs of ~95 KB fit one SM
@@ -1540,6 +1603,7 @@ static int launch_sia(svo_b200_ctx* ctx, const SiaParams& P, int B, int threads,
     if (threads <= 384) return go(sia_kernel<1, EVAL, 384, 2, 1, true, false>);
     return go(sia_kernel<1, EVAL, 512, 1, 1, true, false>);
   }
+  if (threads == 160 && bq) return plain ? go(sia_kernel<2, EVAL, 160, 4, 1, EVAL, false>) : go(sia_kernel<2, EVAL, 160, 4, 1, true, false>);
   if (threads == 160) return plain ? go(sia_kernel<2, EVAL, 160, 3, 1, EVAL, false>) : go(sia_kernel<2, EVAL, 160, 3, 1, true, false>);
   return go(sia_kernel<2, EVAL, 512, 1, 1, true, false>);
 }
@@ -1682,8 +1746,8 @@ int svo_b200_sia_batch_stage(svo_b200_ctx* ctx, int B, const svo_b200_frame* con
   int rc = fill_common(ctx, st.P, ref[0], cam, opt);
   if (rc) return rc;
   int stage_cap = 0;
-  rc = pick_launch(ctx, B, st.max_feat, opt->max_level - opt->min_level + 1, st.threads, st.fpt, st.cluster, st.upfront, stage_cap,
-                   st.smem);
+  rc = pick_launch(ctx, B, st.max_feat, opt->max_level - opt->min_level + 1, st.threads, st.fpt, st.cluster, st.upfront, st.bq,
+                   stage_cap, st.smem);
   if (rc) return rc;
   st.P.stage_cap = stage_cap;
   st.P.slots = st.threads * st.fpt;
@@ -1742,7 +1806,7 @@ int svo_b200_sia_batch_run(svo_b200_ctx* ctx) {
   if (!ctx || !ctx->sia || !ctx->sia->staged) return set_err(ctx, SVO_B200_EINVAL, "sia_batch_run: nothing staged");
   cudaSetDevice(ctx->device);
   SiaBatchState& st = *ctx->sia;
-  return launch_sia<false>(ctx, st.P, st.B, st.threads, st.fpt, st.cluster, st.upfront, st.smem);
+  return launch_sia<false>(ctx, st.P, st.B, st.threads, st.fpt, st.cluster, st.upfront, st.bq, st.smem);
 }
 
 int svo_b200_sia_batch_fetch(svo_b200_ctx* ctx, double* T_out, uint8_t* visible_out, double* H_out,
@@ -1845,7 +1909,7 @@ int svo_b200_sparse_residuals(svo_b200_ctx* ctx, const svo_b200_frame* ref, cons
   st.P.Jres_out = reinterpret_cast<double*>(ds + o_j);
   st.P.chi2_out = reinterpret_cast<double*>(ds + o_c);
   st.P.n_meas_out = reinterpret_cast<long long*>(ds + o_n);
-  if ((rc = launch_sia<true>(ctx, st.P, 1, st.threads, st.fpt, st.cluster, false, st.smem))) return rc;
+  if ((rc = launch_sia<true>(ctx, st.P, 1, st.threads, st.fpt, st.cluster, false, st.bq, st.smem))) return rc;
   double Tdummy[12];
   if ((rc = svo_b200_sia_batch_fetch(ctx, Tdummy, visible_io, H_out, nullptr))) return rc;
   if (ref_patch_out) SVO_CUDA_CHECK(ctx, cudaMemcpy(ref_patch_out, ds + o_rp, sizeof(float) * 16 * (size_t)N, cudaMemcpyDeviceToHost));
