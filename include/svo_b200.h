@@ -173,7 +173,8 @@ int svo_b200_sia_batch_fetch(svo_b200_ctx* ctx, double* T_out /*B*12*/, uint8_t*
 /* Launch geometry of the alignment kernel (tuning / tests; results agree to rounding between geometries).
  *   ctas_per_pair: -1 = automatic (a 4-CTA thread-block cluster per pair while 4*B <= #SMs, i.e. live streams and
  *                  small batches; one CTA per pair otherwise), or 1, 2, 4, 8 (clusters need <= 96*ctas features per pair).
- *   features_per_thread: 0 = automatic, 1, 2 (one CTA per pair only). */
+ *   features_per_thread: 0 = automatic (2 whenever one CTA per pair is used and every pair has <= 304 features), 1, or 2
+ *                  (one CTA per pair only; pairs with more than 304 features run with 1). */
 int svo_b200_sia_config(svo_b200_ctx* ctx, int ctas_per_pair, int features_per_thread);
 /* Small batches in the 4-CTA cluster geometry (every CTA alone on an SM) prepare the reference patches, H and its
  * factorisation of ALL pyramid levels before the first Gauss-Newton iteration ("upfront"; none of it depends on the pose,
