@@ -145,7 +145,6 @@ struct SiaSharedT {
   Solver6 sol_tot;                              // factorisation of Htot
   SiaState st[2];                               // double-buffered like `part`
   int h_is_tot, n_iters, sum_vis, sum_in, n_in_last, n_trace;  // thread 0 of CTA rank 0 only
-  unsigned mbar_phase;
   unsigned xg_seq;     // feature split over GPUs: exchanges completed (warp 0) ...
   unsigned xg_failed;  // ... and "an exchange timed out" (must directly follow xg_seq)
   alignas(16) double pub[12];  // CS == 1: the pose (R row-major, t) warp 0 publishes after its Gauss-Newton tail
@@ -648,7 +647,6 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
     mbar_init(&s.xbar[0], 1);
     mbar_init(&s.xbar[1], 1);
     fence_mbar_init();
-    s.mbar_phase = 0;  // use k of the barrier completes phase parity k&1; the blob copy is use 0
     // ---- TMA: the packed feature records of this CTA's features, four bulk copies (px, f, pos, has_point
     //      sections of the pair's blob) into the (idle) patch arrays -- issued first, everything else this thread
     //      initialises runs in the shadow of that copy
@@ -930,6 +928,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
   const int lvl_hi = EVAL ? P.eval_level : P.max_level;
   const int lvl_lo = EVAL ? P.eval_level : P.min_level;
   unsigned vis_levels = 0;  // UP: bit li = this thread's feature is visible at level lvl_hi - li (set-only across levels)
+  unsigned img_phase = 0;   // parity of the most recent use of s.mbar (the blob copy of the prologue was use 0)
   if constexpr (UP) {
     SIA_DBG(long long tu0 = 0;)
       SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) tu0 = clock64();)
@@ -983,8 +982,12 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
     int mode = kModeGlobal;
     if (img_bytes + 16u <= (uint32_t)P.stage_cap) mode = kModeImage;
     else if (WIN && P.use_windows && (W & 7) == 0 && kWinBytes * SA <= P.stage_cap) mode = kModeWindow;
+    // Phase parity of this use of s.mbar, kept by every thread in a register (use k completes parity k & 1; the blob copy was
+    // use 0).  NOT read from shared memory: in the upfront variant no barrier separates thread 0's update from the other
+    // warps' wait, and a stale parity lets them through before the image has landed (found by running the tests under
+    // compute-sanitizer, whose timing exposed it; `mode` is the same in all threads).
+    if (mode == kModeImage) img_phase ^= 1u;
     if (mode == kModeImage && tid == 0) {
-      s.mbar_phase ^= 1u;
       fence_proxy_async();
       mbar_expect_tx(&s.mbar, img_bytes);
       tma_bulk_g2s(stage, cur_img, img_bytes, &s.mbar);
@@ -1040,7 +1043,7 @@ __global__ void __launch_bounds__(MAXT, MINB) sia_kernel(const SiaParams P) {
       if (leader) s.sum_vis += (int)up.sums[li][21];
       SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { tq1 = tq2 = clock64(); s.tk[7] += tq1 - tq0; })
     }
-    if (mode == kModeImage) mbar_wait(&s.mbar, s.mbar_phase);
+    if (mode == kModeImage) mbar_wait(&s.mbar, img_phase);
     if (mode == kModeWindow) cp_async_wait_all();  // each thread reads only the window it copied itself
       SIA_DBG(if ((SVO_SIA_DEBUG && P.debug) && tid == 0) { s.tk[0] += clock64() - tq0; s.tkx[1] += clock64() - tq2; })
 
