@@ -538,6 +538,9 @@ enum { kModeGlobal = 0, kModeImage = 1, kModeWindow = 2 };
 
 // slot of Bq[r][c] in the 32-value patch cache (BQ): row 0 cols 1..4 -> 0..3, rows 1..4 cols 0..5 -> 4..27, row 5 cols 1..4 -> 28..31
 __host__ __device__ constexpr int bq_idx(int r, int c) { return r == 0 ? c - 1 : r == 5 ? 28 + c - 1 : 4 + (r - 1) * 6 + c; }
+static_assert(bq_idx(0, 1) == 0 && bq_idx(0, 4) == 3 && bq_idx(1, 0) == 4 && bq_idx(1, 5) == 9 && bq_idx(4, 5) == 27 &&
+                  bq_idx(5, 1) == 28 && bq_idx(5, 4) == 31,
+              "the 32 used entries of the 6x6 bilinear reference array map onto 0..31 without gaps");
 
 // xyz_cur = T_cur_from_ref * xyz_ref.  One CTA per pair (CS == 1): the pose is read from shared memory (s.pub, published by
 // warp 0's Gauss-Newton tail) at the point of use -- six 128-bit shared loads per feature instead of 24 registers that stay

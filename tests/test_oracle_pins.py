@@ -270,6 +270,55 @@ def test_oracle_residual_pass_equals_reference_source_compiled_here(oracle, leve
     assert np.allclose(r["Jres"], o["Jres"], rtol=1e-9, atol=1e-6)
 
 
+@pytest.mark.parametrize("level", [0, 2, 4])
+def test_oracle_residual_pass_with_patches_outside_the_image_equals_reference(oracle, level):
+    """computeResiduals' per-patch border test (sparse_img_align.cpp:190): features right up to the image border and a large
+    motion, so that visible patches project outside the current image and are skipped -- the reference's n_meas_, the
+    per-pixel |res| of the patches that stay, chi2, H_ and Jres_ vs the oracle."""
+    _need_ref(oracle)
+    rng = np.random.default_rng(5)
+    cam = synth.camera_for(640, 480)
+    plane, tex = synth.Plane.tilted(), synth.make_texture(7)
+    T_ref_w = synth.base_pose()
+    xi = np.array([0.07, -0.06, 0.05, np.deg2rad(1.2), np.deg2rad(-1.4), np.deg2rad(1.0)])
+    T = synth.se3_exp(xi)
+    ref_pyr = synth.build_pyramid(synth.render(cam, T_ref_w, plane, tex), 5)
+    cur_pyr = synth.build_pyramid(synth.render(cam, synth.se3_mul(T, T_ref_w), plane, tex), 5)
+    px = synth.jittered_features(rng, cam, 300, margin=4.0)
+    f = cam.cam2world(px)
+    pos = synth.intersect(plane, T_ref_w, f)
+    hp = (rng.uniform(size=300) > 0.05).astype(np.uint8)
+    ref_pos = synth.se3_inv(T_ref_w)[:, 3].copy()
+    r = oracle.ref_sparse_residuals(ref_pyr[0], cur_pyr[0], 5, cam, T_ref_w, synth.se3_mul(T, T_ref_w), px, f, pos, hp, level)
+    o = oracle.sparse_residuals(ref_pyr[level], cur_pyr[level], level, cam, T, px, f, pos, hp, ref_pos)
+    v, m = o["visible"].astype(bool), o["in_image"].astype(bool)
+    assert np.array_equal(r["visible"], o["visible"])
+    assert 0 < m.sum() < v.sum()  # the case really has visible patches that leave the current image
+    assert r["n_meas"] == o["n_meas"] == 16 * int(m.sum())
+    assert np.array_equal(r["ref_patch"][v], o["ref_patch"][v])
+    same = np.abs(o["residuals"][m]) == r["abs_res"]
+    assert same.mean() >= 0.99 and np.max(np.abs(np.abs(o["residuals"][m]) - r["abs_res"])) <= 1e-4
+    assert abs(r["chi2"] - o["chi2"]) <= 1e-6 * abs(o["chi2"])
+    assert np.allclose(r["H"], o["H"], rtol=1e-12, atol=1e-9 * np.abs(o["H"]).max())
+    assert np.allclose(r["Jres"], o["Jres"], rtol=1e-9, atol=1e-5)
+
+
+@pytest.mark.parametrize("n,outliers,noise,n_iter", [(8, 0.0, 0.5, 10), (40, 0.3, 1.0, 10), (1000, 0.1, 2.0, 3), (250, 0.03, 1.0, 1)])
+def test_oracle_pose_optimizer_edge_cases_equal_reference_source_compiled_here(oracle, n, outliers, noise, n_iter):
+    """pose_optimizer::optimizeGaussNewton of the compiled reference at the corners of its behaviour: a handful of
+    observations, a third of them gross outliers (Tukey weights, the culling of :129-145), few iterations (no convergence,
+    the fixed scale of iteration 5 never reached)."""
+    _need_ref(oracle)
+    c = synth.make_pose_opt_case(90 + n, n=n, width=752, height=480, px_noise=noise, outlier_frac=outliers)
+    r = oracle.ref_pose_optimize(2.0, n_iter, c["cam"], c["T_init"], c["f"], c["pos"], c["level"], c["has_point"])
+    o = oracle.pose_optimize(2.0, n_iter, c["cam"].fx, c["T_init"], c["f"], c["pos"], c["level"], c["has_point"])
+    assert np.array_equal(r["has_point"], o["has_point"])
+    assert r["num_obs"] == o["num_obs"]
+    assert np.allclose(r["T"], o["T"], rtol=0, atol=1e-10)
+    for k in ("estimated_scale", "error_init", "error_final"):
+        assert np.isclose(r[k], o[k], rtol=1e-9), k
+
+
 def test_oracle_pose_optimizer_equals_reference_source_compiled_here(oracle):
     _need_ref(oracle)
     for seed in (3, 4):
