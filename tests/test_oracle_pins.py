@@ -237,6 +237,36 @@ def test_oracle_sparse_img_align_equals_reference_source_compiled_here(oracle, s
     assert np.array_equal(r["ref_patch"][v], q["ref_patch"][v])
 
 
+@pytest.mark.parametrize("case", ["two_iterations", "five_features", "bad_initial_pose", "no_points"])
+def test_oracle_sparse_img_align_corner_cases_equal_reference_source_compiled_here(oracle, case):
+    """svo::SparseImgAlign::run of the compiled reference at the corners of the Gauss-Newton driver: the iteration limit
+    (no convergence at any level), a handful of features (H barely determined), an initial pose far enough off that updates get
+    rejected (chi2 increases -> roll-back, :44-52 of the stand-in NLLSSolver), and a frame whose features have no 3D point."""
+    _need_ref(oracle)
+    n_feat = 5 if case == "five_features" else 200
+    p = synth.make_frame_pair(77, n_feat=n_feat, trans=0.05, rot_deg=1.0)
+    n_iter = 2 if case == "two_iterations" else 30
+    T0 = synth.se3_identity()
+    if case == "bad_initial_pose":
+        T0 = synth.se3_exp(np.array([0.15, -0.12, 0.1, 0.03, -0.025, 0.02]))
+    if case == "no_points":
+        p["has_point"][:] = 0
+    r = oracle.ref_sparse_img_align(p["ref_pyr"][0], p["cur_pyr"][0], p["n_levels"], p["cam"], p["T_ref_w"],
+                                    synth.se3_mul(T0, p["T_ref_w"]), p["px"], p["f"], p["pos"], p["has_point"], 4, 0, n_iter)
+    o = oracle.sparse_img_align(p["ref_pyr"], p["cur_pyr"], p["cam"], T0, p["px"], p["f"], p["pos"], p["has_point"],
+                                p["ref_pos"], 4, 0, n_iter)
+    assert r["n_tracked"] == o["n_tracked"]
+    assert np.array_equal(r["visible"], o["visible"])
+    # T_cur_from_ref is re-formed by the reference from the two world poses: 1e-9 on the final pose, as in the main pin
+    assert np.allclose(r["T_cur_w"], synth.se3_mul(o["T"], p["T_ref_w"]), rtol=0, atol=1e-8 if case == "bad_initial_pose" else 1e-9)
+    if case == "two_iterations":
+        assert 5 < len(o["trace"]) <= 10 and max(t["iter"] for t in o["trace"]) == 1  # the iteration limit ended the levels
+    if case == "bad_initial_pose":
+        assert any(not t["accepted"] for t in o["trace"])  # the roll-back path really ran
+    if case == "no_points":
+        assert o["n_tracked"] == 0 and np.allclose(o["T"], T0)
+
+
 @pytest.mark.parametrize("level", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("camera", ["pinhole", "atan", "pinhole_radtan"])
 def test_oracle_residual_pass_equals_reference_source_compiled_here(oracle, level, camera):
