@@ -300,6 +300,30 @@ def test_oracle_residual_pass_equals_reference_source_compiled_here(oracle, leve
     assert np.allclose(r["Jres"], o["Jres"], rtol=1e-9, atol=1e-6)
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_oracle_residual_pass_random_poses_equal_reference(oracle, seed):
+    """Randomised version of the residual pin: random scene seed, level, pose perturbation (up to 4 cm / 1 degree) and
+    missing points; every quantity computeResiduals leaves behind must match (counts and patch cache exactly, per-pixel
+    residual magnitudes bit for bit but for the rare coordinate on a rounding boundary)."""
+    _need_ref(oracle)
+    rng = np.random.default_rng(1000 + seed)
+    p = synth.make_frame_pair(300 + seed, n_feat=int(rng.integers(40, 301)), n_levels=5)
+    p["has_point"][rng.uniform(size=len(p["has_point"])) < 0.1] = 0
+    level = int(rng.integers(0, 5))
+    T = synth.se3_exp(np.concatenate([rng.uniform(-0.04, 0.04, 3), np.deg2rad(rng.uniform(-1.0, 1.0, 3))]))
+    r = oracle.ref_sparse_residuals(p["ref_pyr"][0], p["cur_pyr"][0], p["n_levels"], p["cam"], p["T_ref_w"],
+                                    synth.se3_mul(T, p["T_ref_w"]), p["px"], p["f"], p["pos"], p["has_point"], level)
+    o = oracle.sparse_residuals(p["ref_pyr"][level], p["cur_pyr"][level], level, p["cam"], T, p["px"], p["f"], p["pos"],
+                                p["has_point"], p["ref_pos"])
+    v, m = o["visible"].astype(bool), o["in_image"].astype(bool)
+    assert np.array_equal(r["visible"], o["visible"]) and np.array_equal(r["ref_patch"][v], o["ref_patch"][v])
+    assert r["n_meas"] == o["n_meas"] == 16 * int(m.sum()) and m.sum() > 0
+    d = np.abs(np.abs(o["residuals"][m]) - r["abs_res"])
+    assert (d == 0).mean() >= 0.99 and d.max() <= 1e-4
+    assert abs(r["chi2"] - o["chi2"]) <= 1e-6 * abs(o["chi2"])
+    assert np.allclose(r["H"], o["H"], rtol=1e-12, atol=1e-9 * np.abs(o["H"]).max())
+
+
 @pytest.mark.parametrize("level", [0, 2, 4])
 def test_oracle_residual_pass_with_patches_outside_the_image_equals_reference(oracle, level):
     """computeResiduals' per-patch border test (sparse_img_align.cpp:190): features right up to the image border and a large
